@@ -1,0 +1,293 @@
+/*
+ * mamba_tts_b200.h -- C ABI of the B200 (sm_100a) MambaTTSDecoder hot-path library.
+ *
+ * This is the drop-in boundary.  The reference (whcorkran/mamba-TTS-project) reaches all of its SSM
+ * arithmetic through ONE third-party Python call, `Mamba(d_model)` (mamba_decoder.py:4,29,61,63).
+ * Underneath, `mamba_ssm` binds two pybind11 extensions that take `at::Tensor`s
+ * (`selective_scan_cuda.{fwd,bwd}`, `causal_conv1d_cuda.{causal_conv1d_fwd,causal_conv1d_bwd,
+ * causal_conv1d_update}`) plus a Triton kernel (`selective_state_update`).  Every entry point
+ * below replaces one of those bindings with a plain-C call: POD parameter struct of device
+ * pointers / sizes / element strides + a CUDA stream.  No torch types cross this line.
+ *
+ * Rules:
+ *   - the caller owns every buffer (inputs, outputs, saved-for-backward, workspaces); the library
+ *     never allocates, frees or retains a pointer past the call;
+ *   - work is enqueued on `stream`, asynchronously, with no host synchronisation and no allocation,
+ *     so every call is CUDA-graph capturable;
+ *   - return value 0 = success; >0 = MTTS_ERR_* argument error (nothing was launched);
+ *     <0 = -(cudaError_t) reported by the launch.  `mtts_error_string` explains either;
+ *   - in-place mutation happens only where stated (conv_state / ssm_state / accumulate-into grads);
+ *   - there is NO CPU path: without a CUDA device every compute call fails.
+ *
+ * Layout conventions (upstream's): activations are channel-major `(batch, dim, seqlen)` with unit
+ * stride along seqlen; B/C are `(batch, dstate, seqlen)`; A is `(dim, dstate)` fp32 = -exp(A_log);
+ * D, delta_bias, conv weight `(dim, width)` and conv bias are fp32.  "io dtype" is the element type
+ * of the activation tensors of one call (all the same): MTTS_F32 or MTTS_BF16.
+ * All strides are in ELEMENTS.
+ */
+#ifndef MAMBA_TTS_B200_H_
+#define MAMBA_TTS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mtts_stream_t; /* a cudaStream_t */
+
+enum { MTTS_F32 = 0, MTTS_BF16 = 1 };
+
+enum {
+  MTTS_OK = 0,
+  MTTS_ERR_NULL = 1,      /* a required pointer is NULL                         */
+  MTTS_ERR_SHAPE = 2,     /* a dimension is out of the supported range          */
+  MTTS_ERR_DTYPE = 3,     /* unknown io dtype                                   */
+  MTTS_ERR_ALIGN = 4,     /* pointer/stride alignment the kernel cannot handle  */
+  MTTS_ERR_UNSUPPORTED = 5
+};
+
+/* Timesteps between two saved scan states ("checkpoints"): selective_scan_fwd writes the state at
+ * the START of every chunk of this many timesteps; selective_scan_bwd recomputes inside a chunk. */
+#define MTTS_SCAN_CHUNK 256
+#define MTTS_MAX_DSTATE 256
+#define MTTS_MAX_CONV_WIDTH 4
+
+const char* mtts_error_string(int code);
+int mtts_abi_version(void);
+/* Compiled-for architecture, e.g. 100 for sm_100a. */
+int mtts_target_sm(void);
+/* sizeof() of the n-th parameter struct below (declaration order, from 0); -1 past the end.
+ * Lets a foreign binding verify its mirror of the layout when it loads the library. */
+int mtts_sizeof_params(int which);
+
+/* ---------------------------------------------------------------------------------------------
+ * causal_conv1d_fwd  -- replaces causal_conv1d_cuda.causal_conv1d_fwd (called by
+ * mamba_ssm Mamba.forward, reached from mamba_decoder.py:61).
+ *   out[b,d,t] = act( bias[d] + sum_{k<width} weight[d,k] * x[b,d,t-(width-1)+k] ),  x[t<0] taken
+ *   from initial_states[b,d,(width-1)+t] or 0.  act = SiLU when silu != 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, seqlen, width; /* width in 2..4 */
+  int32_t io_dtype;
+  int32_t silu;
+  const void* x;
+  int64_t x_batch_stride, x_dim_stride;
+  const float* weight; /* (dim, width) contiguous */
+  const float* bias;   /* (dim) or NULL */
+  const void* initial_states; /* (batch, dim, width-1) io dtype, or NULL */
+  int64_t init_batch_stride, init_dim_stride;
+  void* out;
+  int64_t out_batch_stride, out_dim_stride;
+} mtts_conv1d_fwd_params;
+int mtts_causal_conv1d_fwd(const mtts_conv1d_fwd_params* p, mtts_stream_t stream);
+
+/* causal_conv1d_bwd -- replaces causal_conv1d_cuda.causal_conv1d_bwd.
+ * dweight (dim,width) and dbias (dim) are fp32 and ACCUMULATED INTO (caller zero-fills). */
+typedef struct {
+  int32_t batch, dim, seqlen, width;
+  int32_t io_dtype;
+  int32_t silu;
+  const void* x;
+  int64_t x_batch_stride, x_dim_stride;
+  const float* weight;
+  const float* bias;
+  const void* initial_states;
+  int64_t init_batch_stride, init_dim_stride;
+  const void* dout;
+  int64_t dout_batch_stride, dout_dim_stride;
+  void* dx;
+  int64_t dx_batch_stride, dx_dim_stride;
+  float* dweight;
+  float* dbias; /* may be NULL */
+} mtts_conv1d_bwd_params;
+int mtts_causal_conv1d_bwd(const mtts_conv1d_bwd_params* p, mtts_stream_t stream);
+
+/* causal_conv1d_update -- replaces causal_conv1d_cuda.causal_conv1d_update (Mamba.step).
+ * conv_state (batch, dim, width) io dtype is rolled left by one IN PLACE, x written last. */
+typedef struct {
+  int32_t batch, dim, width;
+  int32_t io_dtype;
+  int32_t silu;
+  const void* x; /* (batch, dim) */
+  int64_t x_batch_stride;
+  void* conv_state; /* contiguous (batch, dim, width) */
+  const float* weight;
+  const float* bias;
+  void* out; /* (batch, dim) */
+  int64_t out_batch_stride;
+} mtts_conv1d_update_params;
+int mtts_causal_conv1d_update(const mtts_conv1d_update_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * selective_scan_fwd -- replaces selective_scan_cuda.fwd (mamba_ssm selective_scan_fn /
+ * mamba_inner_fn, reached from mamba_decoder.py:61).
+ *   dl = delta + delta_bias; dl = softplus(dl) if delta_softplus
+ *   h_t = exp(dl_t * A) * h_{t-1} + dl_t * B_t * u_t ;  y_t = <C_t, h_t> + D * u_t
+ *   out_t = y_t * silu(z_t)   (z optional)
+ * checkpoints (batch, dim, nchunks, dstate) fp32, nchunks = ceil(seqlen / MTTS_SCAN_CHUNK):
+ *   state at the start of each chunk (chunk 0 = initial state); NULL when no backward follows.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, seqlen, dstate;
+  int32_t io_dtype;
+  int32_t delta_softplus;
+  const void* u;
+  int64_t u_batch_stride, u_dim_stride;
+  const void* delta;
+  int64_t delta_batch_stride, delta_dim_stride;
+  const float* A; /* (dim, dstate) contiguous */
+  const void* B;
+  int64_t B_batch_stride, B_state_stride;
+  const void* C;
+  int64_t C_batch_stride, C_state_stride;
+  const float* D;          /* (dim) or NULL */
+  const float* delta_bias; /* (dim) or NULL */
+  const void* z;           /* or NULL */
+  int64_t z_batch_stride, z_dim_stride;
+  const float* initial_state; /* (batch, dim, dstate) contiguous or NULL */
+  void* out;
+  int64_t out_batch_stride, out_dim_stride;
+  float* last_state;  /* (batch, dim, dstate) contiguous or NULL */
+  float* checkpoints; /* see above, or NULL */
+} mtts_scan_fwd_params;
+int mtts_selective_scan_fwd(const mtts_scan_fwd_params* p, mtts_stream_t stream);
+
+/* selective_scan_bwd -- replaces selective_scan_cuda.bwd.  Recomputes the states inside each chunk
+ * from `checkpoints`.  dB, dC (batch, dstate, seqlen) fp32 contiguous, dA (dim, dstate), dD (dim),
+ * ddelta_bias (dim) fp32 are ACCUMULATED INTO (caller zero-fills).  du, ddelta, dz are io dtype. */
+typedef struct {
+  int32_t batch, dim, seqlen, dstate;
+  int32_t io_dtype;
+  int32_t delta_softplus;
+  const void* u;
+  int64_t u_batch_stride, u_dim_stride;
+  const void* delta;
+  int64_t delta_batch_stride, delta_dim_stride;
+  const float* A;
+  const void* B;
+  int64_t B_batch_stride, B_state_stride;
+  const void* C;
+  int64_t C_batch_stride, C_state_stride;
+  const float* D;
+  const float* delta_bias;
+  const void* z;
+  int64_t z_batch_stride, z_dim_stride;
+  const void* dout;
+  int64_t dout_batch_stride, dout_dim_stride;
+  const float* checkpoints;
+  void* du;
+  int64_t du_batch_stride, du_dim_stride;
+  void* ddelta;
+  int64_t ddelta_batch_stride, ddelta_dim_stride;
+  void* dz; /* required iff z != NULL */
+  int64_t dz_batch_stride, dz_dim_stride;
+  float* dA;
+  float* dB;
+  float* dC;
+  float* dD;          /* required iff D != NULL */
+  float* ddelta_bias; /* required iff delta_bias != NULL */
+} mtts_scan_bwd_params;
+int mtts_selective_scan_bwd(const mtts_scan_bwd_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * selective_state_update -- replaces mamba_ssm.ops.triton.selective_state_update (Mamba.step).
+ * state (batch, dim, dstate) fp32 contiguous, updated IN PLACE.  x, dt, z, out (batch, dim);
+ * B, C (batch, dstate): io dtype, rows contiguous.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, dstate;
+  int32_t io_dtype;
+  int32_t dt_softplus;
+  float* state;
+  const void* x;
+  int64_t x_batch_stride;
+  const void* dt;
+  int64_t dt_batch_stride;
+  const float* A;
+  const void* B;
+  int64_t B_batch_stride;
+  const void* C;
+  int64_t C_batch_stride;
+  const float* D;       /* or NULL */
+  const void* z;        /* or NULL */
+  int64_t z_batch_stride;
+  const float* dt_bias; /* or NULL */
+  void* out;
+  int64_t out_batch_stride;
+} mtts_state_update_params;
+int mtts_selective_state_update(const mtts_state_update_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * mamba_decode_step -- the whole inner part of Mamba.step in ONE launch (mamba_decoder.py:63 ->
+ * Mamba.step: causal_conv1d_update -> x_proj -> dt_proj -> selective_state_update -> gate):
+ *   x, z = xz[:, :dim], xz[:, dim:]
+ *   conv_state <- roll(conv_state); conv_state[..., -1] = x ; xc = silu(<conv_state, w> + b)
+ *   (dt_low, B, C) = x_proj_w @ xc ;  dt = softplus(dt_proj_w @ dt_low + dt_bias)
+ *   ssm_state <- ssm_state * exp(dt A) + dt B xc ;  y = <ssm_state, C> + D xc ;  y *= silu(z)
+ * xz, y, conv_state, x_proj_w (dt_rank + 2 dstate, dim), dt_proj_w (dim, dt_rank) are io dtype and
+ * contiguous; ssm_state fp32.  Both states are updated IN PLACE.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim, dstate, dt_rank, width;
+  int32_t io_dtype;
+  const void* xz; /* (batch, 2*dim) */
+  int64_t xz_batch_stride;
+  void* conv_state; /* (batch, dim, width) */
+  float* ssm_state; /* (batch, dim, dstate) */
+  const float* conv_weight; /* (dim, width) */
+  const float* conv_bias;   /* (dim) or NULL */
+  const void* x_proj_w;
+  const void* dt_proj_w;
+  const float* dt_bias; /* (dim) */
+  const float* A;       /* (dim, dstate) */
+  const float* D;       /* (dim) */
+  void* y;              /* (batch, dim) */
+  int64_t y_batch_stride;
+} mtts_decode_step_params;
+int mtts_mamba_decode_step(const mtts_decode_step_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * cross_attn_decode -- single-query attention of decode_step against the cached K/V of
+ * [ref || text] (mamba_decoder.py:72-77 with T_q = 1; K/V projected once per generation, D9).
+ *   q (batch, heads*head_dim) already projected (bias included, NOT yet scaled);
+ *   k, v (batch, t_kv, heads*head_dim) contiguous; mask (batch, t_kv) uint8, 1 = attend, or NULL;
+ *   out (batch, heads*head_dim) = softmax(q k^T / sqrt(head_dim) + mask) v, fp32 softmax.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, heads, head_dim, t_kv;
+  int32_t io_dtype;
+  const void* q;
+  const void* k;
+  const void* v;
+  const uint8_t* mask;
+  void* out;
+} mtts_cross_attn_decode_params;
+int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * layernorm_film -- LayerNorm (eps 1e-5, affine) optionally followed by FiLM and optionally
+ * preceded by a residual add; the memory-bound glue of mamba_decoder.py:59,67,81-86.
+ *   s   = x + residual          (residual optional; s is written to sum_out when non-NULL)
+ *   out = LN(s) * gamma_b + beta_b     (gamma/beta (batch, dim) optional FiLM terms, fp32)
+ * x, residual, sum_out, out: (rows, dim) contiguous io dtype, rows = batch * rows_per_batch.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows, dim, rows_per_batch;
+  int32_t io_dtype;
+  float eps;
+  const void* x;
+  const void* residual; /* or NULL */
+  void* sum_out;        /* or NULL */
+  const float* ln_weight;
+  const float* ln_bias;
+  const float* film_gamma; /* (rows / rows_per_batch, dim) or NULL */
+  const float* film_beta;
+  void* out;
+} mtts_layernorm_film_params;
+int mtts_layernorm_film(const mtts_layernorm_film_params* p, mtts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMBA_TTS_B200_H_ */

@@ -1,0 +1,183 @@
+"""ctypes binding of the C-ABI library (``include/mamba_tts_b200.h``).
+
+This is the *only* way the Python host code reaches the kernels: POD structs of raw device
+pointers, sizes and element strides plus the current CUDA stream.  There is no fallback: if the
+shared library is missing or a call returns non-zero, a ``RuntimeError`` is raised (SURVEY.md 8b
+"Errors"; upstream raises from ``TORCH_CHECK``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmamba_tts_b200.so")
+
+F32, BF16 = 0, 1
+SCAN_CHUNK = 256
+MAX_DSTATE = 256
+MAX_CONV_WIDTH = 4
+
+_i32, _i64, _ptr, _f32 = C.c_int32, C.c_int64, C.c_void_p, C.c_float
+
+
+def _struct(name, spec):
+    """spec: whitespace separated 'type:name' tokens; type in i (int32) l (int64) p (pointer) f (float)."""
+    kinds = {"i": _i32, "l": _i64, "p": _ptr, "f": _f32}
+    fields = []
+    for tok in spec.split():
+        k, n = tok.split(":")
+        fields.append((n, kinds[k]))
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+Conv1dFwdParams = _struct("Conv1dFwdParams", """
+    i:batch i:dim i:seqlen i:width i:io_dtype i:silu
+    p:x l:x_batch_stride l:x_dim_stride p:weight p:bias
+    p:initial_states l:init_batch_stride l:init_dim_stride
+    p:out l:out_batch_stride l:out_dim_stride""")
+
+Conv1dBwdParams = _struct("Conv1dBwdParams", """
+    i:batch i:dim i:seqlen i:width i:io_dtype i:silu
+    p:x l:x_batch_stride l:x_dim_stride p:weight p:bias
+    p:initial_states l:init_batch_stride l:init_dim_stride
+    p:dout l:dout_batch_stride l:dout_dim_stride
+    p:dx l:dx_batch_stride l:dx_dim_stride p:dweight p:dbias""")
+
+Conv1dUpdateParams = _struct("Conv1dUpdateParams", """
+    i:batch i:dim i:width i:io_dtype i:silu
+    p:x l:x_batch_stride p:conv_state p:weight p:bias p:out l:out_batch_stride""")
+
+ScanFwdParams = _struct("ScanFwdParams", """
+    i:batch i:dim i:seqlen i:dstate i:io_dtype i:delta_softplus
+    p:u l:u_batch_stride l:u_dim_stride
+    p:delta l:delta_batch_stride l:delta_dim_stride
+    p:A
+    p:B l:B_batch_stride l:B_state_stride
+    p:C l:C_batch_stride l:C_state_stride
+    p:D p:delta_bias
+    p:z l:z_batch_stride l:z_dim_stride
+    p:initial_state
+    p:out l:out_batch_stride l:out_dim_stride
+    p:last_state p:checkpoints""")
+
+ScanBwdParams = _struct("ScanBwdParams", """
+    i:batch i:dim i:seqlen i:dstate i:io_dtype i:delta_softplus
+    p:u l:u_batch_stride l:u_dim_stride
+    p:delta l:delta_batch_stride l:delta_dim_stride
+    p:A
+    p:B l:B_batch_stride l:B_state_stride
+    p:C l:C_batch_stride l:C_state_stride
+    p:D p:delta_bias
+    p:z l:z_batch_stride l:z_dim_stride
+    p:dout l:dout_batch_stride l:dout_dim_stride
+    p:checkpoints
+    p:du l:du_batch_stride l:du_dim_stride
+    p:ddelta l:ddelta_batch_stride l:ddelta_dim_stride
+    p:dz l:dz_batch_stride l:dz_dim_stride
+    p:dA p:dB p:dC p:dD p:ddelta_bias""")
+
+StateUpdateParams = _struct("StateUpdateParams", """
+    i:batch i:dim i:dstate i:io_dtype i:dt_softplus
+    p:state p:x l:x_batch_stride p:dt l:dt_batch_stride p:A
+    p:B l:B_batch_stride p:C l:C_batch_stride p:D
+    p:z l:z_batch_stride p:dt_bias p:out l:out_batch_stride""")
+
+DecodeStepParams = _struct("DecodeStepParams", """
+    i:batch i:dim i:dstate i:dt_rank i:width i:io_dtype
+    p:xz l:xz_batch_stride p:conv_state p:ssm_state p:conv_weight p:conv_bias
+    p:x_proj_w p:dt_proj_w p:dt_bias p:A p:D p:y l:y_batch_stride""")
+
+CrossAttnDecodeParams = _struct("CrossAttnDecodeParams", """
+    i:batch i:heads i:head_dim i:t_kv i:io_dtype
+    p:q p:k p:v p:mask p:out""")
+
+LayerNormFilmParams = _struct("LayerNormFilmParams", """
+    i:rows i:dim i:rows_per_batch i:io_dtype f:eps
+    p:x p:residual p:sum_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:out""")
+
+# declaration order of the header == argument of mtts_sizeof_params
+PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
+                 ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
+                 LayerNormFilmParams]
+
+# every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
+ENTRY_POINTS = {
+    "mtts_error_string": None,
+    "mtts_abi_version": None,
+    "mtts_target_sm": None,
+    "mtts_sizeof_params": None,
+    "mtts_causal_conv1d_fwd": Conv1dFwdParams,
+    "mtts_causal_conv1d_bwd": Conv1dBwdParams,
+    "mtts_causal_conv1d_update": Conv1dUpdateParams,
+    "mtts_selective_scan_fwd": ScanFwdParams,
+    "mtts_selective_scan_bwd": ScanBwdParams,
+    "mtts_selective_state_update": StateUpdateParams,
+    "mtts_mamba_decode_step": DecodeStepParams,
+    "mtts_cross_attn_decode": CrossAttnDecodeParams,
+    "mtts_layernorm_film": LayerNormFilmParams,
+}
+
+_lib = None
+launch_count = 0  # kernels launched through this binding (bench.py's ``gpu_launches``)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m mamba_tts_project_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mtts_error_string.restype = C.c_char_p
+    lib.mtts_error_string.argtypes = [C.c_int]
+    lib.mtts_abi_version.restype = C.c_int
+    lib.mtts_target_sm.restype = C.c_int
+    lib.mtts_sizeof_params.restype = C.c_int
+    lib.mtts_sizeof_params.argtypes = [C.c_int]
+    for name, st in ENTRY_POINTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        if st is not None:
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(st), C.c_void_p]
+    for i, st in enumerate(PARAM_STRUCTS):
+        if lib.mtts_sizeof_params(i) != C.sizeof(st):
+            raise RuntimeError(f"ABI mismatch: {st.__name__} is {C.sizeof(st)} bytes in Python, "
+                               f"{lib.mtts_sizeof_params(i)} in the library")
+    _lib = lib
+    return lib
+
+
+def io_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mamba_tts_project_b200 ops are CUDA-only (sm_100a); got a "
+                               f"{t.device} tensor.  There is no CPU path.")
+
+
+def call(name: str, params) -> None:
+    """Enqueue one library call on torch's current stream of the current device."""
+    global launch_count
+    lib = load()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.mtts_error_string(rc).decode()}")
+    launch_count += 1

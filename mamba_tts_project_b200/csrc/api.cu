@@ -1,0 +1,38 @@
+// Library-level entry points of the C ABI (mamba_tts_b200.h).
+#include <cuda_runtime.h>
+
+#include "mamba_tts_b200.h"
+
+extern "C" const char* mtts_error_string(int code) {
+  if (code < 0) return cudaGetErrorString(static_cast<cudaError_t>(-code));
+  switch (code) {
+    case MTTS_OK: return "ok";
+    case MTTS_ERR_NULL: return "a required pointer is NULL";
+    case MTTS_ERR_SHAPE: return "a dimension is outside the supported range";
+    case MTTS_ERR_DTYPE: return "unknown io dtype (expected MTTS_F32 or MTTS_BF16)";
+    case MTTS_ERR_ALIGN: return "pointer or stride alignment not supported";
+    case MTTS_ERR_UNSUPPORTED: return "unsupported variant";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int mtts_abi_version(void) { return 1; }
+
+extern "C" int mtts_target_sm(void) { return 100; }
+
+// sizeof() of every parameter struct, so a foreign-language binding (ctypes / cgo / JNI) can check
+// its mirror of the layout at load time.  `which` follows the declaration order in the header.
+extern "C" int mtts_sizeof_params(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(mtts_conv1d_fwd_params);
+    case 1: return (int)sizeof(mtts_conv1d_bwd_params);
+    case 2: return (int)sizeof(mtts_conv1d_update_params);
+    case 3: return (int)sizeof(mtts_scan_fwd_params);
+    case 4: return (int)sizeof(mtts_scan_bwd_params);
+    case 5: return (int)sizeof(mtts_state_update_params);
+    case 6: return (int)sizeof(mtts_decode_step_params);
+    case 7: return (int)sizeof(mtts_cross_attn_decode_params);
+    case 8: return (int)sizeof(mtts_layernorm_film_params);
+    default: return -1;
+  }
+}

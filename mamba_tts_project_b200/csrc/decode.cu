@@ -1,0 +1,408 @@
+// Single-token (decode_step) kernels for sm_100a.
+//   mtts_selective_state_update -- replaces mamba_ssm's Triton selective_state_update
+//   mtts_mamba_decode_step      -- conv-update + x_proj + dt_proj + state update + gate, ONE launch
+//   mtts_cross_attn_decode      -- 1-query attention against the cached K/V of [ref || text]
+//   mtts_layernorm_film         -- residual add + LayerNorm + FiLM glue
+// All reached from MambaTTSDecoder.decode_step (mamba_decoder.py:188-256) -> layer (:59-89).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mtts {
+
+// ------------------------------------------------------------------------------------------------
+// selective_state_update: one thread per (batch, channel), dstate states in a register loop.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) state_update_kernel(const mtts_state_update_params p) {
+  extern __shared__ float sm_bc[];  // B then C of this batch element
+  const int b = blockIdx.y, N = p.dstate;
+  const T* Bp = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
+  const T* Cp = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    sm_bc[n] = Io<T>::to_f(Bp[n]);
+    sm_bc[N + n] = Io<T>::to_f(Cp[n]);
+  }
+  __syncthreads();
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= p.dim) return;
+  const float x = Io<T>::to_f(reinterpret_cast<const T*>(p.x)[(int64_t)b * p.x_batch_stride + d]);
+  float dt = Io<T>::to_f(reinterpret_cast<const T*>(p.dt)[(int64_t)b * p.dt_batch_stride + d]);
+  if (p.dt_bias) dt += p.dt_bias[d];
+  if (p.dt_softplus) dt = softplus_f(dt);
+  float* st = p.state + ((int64_t)b * p.dim + d) * N;
+  const float* Ar = p.A + (int64_t)d * N;
+  const float dtx = dt * x, dt2 = dt * kLog2e;
+  float y = p.D ? p.D[d] * x : 0.f;
+  if ((N & 3) == 0) {
+    for (int n = 0; n < N; n += 4) {
+      float4 h = *reinterpret_cast<float4*>(st + n);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(Ar + n));
+      h.x = fmaf(ex2f(dt2 * a.x), h.x, dtx * sm_bc[n]);
+      h.y = fmaf(ex2f(dt2 * a.y), h.y, dtx * sm_bc[n + 1]);
+      h.z = fmaf(ex2f(dt2 * a.z), h.z, dtx * sm_bc[n + 2]);
+      h.w = fmaf(ex2f(dt2 * a.w), h.w, dtx * sm_bc[n + 3]);
+      *reinterpret_cast<float4*>(st + n) = h;
+      y = fmaf(h.x, sm_bc[N + n], y);
+      y = fmaf(h.y, sm_bc[N + n + 1], y);
+      y = fmaf(h.z, sm_bc[N + n + 2], y);
+      y = fmaf(h.w, sm_bc[N + n + 3], y);
+    }
+  } else {
+    for (int n = 0; n < N; ++n) {
+      const float h = fmaf(ex2f(dt2 * Ar[n]), st[n], dtx * sm_bc[n]);
+      st[n] = h;
+      y = fmaf(h, sm_bc[N + n], y);
+    }
+  }
+  if (p.z) y *= silu_f(Io<T>::to_f(reinterpret_cast<const T*>(p.z)[(int64_t)b * p.z_batch_stride + d]));
+  reinterpret_cast<T*>(p.out)[(int64_t)b * p.out_batch_stride + d] = Io<T>::from_f(y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused decode step.  One thread-block CLUSTER per batch element: the S CTAs of a cluster split the
+// d_inner channels; x_proj is a split-K product whose partial sums are exchanged through distributed
+// shared memory, so the whole Mamba.step inner part is one launch with no global round trip.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kStepThreads) decode_step_kernel(const mtts_decode_step_params p,
+                                                                   const int cpc) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = cluster.num_blocks();
+  const int rank = cluster.block_rank();
+  const int b = blockIdx.y;
+  const int N = p.dstate, R = p.dt_rank, W = p.width, J = R + 2 * N;
+  const int c_lo = rank * cpc, c_hi = min(p.dim, c_lo + cpc);
+  const int nown = max(0, c_hi - c_lo);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kStepThreads / 32;
+
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;           // [cpc]  conv output of the own channels
+  float* part = xs + cpc;   // [J]    own split-K partial of x_proj
+  float* xdbl = part + J;   // [J]    full x_proj output (dt_low | B | C)
+
+  // 1. conv update on the own channels (state rolled in place)
+  const T* xz = reinterpret_cast<const T*>(p.xz) + (int64_t)b * p.xz_batch_stride;
+  for (int i = threadIdx.x; i < nown; i += kStepThreads) {
+    const int d = c_lo + i;
+    T* st = reinterpret_cast<T*>(p.conv_state) + ((int64_t)b * p.dim + d) * W;
+    const T xin = xz[d];
+    float acc = p.conv_bias ? p.conv_bias[d] : 0.f;
+#pragma unroll
+    for (int k = 0; k < MTTS_MAX_CONV_WIDTH - 1; ++k) {
+      if (k < W - 1) {
+        const T v = st[k + 1];
+        acc = fmaf(p.conv_weight[d * W + k], Io<T>::to_f(v), acc);
+        st[k] = v;
+      }
+    }
+    acc = fmaf(p.conv_weight[d * W + W - 1], Io<T>::to_f(xin), acc);
+    st[W - 1] = xin;
+    xs[i] = Io<T>::to_f(Io<T>::from_f(silu_f(acc)));  // activation dtype, like the reference
+  }
+  __syncthreads();
+
+  // 2. split-K x_proj: part[j] = sum_{d own} Wx[j, d] * xs[d]
+  const T* Wx = reinterpret_cast<const T*>(p.x_proj_w);
+  for (int j = warp; j < J; j += kWarps) {
+    const T* wr = Wx + (int64_t)j * p.dim + c_lo;
+    float acc = 0.f;
+    for (int i = lane; i < nown; i += 32) acc = fmaf(Io<T>::to_f(wr[i]), xs[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) part[j] = acc;
+  }
+  cluster.sync();
+
+  // 3. all-gather-reduce the partials over the cluster through DSMEM
+  for (int j = threadIdx.x; j < J; j += kStepThreads) {
+    float s = 0.f;
+    for (int r = 0; r < S; ++r) s += cluster.map_shared_rank(part, r)[j];
+    // the reference rounds x_proj's output to the activation dtype before dt_proj / the update
+    xdbl[j] = Io<T>::to_f(Io<T>::from_f(s));
+  }
+  __syncthreads();
+
+  // 4./5. dt_proj + softplus + state update + gate on the own channels
+  const T* Wdt = reinterpret_cast<const T*>(p.dt_proj_w);
+  for (int i = threadIdx.x; i < nown; i += kStepThreads) {
+    const int d = c_lo + i;
+    float dt = 0.f;
+    const T* wr = Wdt + (int64_t)d * R;
+    for (int r = 0; r < R; ++r) dt = fmaf(Io<T>::to_f(wr[r]), xdbl[r], dt);
+    dt = Io<T>::to_f(Io<T>::from_f(dt));
+    dt = softplus_f(dt + p.dt_bias[d]);
+    const float x = xs[i];
+    const float dtx = dt * x, dt2 = dt * kLog2e;
+    float* st = p.ssm_state + ((int64_t)b * p.dim + d) * N;
+    const float* Ar = p.A + (int64_t)d * N;
+    float y = p.D[d] * x;
+    if ((N & 3) == 0) {
+      for (int n = 0; n < N; n += 4) {
+        float4 h = *reinterpret_cast<float4*>(st + n);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(Ar + n));
+        h.x = fmaf(ex2f(dt2 * a.x), h.x, dtx * xdbl[R + n]);
+        h.y = fmaf(ex2f(dt2 * a.y), h.y, dtx * xdbl[R + n + 1]);
+        h.z = fmaf(ex2f(dt2 * a.z), h.z, dtx * xdbl[R + n + 2]);
+        h.w = fmaf(ex2f(dt2 * a.w), h.w, dtx * xdbl[R + n + 3]);
+        *reinterpret_cast<float4*>(st + n) = h;
+        y = fmaf(h.x, xdbl[R + N + n], y);
+        y = fmaf(h.y, xdbl[R + N + n + 1], y);
+        y = fmaf(h.z, xdbl[R + N + n + 2], y);
+        y = fmaf(h.w, xdbl[R + N + n + 3], y);
+      }
+    } else {
+      for (int n = 0; n < N; ++n) {
+        const float h = fmaf(ex2f(dt2 * Ar[n]), st[n], dtx * xdbl[R + n]);
+        st[n] = h;
+        y = fmaf(h, xdbl[R + N + n], y);
+      }
+    }
+    y *= silu_f(Io<T>::to_f(xz[p.dim + d]));
+    reinterpret_cast<T*>(p.y)[(int64_t)b * p.y_batch_stride + d] = Io<T>::from_f(y);
+  }
+  // no CTA may exit while a peer can still read its `part`
+  cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention for one query token per batch element.  CTA = (batch, head).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads)
+cross_attn_decode_kernel(const mtts_cross_attn_decode_params p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int kWarps = kAttnThreads / 32;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int dh = p.head_dim, Tk = p.t_kv, Dm = p.heads * dh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sc = sm;                 // [Tk] scores -> probabilities
+  float* qs = sc + Tk;            // [dh]
+  float* acc_s = qs + dh;         // [kWarps][dh]
+  __shared__ float red_s[kWarps];
+
+  const float scale = rsqrtf((float)dh);
+  const T* q = reinterpret_cast<const T*>(p.q) + (int64_t)b * Dm + h * dh;
+  // torch scales q before QK^T and keeps it in the activation dtype
+  for (int e = threadIdx.x; e < dh; e += kAttnThreads)
+    qs[e] = Io<T>::to_f(Io<T>::from_f(Io<T>::to_f(q[e]) * scale));
+  __syncthreads();
+
+  const T* Kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * Tk * Dm + h * dh;
+  const T* Vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * Tk * Dm + h * dh;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * Tk : nullptr;
+
+  float lmax = -INFINITY;
+  for (int t = warp; t < Tk; t += kWarps) {
+    const T* kr = Kb + (int64_t)t * Dm;
+    float s = 0.f;
+    for (int e = lane; e < dh; e += 32) s = fmaf(Io<T>::to_f(kr[e]), qs[e], s);
+    s = warp_sum(s);
+    if (mk && !mk[t]) s = -INFINITY;
+    if (lane == 0) sc[t] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  if (lane == 0) red_s[warp] = lmax;
+  __syncthreads();
+  float gmax = red_s[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) gmax = fmaxf(gmax, red_s[w]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int t = threadIdx.x; t < Tk; t += kAttnThreads) {
+    const float e = ex2f((sc[t] - gmax) * kLog2e);  // all-masked row -> NaN like torch
+    sc[t] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red_s[warp] = lsum;
+  __syncthreads();
+  float gsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) gsum += red_s[w];
+  const float inv = 1.f / gsum;
+
+  // out[e] = sum_t p_t V[t, e]; warps split t, lanes split e
+  for (int e0 = 0; e0 < dh; e0 += 32) {
+    const int e = e0 + lane;
+    float a = 0.f;
+    if (e < dh)
+      for (int t = warp; t < Tk; t += kWarps) a = fmaf(sc[t], Io<T>::to_f(Vb[(int64_t)t * Dm + e]), a);
+    if (e < dh) acc_s[warp * dh + e] = a;
+  }
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t)b * Dm + h * dh;
+  for (int e = threadIdx.x; e < dh; e += kAttnThreads) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) a += acc_s[w * dh + e];
+    out[e] = Io<T>::from_f(a * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (residual add) + LayerNorm + (FiLM): one warp per row.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_film_kernel(const mtts_layernorm_film_params p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const int Dm = p.dim;
+  const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)row * Dm;
+  const T* r = p.residual ? reinterpret_cast<const T*>(p.residual) + (int64_t)row * Dm : nullptr;
+  T* so = p.sum_out ? reinterpret_cast<T*>(p.sum_out) + (int64_t)row * Dm : nullptr;
+  float s = 0.f;
+  for (int e = lane; e < Dm; e += 32) {
+    float v = Io<T>::to_f(x[e]);
+    if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
+    if (so) so[e] = Io<T>::from_f(v);
+    s += v;
+  }
+  const float mean = warp_sum(s) / (float)Dm;
+  float q = 0.f;
+  for (int e = lane; e < Dm; e += 32) {
+    float v;
+    if (so) v = Io<T>::to_f(so[e]);  // sum_out may alias x: never re-add the residual
+    else {
+      v = Io<T>::to_f(x[e]);
+      if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
+    }
+    const float dlt = v - mean;
+    q = fmaf(dlt, dlt, q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)Dm + p.eps);
+  const int bidx = row / p.rows_per_batch;
+  const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
+  const float* bet = p.film_beta ? p.film_beta + (int64_t)bidx * Dm : nullptr;
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t)row * Dm;
+  for (int e = lane; e < Dm; e += 32) {
+    float v;
+    if (so) v = Io<T>::to_f(so[e]);
+    else {
+      v = Io<T>::to_f(x[e]);
+      if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
+    }
+    float o = fmaf((v - mean) * rstd, p.ln_weight[e], p.ln_bias[e]);
+    if (gam) {
+      o = Io<T>::to_f(Io<T>::from_f(o));  // the reference materialises LN(x) before FiLM
+      o = fmaf(gam[e], o, bet ? bet[e] : 0.f);
+    }
+    out[e] = Io<T>::from_f(o);
+  }
+}
+
+template <typename T>
+static int launch_decode_step(const mtts_decode_step_params& p, cudaStream_t s) {
+  // cluster size: enough CTAs to cover the chip, at least 32 channels per CTA
+  int S = 8;
+  while (S > 1 && (p.batch * S > 2 * kNumSMs * 2 || p.dim / S < 32)) S >>= 1;
+  const int cpc = (p.dim + S - 1) / S;
+  const int J = p.dt_rank + 2 * p.dstate;
+  const size_t smem = sizeof(float) * ((size_t)cpc + 2 * J);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, p.batch);
+  cfg.blockDim = dim3(kStepThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  auto kern = decode_step_kernel<T>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, cpc);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  return launch_status();
+}
+
+}  // namespace mtts
+
+extern "C" int mtts_selective_state_update(const mtts_state_update_params* p, mtts_stream_t stream) {
+  if (!p || !p->state || !p->x || !p->dt || !p->A || !p->B || !p->C || !p->out) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->dim < 0 || p->dstate < 1 || p->dstate > MTTS_MAX_DSTATE || p->batch > 65535)
+    return MTTS_ERR_SHAPE;
+  if (p->batch == 0 || p->dim == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const dim3 grid((p->dim + 127) / 128, p->batch);
+  const size_t smem = sizeof(float) * 2 * p->dstate;
+  switch (p->io_dtype) {
+    case MTTS_F32: mtts::state_update_kernel<float><<<grid, 128, smem, s>>>(*p); break;
+    case MTTS_BF16: mtts::state_update_kernel<__nv_bfloat16><<<grid, 128, smem, s>>>(*p); break;
+    default: return MTTS_ERR_DTYPE;
+  }
+  return mtts::launch_status();
+}
+
+extern "C" int mtts_mamba_decode_step(const mtts_decode_step_params* p, mtts_stream_t stream) {
+  if (!p || !p->xz || !p->conv_state || !p->ssm_state || !p->conv_weight || !p->x_proj_w ||
+      !p->dt_proj_w || !p->dt_bias || !p->A || !p->D || !p->y)
+    return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->dim < 1 || p->dstate < 1 || p->dstate > MTTS_MAX_DSTATE || p->dt_rank < 1 ||
+      p->width < 2 || p->width > MTTS_MAX_CONV_WIDTH || p->batch > 65535)
+    return MTTS_ERR_SHAPE;
+  if (p->batch == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->io_dtype) {
+    case MTTS_F32: return mtts::launch_decode_step<float>(*p, s);
+    case MTTS_BF16: return mtts::launch_decode_step<__nv_bfloat16>(*p, s);
+    default: return MTTS_ERR_DTYPE;
+  }
+}
+
+extern "C" int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->out) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->heads < 1 || p->head_dim < 1 || p->t_kv < 1 || p->batch > 65535)
+    return MTTS_ERR_SHAPE;
+  if (p->batch == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * ((size_t)p->t_kv + p->head_dim + (mtts::kAttnThreads / 32) * p->head_dim);
+  if (smem > 200 * 1024) return MTTS_ERR_SHAPE;
+  const dim3 grid(p->heads, p->batch);
+  cudaError_t e;
+  switch (p->io_dtype) {
+    case MTTS_F32:
+      if (smem > 48 * 1024 &&
+          (e = cudaFuncSetAttribute(mtts::cross_attn_decode_kernel<float>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return -static_cast<int>(e);
+      mtts::cross_attn_decode_kernel<float><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
+      break;
+    case MTTS_BF16:
+      if (smem > 48 * 1024 &&
+          (e = cudaFuncSetAttribute(mtts::cross_attn_decode_kernel<__nv_bfloat16>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return -static_cast<int>(e);
+      mtts::cross_attn_decode_kernel<__nv_bfloat16><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
+      break;
+    default: return MTTS_ERR_DTYPE;
+  }
+  return mtts::launch_status();
+}
+
+extern "C" int mtts_layernorm_film(const mtts_layernorm_film_params* p, mtts_stream_t stream) {
+  if (!p || !p->x || !p->ln_weight || !p->ln_bias || !p->out) return MTTS_ERR_NULL;
+  if (p->rows < 0 || p->dim < 1 || p->rows_per_batch < 1) return MTTS_ERR_SHAPE;
+  if (p->rows == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 8;
+  const dim3 grid((p->rows + rows_per_cta - 1) / rows_per_cta);
+  switch (p->io_dtype) {
+    case MTTS_F32: mtts::layernorm_film_kernel<float><<<grid, 256, 0, s>>>(*p); break;
+    case MTTS_BF16: mtts::layernorm_film_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p); break;
+    default: return MTTS_ERR_DTYPE;
+  }
+  return mtts::launch_status();
+}

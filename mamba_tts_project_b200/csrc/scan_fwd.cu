@@ -1,0 +1,216 @@
+// selective_scan forward for sm_100a.  Replaces selective_scan_cuda.fwd (mamba_ssm), which the
+// reference reaches through Mamba.forward at mamba_decoder.py:61.  Math: see mamba_tts_b200.h.
+//
+// Per (lane, dstate row): one MUFU.EX2 per timestep-state (the binding unit on B200: 16/clk/SM),
+// sweep 1 builds the lane-local affine map, a 5-step shuffle scan stitches the 32 lanes, sweep 2
+// replays the recurrence from the true incoming state and contracts with C.
+#include "scan_common.cuh"
+
+namespace mtts {
+
+template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
+  using Tile = ScanTile<kItems>;
+  constexpr int kThreads = kWarps * 32;
+  constexpr int G = kWarps * kCPW;
+  constexpr int kLanesPerChunk = MTTS_SCAN_CHUNK / kItems;
+  constexpr int kChunksPerTile = Tile::kLen / MTTS_SCAN_CHUNK;
+
+  extern __shared__ __align__(16) float smem[];
+  const int N = p.dstate, L = p.seqlen;
+  float* Bs = smem;
+  float* Cs = Bs + kScanNChunk * Tile::kRow;
+  float* A2s = Cs + kScanNChunk * Tile::kRow;  // A * log2(e), [G][N]
+  float* hs = A2s + G * N;                     // running state,  [G][N]
+
+  const int b = blockIdx.y, c0 = blockIdx.x * G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int idx = threadIdx.x; idx < G * N; idx += kThreads) {
+    const int cl = idx / N, n = idx - cl * N, c = c0 + cl;
+    float a2 = 0.f, h = 0.f;
+    if (c < p.dim) {
+      a2 = p.A[(int64_t)c * N + n] * kLog2e;
+      const int64_t bc = (int64_t)b * p.dim + c;
+      if (p.initial_state) h = p.initial_state[bc * N + n];
+      if (p.checkpoints) p.checkpoints[bc * nchunks * N + n] = h;
+    }
+    A2s[idx] = a2;
+    hs[idx] = h;
+  }
+  __syncthreads();
+
+  const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
+  const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
+  const int ntiles = (L + Tile::kLen - 1) / Tile::kLen;
+  const bool restage_per_pass = N > kScanNChunk;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int t0 = tile * Tile::kLen;
+    const int tl = t0 + lane * kItems;
+#pragma unroll 1
+    for (int pass = 0; pass < kCPW; ++pass) {
+      const int cl = pass * kWarps + warp;
+      const int c = c0 + cl;
+      const bool cvalid = c < p.dim;  // warp-uniform
+
+      float dl[kItems], du[kItems], y[kItems];
+      float dsum = 0.f;
+      if (cvalid) {
+        const T* urow = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride +
+                        (int64_t)c * p.u_dim_stride;
+        const T* drow = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride +
+                        (int64_t)c * p.delta_dim_stride;
+        load_items<T, kItems, kVec>(urow, tl, L, du);
+        load_items<T, kItems, kVec>(drow, tl, L, dl);
+        const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
+        const float Dv = p.D ? p.D[c] : 0.f;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+          float x = dl[i] + bias;
+          if (p.delta_softplus) x = softplus_f(x);
+          if (tl + i >= L) x = 0.f;  // padding: decay 1, input 0 = identity step
+          const float uu = du[i];
+          dl[i] = x;
+          y[i] = Dv * uu;
+          du[i] = x * uu;
+          dsum += x;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) dl[i] = du[i] = y[i] = 0.f;
+      }
+
+      for (int n0 = 0; n0 < N; n0 += kScanNChunk) {
+        const int ncnt = min(kScanNChunk, N - n0);
+        if (restage_per_pass || pass == 0) {
+          __syncthreads();  // every warp is done reading the previous B/C tile
+          stage_rows<T, kItems, kVec, kThreads>(Bb, p.B_state_stride, n0, ncnt, t0, L, Bs);
+          stage_rows<T, kItems, kVec, kThreads>(Cb, p.C_state_stride, n0, ncnt, t0, L, Cs);
+          __syncthreads();
+        }
+        if (!cvalid) continue;
+#pragma unroll 1
+        for (int nn = 0; nn < ncnt; ++nn) {
+          const int n = n0 + nn;
+          const float A2 = A2s[cl * N + n];
+          const float h_in = hs[cl * N + n];
+          float a[kItems], bx[kItems], tmp[kItems];
+          lane_row<kItems>(Bs + nn * Tile::kRow + lane * Tile::kSeg, tmp);
+          float hl = 0.f;
+#pragma unroll
+          for (int i = 0; i < kItems; ++i) {
+            a[i] = ex2f(dl[i] * A2);
+            bx[i] = du[i] * tmp[i];
+            hl = fmaf(a[i], hl, bx[i]);
+          }
+          float P = ex2f(A2 * dsum);  // product of the lane's decays
+          warp_scan_affine_up(P, hl, lane);
+          float Pe = __shfl_up_sync(0xffffffffu, P, 1);
+          float he = __shfl_up_sync(0xffffffffu, hl, 1);
+          if (lane == 0) {
+            Pe = 1.f;
+            he = 0.f;
+          }
+          float h = fmaf(Pe, h_in, he);  // state entering this lane's first timestep
+          lane_row<kItems>(Cs + nn * Tile::kRow + lane * Tile::kSeg, tmp);
+#pragma unroll
+          for (int i = 0; i < kItems; ++i) {
+            h = fmaf(a[i], h, bx[i]);
+            y[i] = fmaf(h, tmp[i], y[i]);
+          }
+          // h = state after this lane's last timestep
+          if (lane == 31) hs[cl * N + n] = h;
+          if (p.checkpoints && ((lane + 1) % kLanesPerChunk) == 0) {
+            const int k = tile * kChunksPerTile + (lane + 1) / kLanesPerChunk;
+            if (k < nchunks)
+              p.checkpoints[(((int64_t)b * p.dim + c) * nchunks + k) * N + n] = h;
+          }
+        }
+        __syncwarp();
+      }
+
+      if (cvalid) {
+        if (p.z) {
+          const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride +
+                          (int64_t)c * p.z_dim_stride;
+          float zv[kItems];
+          load_items<T, kItems, kVec>(zrow, tl, L, zv);
+#pragma unroll
+          for (int i = 0; i < kItems; ++i) y[i] *= silu_f(zv[i]);
+        }
+        T* orow = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_batch_stride +
+                  (int64_t)c * p.out_dim_stride;
+        store_items<T, kItems, kVec>(orow, tl, L, y);
+      }
+    }
+  }
+
+  if (p.last_state) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * N; idx += kThreads) {
+      const int cl = idx / N, n = idx - cl * N, c = c0 + cl;
+      if (c < p.dim) p.last_state[((int64_t)b * p.dim + c) * N + n] = hs[idx];
+    }
+  }
+}
+
+template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
+static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
+  using Tile = ScanTile<kItems>;
+  constexpr int G = kWarps * kCPW;
+  const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
+  const size_t smem = sizeof(float) * (2 * kScanNChunk * Tile::kRow + 2 * (size_t)G * p.dstate);
+  auto kern = scan_fwd_kernel<T, kItems, kWarps, kCPW, kVec>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  const dim3 grid((p.dim + G - 1) / G, p.batch);
+  kern<<<grid, kWarps * 32, smem, stream>>>(p, nchunks);
+  return launch_status();
+}
+
+template <typename T>
+static int dispatch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
+  const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&
+                   vec_ok<T>(p.C, p.C_batch_stride, p.C_state_stride, p.seqlen) &&
+                   vec_ok<T>(p.z, p.z_batch_stride, p.z_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen);
+  const bool two = p.dstate <= kScanNChunk && p.dim >= 16;
+  if (vec) {
+    return two ? launch_scan_fwd<T, 16, 8, 2, true>(p, stream)
+               : launch_scan_fwd<T, 16, 8, 1, true>(p, stream);
+  }
+  return two ? launch_scan_fwd<T, 16, 8, 2, false>(p, stream)
+             : launch_scan_fwd<T, 16, 8, 1, false>(p, stream);
+}
+
+}  // namespace mtts
+
+extern "C" int mtts_selective_scan_fwd(const mtts_scan_fwd_params* p, mtts_stream_t stream) {
+  if (!p || !p->u || !p->delta || !p->A || !p->B || !p->C || !p->out) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->dim < 0 || p->seqlen < 0 || p->dstate < 1 ||
+      p->dstate > MTTS_MAX_DSTATE || p->batch > 65535)
+    return MTTS_ERR_SHAPE;
+  if (p->batch == 0 || p->dim == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->seqlen == 0) {
+    // nothing to scan: the state passes through
+    if (p->last_state) {
+      const size_t bytes = sizeof(float) * (size_t)p->batch * p->dim * p->dstate;
+      cudaError_t e = p->initial_state
+                          ? cudaMemcpyAsync(p->last_state, p->initial_state, bytes,
+                                            cudaMemcpyDeviceToDevice, s)
+                          : cudaMemsetAsync(p->last_state, 0, bytes, s);
+      if (e != cudaSuccess) return -static_cast<int>(e);
+    }
+    return MTTS_OK;
+  }
+  switch (p->io_dtype) {
+    case MTTS_F32: return mtts::dispatch_scan_fwd<float>(*p, s);
+    case MTTS_BF16: return mtts::dispatch_scan_fwd<__nv_bfloat16>(*p, s);
+    default: return MTTS_ERR_DTYPE;
+  }
+}

@@ -1,0 +1,325 @@
+"""B200 decoder: host-side mirror of ``/root/reference/mamba_decoder.py``.
+
+Same classes, constructor arguments, call signatures, module tree / state_dict keys and error
+behaviour as the reference's ``MambaTTSDecoderLayer`` (``:25-91``) and ``MambaTTSDecoder``
+(``:94-256``), so a reference checkpoint loads unchanged and a caller (``train.py:62-67,220-227``)
+switches by changing one import.  What differs is underneath:
+
+* ``forward``      teacher-forced path: Mamba conv + scan on the sm_100a library (autograd through
+                   the recompute backward), attention without the discarded weights (D8).
+* ``decode_step``  same signature and return value; K/V of [ref || text], the FiLM (gamma, beta)
+                   and the dtype-converted weights are cached across steps instead of being
+                   recomputed every step (D9) -- numerically identical.
+* ``generate``     the missing caller of ``decode_step``: greedy / sampled loop,
+                   one CUDA graph per step, states updated in place.
+
+Decisions on the reference's defects are listed in DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .mamba import Mamba
+
+
+def _join_memory(text_hidden, text_mask, ref_hidden, ref_mask):
+    """[ref || text] memory and validity mask (``mamba_decoder.py:148-165,226-241``); True = attend."""
+    if ref_hidden is None:
+        return text_hidden, text_mask
+    B = text_hidden.shape[0]
+    assert ref_hidden.dim() == 3 and ref_hidden.shape[0] == B, "ref_hidden must be (B, T_ref, d_model)"
+    if ref_mask is None:
+        ref_mask = torch.ones(B, ref_hidden.shape[1], dtype=torch.bool, device=ref_hidden.device)
+    else:
+        assert ref_mask.dim() == 2 and ref_mask.shape[0] == B, "ref_mask must be (B, T_ref) bool"
+    memory = torch.cat([ref_hidden, text_hidden], dim=1)
+    mask = ref_mask if text_mask is None else torch.cat([ref_mask, text_mask], dim=1)
+    return memory, mask
+
+
+class CrossAttention(nn.Module):
+    """``nn.MultiheadAttention(embed_dim, num_heads, batch_first=True)`` with the same parameter
+    names (``in_proj_weight``, ``in_proj_bias``, ``out_proj.{weight,bias}``) and arithmetic
+    (``mamba_decoder.py:32-36,72-77``); never materialises the averaged weights (D8)."""
+
+    def __init__(self, embed_dim, num_heads):
+        super().__init__()
+        assert embed_dim % num_heads == 0, "embed_dim must be divisible by num_heads"
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+    def project_kv(self, memory, dtype=None):
+        E = self.embed_dim
+        w, b = self.in_proj_weight, self.in_proj_bias
+        if dtype is not None:
+            w, b, memory = w.to(dtype), b.to(dtype), memory.to(dtype)
+        k = F.linear(memory, w[E:2 * E], b[E:2 * E])
+        v = F.linear(memory, w[2 * E:], b[2 * E:])
+        return k, v
+
+    def forward(self, query, memory, key_padding_mask=None):
+        """query (B, T, E); memory (B, T_kv, E); key_padding_mask (B, T_kv) True = IGNORE."""
+        B, T, E = query.shape
+        H, dh = self.num_heads, self.head_dim
+        q = F.linear(query, self.in_proj_weight[:E], self.in_proj_bias[:E])
+        k, v = self.project_kv(memory)
+        q = q.view(B, T, H, dh).transpose(1, 2)
+        k = k.view(B, -1, H, dh).transpose(1, 2)
+        v = v.view(B, -1, H, dh).transpose(1, 2)
+        bias = None
+        if key_padding_mask is not None:
+            bias = torch.zeros(B, 1, 1, k.shape[2], dtype=q.dtype, device=q.device)
+            bias.masked_fill_(key_padding_mask[:, None, None, :], float("-inf"))
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias)
+        o = o.transpose(1, 2).reshape(B, T, E)
+        return self.out_proj(o)
+
+
+class MambaTTSDecoderLayer(nn.Module):
+    def __init__(self, d_model, n_heads, d_ff, d_style, d_state=16, d_conv=4, expand=2):
+        super().__init__()
+        self.norm_mamba = nn.LayerNorm(d_model)
+        self.mamba = Mamba(d_model, d_state=d_state, d_conv=d_conv, expand=expand)
+        self.norm_cross = nn.LayerNorm(d_model)
+        self.cross_attn = CrossAttention(d_model, n_heads)
+        self.norm_ff = nn.LayerNorm(d_model)
+        self.ff = nn.Sequential(nn.Linear(d_model, d_ff), nn.GELU(), nn.Linear(d_ff, d_model))
+        self.style_mlp = nn.Sequential(nn.Linear(d_style, 2 * d_model), nn.Tanh())
+
+    def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):
+        h = self.norm_mamba(x)
+        if mamba_state is None:
+            h_mamba, new_state = self.mamba(h)
+        else:
+            h_mamba, new_state = self.mamba(h, mamba_state)
+        x = x + h_mamba
+
+        h = self.norm_cross(x)
+        key_padding_mask = None if text_mask is None else ~text_mask
+        x = x + self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask)
+
+        h = self.norm_ff(x)
+        gamma, beta = torch.chunk(self.style_mlp(z_style), 2, dim=-1)
+        h = gamma.unsqueeze(1) * h + beta.unsqueeze(1)
+        x = x + self.ff(h)
+        return x, new_state
+
+
+class _LayerStepWeights:
+    """Per-layer weights in the decode dtype + the generation-constant tensors (K, V, gamma, beta)."""
+
+    def __init__(self, layer: MambaTTSDecoderLayer, dtype, memory, z_style):
+        E = layer.cross_attn.embed_dim
+        ca = layer.cross_attn
+        f32 = torch.float32
+        self.mamba = layer.mamba._step_weights(dtype)
+        self.ln1 = (layer.norm_mamba.weight.detach().to(f32).contiguous(),
+                    layer.norm_mamba.bias.detach().to(f32).contiguous(), layer.norm_mamba.eps)
+        self.ln2 = (layer.norm_cross.weight.detach().to(f32).contiguous(),
+                    layer.norm_cross.bias.detach().to(f32).contiguous(), layer.norm_cross.eps)
+        self.ln3 = (layer.norm_ff.weight.detach().to(f32).contiguous(),
+                    layer.norm_ff.bias.detach().to(f32).contiguous(), layer.norm_ff.eps)
+        self.wq = ca.in_proj_weight.detach()[:E].to(dtype).contiguous()
+        self.bq = ca.in_proj_bias.detach()[:E].to(dtype).contiguous()
+        self.wo = ca.out_proj.weight.detach().to(dtype).contiguous()
+        self.bo = ca.out_proj.bias.detach().to(dtype).contiguous()
+        self.w1 = layer.ff[0].weight.detach().to(dtype).contiguous()
+        self.b1 = layer.ff[0].bias.detach().to(dtype).contiguous()
+        self.w2 = layer.ff[2].weight.detach().to(dtype).contiguous()
+        self.b2 = layer.ff[2].bias.detach().to(dtype).contiguous()
+        self.heads = ca.num_heads
+        k, v = ca.project_kv(memory, dtype)
+        self.k, self.v = k.contiguous(), v.contiguous()
+        gb = layer.style_mlp(z_style.to(layer.style_mlp[0].weight.dtype)).to(dtype).float()
+        gamma, beta = gb.chunk(2, dim=-1)
+        self.gamma, self.beta = gamma.contiguous(), beta.contiguous()
+
+
+class GenerationContext:
+    """Everything that is constant over one generation (``decode_step``'s D9 recomputations)."""
+
+    def __init__(self, decoder: "MambaTTSDecoder", text_hidden, z_style, text_mask=None,
+                 ref_hidden=None, ref_mask=None, dtype=None):
+        dtype = dtype if dtype is not None else text_hidden.dtype
+        self.dtype = dtype
+        with torch.no_grad():
+            memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
+            self.batch = memory.shape[0]
+            self.mask = None if mask is None else mask.to(torch.uint8).contiguous()
+            self.layers = [_LayerStepWeights(l, dtype, memory, z_style) for l in decoder.layers]
+            f32 = torch.float32
+            self.ln_out = (decoder.norm_out.weight.detach().to(f32).contiguous(),
+                           decoder.norm_out.bias.detach().to(f32).contiguous(), decoder.norm_out.eps)
+            self.head_w = decoder.head.weight.detach().to(dtype).contiguous()
+            self.head_b = decoder.head.bias.detach().to(dtype).contiguous()
+            self.tok = decoder.token_embed.weight.detach().to(dtype).contiguous()
+            self.pos = decoder.pos_embed.weight.detach().to(dtype).contiguous()
+
+
+class MambaTTSDecoder(nn.Module):
+    def __init__(self, vocab_size_audio, d_model=512, n_layers=8, n_heads=8, d_ff=2048, d_style=256,
+                 max_len=8192, num_quantizers=1, d_state=16, d_conv=4, expand=2):
+        super().__init__()
+        self.vocab_size_audio = vocab_size_audio
+        self.token_embed = nn.Embedding(vocab_size_audio, d_model)
+        self.pos_embed = nn.Embedding(max_len, d_model)
+        self.quant_embed = nn.Embedding(num_quantizers, d_model)
+        self.layers = nn.ModuleList([
+            MambaTTSDecoderLayer(d_model, n_heads, d_ff, d_style, d_state, d_conv, expand)
+            for _ in range(n_layers)])
+        self.norm_out = nn.LayerNorm(d_model)
+        self.head = nn.Linear(d_model, vocab_size_audio)
+        self._gen_key = None
+        self._gen_ctx = None
+
+    # ---- teacher-forced path (mamba_decoder.py:120-186) -----------------------------------------
+    def forward(self, audio_tokens, text_hidden, z_style, text_mask=None, ref_hidden=None,
+                ref_mask=None):
+        if audio_tokens.dim() == 3:
+            B, Q, T = audio_tokens.shape
+            audio_tokens = audio_tokens.reshape(B, Q * T)
+            quant_ids = torch.arange(Q, device=audio_tokens.device).repeat_interleave(T)
+            quant_ids = quant_ids.unsqueeze(0).expand(B, -1)
+            pos_ids = torch.arange(T, device=audio_tokens.device).repeat(Q)  # train.py:123 (D4)
+        elif audio_tokens.dim() == 2:
+            B, T = audio_tokens.shape
+            quant_ids = torch.zeros_like(audio_tokens)
+            pos_ids = torch.arange(T, device=audio_tokens.device)
+        else:
+            raise ValueError("audio_tokens must be (B, T) or (B, Q, T)")
+        if text_mask is not None:
+            assert text_mask.dim() == 2 and text_mask.shape[0] == B, (
+                "text_mask must be shape (B, T_text) with dtype=bool")
+        memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
+
+        x = self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None] + self.quant_embed(quant_ids)
+        for layer in self.layers:
+            x, _ = layer(x=x, text_hidden=memory, z_style=z_style, text_mask=mask, mamba_state=None)
+        return self.head(self.norm_out(x))
+
+    # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------
+    def prepare_generation(self, text_hidden, z_style, text_mask=None, ref_hidden=None,
+                           ref_mask=None, dtype=None):
+        return GenerationContext(self, text_hidden, z_style, text_mask, ref_hidden, ref_mask, dtype)
+
+    def allocate_states(self, batch, dtype):
+        return [l.mamba.allocate_inference_cache(batch, dtype=dtype) for l in self.layers]
+
+    def _context_for(self, text_hidden, z_style, text_mask, ref_hidden, ref_mask):
+        key = tuple(None if t is None else (t.data_ptr(), tuple(t.shape), t._version, t.dtype)
+                    for t in (text_hidden, z_style, text_mask, ref_hidden, ref_mask))
+        key += tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._gen_key != key:
+            self._gen_ctx = self.prepare_generation(text_hidden, z_style, text_mask, ref_hidden, ref_mask)
+            self._gen_key = key
+        return self._gen_ctx
+
+    def _step_core(self, ctx: GenerationContext, x, states):
+        """x (B, d_model) residual stream of the new token -> logits (B, V); states in place."""
+        delta = None  # pending residual branch, folded into the next LayerNorm launch
+        for lw, (conv_state, ssm_state) in zip(ctx.layers, states):
+            h = ops.layernorm_film(x, lw.ln1[0], lw.ln1[1], lw.ln1[2], residual=delta,
+                                   sum_out=x if delta is not None else None)
+            xz = F.linear(h, lw.mamba["in_proj"], lw.mamba["in_bias"])
+            y = ops.mamba_decode_step(xz, conv_state, ssm_state, lw.mamba["conv_w"],
+                                      lw.mamba["conv_b"], lw.mamba["x_proj"], lw.mamba["dt_proj"],
+                                      lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"])
+            m = F.linear(y, lw.mamba["out_proj"], lw.mamba["out_bias"])
+            h = ops.layernorm_film(x, lw.ln2[0], lw.ln2[1], lw.ln2[2], residual=m, sum_out=x)
+            q = F.linear(h, lw.wq, lw.bq)
+            a = ops.cross_attn_decode(q, lw.k, lw.v, lw.heads, mask=ctx.mask)
+            o = F.linear(a, lw.wo, lw.bo)
+            h = ops.layernorm_film(x, lw.ln3[0], lw.ln3[1], lw.ln3[2], residual=o, sum_out=x,
+                                   gamma=lw.gamma, beta=lw.beta)
+            f = F.gelu(F.linear(h, lw.w1, lw.b1))
+            delta = F.linear(f, lw.w2, lw.b2)
+        h = ops.layernorm_film(x, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], residual=delta,
+                               sum_out=x if delta is not None else None)
+        return F.linear(h, ctx.head_w, ctx.head_b)
+
+    @torch.no_grad()
+    def decode_step(self, last_token, text_hidden, z_style, mamba_states, step_index: int,
+                    text_mask=None, ref_hidden=None, ref_mask=None):
+        """Reference signature.  Returns (logits (B, 1, V), new_states); ``mamba_states`` entries may
+        be None on the first step; given states are updated IN PLACE and returned."""
+        if not last_token.is_cuda:
+            raise RuntimeError("MambaTTSDecoder (mamba_tts_project_b200) is CUDA-only")
+        ctx = self._context_for(text_hidden, z_style, text_mask, ref_hidden, ref_mask)
+        B = last_token.shape[0]
+        states = []
+        for i, layer in enumerate(self.layers):
+            st = None if mamba_states is None else mamba_states[i]
+            states.append(st if st is not None else
+                          layer.mamba.allocate_inference_cache(B, dtype=ctx.dtype))
+        x = ctx.tok[last_token[:, 0]] + ctx.pos[step_index]   # no quant_embed here (reference D5)
+        logits = self._step_core(ctx, x.contiguous(), states)
+        return logits.unsqueeze(1), states
+
+    @torch.no_grad()
+    def generate(self, first_token, n_steps, text_hidden, z_style, text_mask=None, ref_hidden=None,
+                 ref_mask=None, start_index=0, temperature=0.0, use_cuda_graph=True, dtype=None,
+                 generator=None):
+        """Autoregressive loop around ``decode_step`` (greedy when temperature == 0).
+
+        first_token (B, 1) int64.  Returns tokens (B, n_steps) int64 (the generated ids).  With
+        ``use_cuda_graph`` one decode step is captured once and replayed: the token, the position
+        counter and the per-layer states live in static device buffers, nothing syncs the host."""
+        ctx = self.prepare_generation(text_hidden, z_style, text_mask, ref_hidden, ref_mask, dtype)
+        B = first_token.shape[0]
+        dev = first_token.device
+        states = self.allocate_states(B, ctx.dtype)
+        tok = first_token[:, 0].clone()
+        pos = torch.full((1,), start_index, dtype=torch.long, device=dev)
+        out = torch.empty(B, n_steps, dtype=torch.long, device=dev)
+        col = torch.zeros(1, dtype=torch.long, device=dev)
+        greedy = temperature == 0.0
+        if not greedy and use_cuda_graph:
+            use_cuda_graph = False  # sampling draws host-side RNG state per step
+
+        def one_step():
+            x = ctx.tok.index_select(0, tok) + ctx.pos.index_select(0, pos)
+            logits = self._step_core(ctx, x, states)
+            if greedy:
+                nxt = logits.argmax(dim=-1)
+            else:
+                probs = torch.softmax(logits.float() / temperature, dim=-1)
+                nxt = torch.multinomial(probs, 1, generator=generator)[:, 0]
+            tok.copy_(nxt)
+            out.index_copy_(1, col, nxt[:, None])
+            pos.add_(1)
+            col.add_(1)
+
+        if not use_cuda_graph:
+            for _ in range(n_steps):
+                one_step()
+            return out
+
+        # warm up on a side stream (cuBLAS workspaces, lazy module loads), then restore the state
+        snap = [(c.clone(), s.clone()) for c, s in states]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_step()
+        torch.cuda.current_stream().wait_stream(side)
+        for (c, s), (c0, s0) in zip(states, snap):
+            c.copy_(c0)
+            s.copy_(s0)
+        tok.copy_(first_token[:, 0])
+        pos.fill_(start_index)
+        col.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step()
+        # capture does not execute: state is still the initial one
+        for _ in range(n_steps):
+            graph.replay()
+        return out

@@ -1,0 +1,381 @@
+"""Operator surface of the hot path -- same names, argument meaning and error behaviour as the
+third-party ops the reference reaches through ``Mamba(d_model)`` (``mamba_decoder.py:4,29,61,63``):
+
+    selective_scan_fn        <- mamba_ssm.ops.selective_scan_interface.selective_scan_fn
+    selective_state_update   <- mamba_ssm.ops.triton.selective_state_update.selective_state_update
+    causal_conv1d_fn         <- causal_conv1d.causal_conv1d_fn
+    causal_conv1d_update     <- causal_conv1d.causal_conv1d_update
+    mamba_inner_fn           <- mamba_ssm.ops.selective_scan_interface.mamba_inner_fn
+
+Every op is a thin ``torch.autograd.Function`` (or plain function) that fills a POD struct and calls
+the sm_100a library through the C ABI (``_lib.call``).  CUDA tensors only; nothing here computes on
+the host, and there is no fallback.  Variants upstream offers that the decoder never uses (complex A,
+constant / grouped 4-D B and C, ``seq_idx``) raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import ptr
+
+__all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
+           "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
+           "layernorm_film"]
+
+
+def _unit_last_stride(t):
+    return t if t is None or t.stride(-1) == 1 else t.contiguous()
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# causal_conv1d
+# ------------------------------------------------------------------------------------------------
+def _conv_args(x, weight, activation):
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    if x.dim() != 3:
+        raise RuntimeError("x must be (batch, dim, seqlen)")
+    dim, width = weight.shape
+    if x.shape[1] != dim:
+        raise RuntimeError("weight must be (dim, width) matching x's dim")
+    if not 2 <= width <= _lib.MAX_CONV_WIDTH:
+        raise RuntimeError("causal_conv1d only supports width between 2 and 4")
+
+
+class _CausalConv1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, initial_states, activation):
+        _lib.require_cuda(x, weight, bias, initial_states)
+        _conv_args(x, weight, activation)
+        x = _unit_last_stride(x)
+        w32, b32 = _f32c(weight), _f32c(bias)
+        init = None
+        if initial_states is not None:
+            init = _unit_last_stride(initial_states.detach().to(x.dtype))
+            if init.shape != (x.shape[0], x.shape[1], weight.shape[1] - 1):
+                raise RuntimeError("initial_states must be (batch, dim, width - 1)")
+        out = torch.empty_like(x, memory_format=torch.contiguous_format)
+        B, Dm, L = x.shape
+        p = _lib.Conv1dFwdParams(
+            batch=B, dim=Dm, seqlen=L, width=weight.shape[1], io_dtype=_lib.io_dtype(x),
+            silu=int(activation is not None), x=ptr(x), x_batch_stride=x.stride(0),
+            x_dim_stride=x.stride(1), weight=ptr(w32), bias=ptr(b32), initial_states=ptr(init),
+            init_batch_stride=0 if init is None else init.stride(0),
+            init_dim_stride=0 if init is None else init.stride(1),
+            out=ptr(out), out_batch_stride=out.stride(0), out_dim_stride=out.stride(1))
+        _lib.call("mtts_causal_conv1d_fwd", p)
+        ctx.save_for_backward(x, w32, b32, init)
+        ctx.activation = activation
+        ctx.wdtype = weight.dtype
+        ctx.bdtype = None if bias is None else bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w32, b32, init = ctx.saved_tensors
+        dout = _unit_last_stride(dout.to(x.dtype))
+        B, Dm, L = x.shape
+        dx = torch.empty_like(x, memory_format=torch.contiguous_format)
+        dw = torch.zeros_like(w32)
+        db = torch.zeros(Dm, dtype=torch.float32, device=x.device)
+        p = _lib.Conv1dBwdParams(
+            batch=B, dim=Dm, seqlen=L, width=w32.shape[1], io_dtype=_lib.io_dtype(x),
+            silu=int(ctx.activation is not None), x=ptr(x), x_batch_stride=x.stride(0),
+            x_dim_stride=x.stride(1), weight=ptr(w32), bias=ptr(b32), initial_states=ptr(init),
+            init_batch_stride=0 if init is None else init.stride(0),
+            init_dim_stride=0 if init is None else init.stride(1),
+            dout=ptr(dout), dout_batch_stride=dout.stride(0), dout_dim_stride=dout.stride(1),
+            dx=ptr(dx), dx_batch_stride=dx.stride(0), dx_dim_stride=dx.stride(1),
+            dweight=ptr(dw), dbias=ptr(db))
+        _lib.call("mtts_causal_conv1d_bwd", p)
+        return (dx, dw.to(ctx.wdtype), None if ctx.bdtype is None else db.to(ctx.bdtype),
+                None, None)
+
+
+def causal_conv1d_fn(x, weight, bias=None, seq_idx=None, initial_states=None,
+                     return_final_states=False, final_states_out=None, activation=None):
+    """x: (batch, dim, seqlen); weight: (dim, width); bias: (dim,); initial_states:
+    (batch, dim, width - 1).  Returns out (batch, dim, seqlen) [, final_states (batch, dim, width-1)]."""
+    if seq_idx is not None:
+        raise NotImplementedError("seq_idx (packed variable-length batches) is not on this path")
+    out = _CausalConv1dFn.apply(x, weight, bias, initial_states, activation)
+    if not return_final_states:
+        return out
+    width = weight.shape[1]
+    with torch.no_grad():
+        hist = x if initial_states is None else torch.cat([initial_states.to(x.dtype), x], dim=-1)
+        final = F.pad(hist, (width - 1 - hist.shape[-1], 0))[..., -(width - 1):] \
+            if hist.shape[-1] < width - 1 else hist[..., -(width - 1):]
+        if final_states_out is not None:
+            final_states_out.copy_(final)
+            final = final_states_out
+    return out, final
+
+
+def causal_conv1d_update(x, conv_state, weight, bias=None, activation=None):
+    """x: (batch, dim); conv_state: (batch, dim, width) rolled left IN PLACE, x written last
+    (``Mamba.step`` convention).  Returns (batch, dim)."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    _lib.require_cuda(x, conv_state, weight, bias)
+    B, Dm = x.shape
+    width = weight.shape[1]
+    if conv_state.shape != (B, Dm, width) or not conv_state.is_contiguous():
+        raise RuntimeError("conv_state must be contiguous (batch, dim, width)")
+    if conv_state.dtype != x.dtype:
+        raise RuntimeError("conv_state and x must have the same dtype")
+    x = _unit_last_stride(x)
+    out = torch.empty(B, Dm, dtype=x.dtype, device=x.device)
+    w32, b32 = _f32c(weight), _f32c(bias)
+    p = _lib.Conv1dUpdateParams(
+        batch=B, dim=Dm, width=width, io_dtype=_lib.io_dtype(x), silu=int(activation is not None),
+        x=ptr(x), x_batch_stride=x.stride(0), conv_state=ptr(conv_state), weight=ptr(w32),
+        bias=ptr(b32), out=ptr(out), out_batch_stride=out.stride(0))
+    _lib.call("mtts_causal_conv1d_update", p)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# selective scan
+# ------------------------------------------------------------------------------------------------
+def scan_num_chunks(seqlen):
+    return (seqlen + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+
+
+class _SelectiveScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state,
+                initial_state):
+        _lib.require_cuda(u, delta, A, B, C, D, z, delta_bias, initial_state)
+        if A.is_complex():
+            raise NotImplementedError("complex A is not on this path")
+        if B.dim() != 3 or C.dim() != 3:
+            raise NotImplementedError("only input-dependent (batch, dstate, seqlen) B and C")
+        batch, dim, L = u.shape
+        N = A.shape[1]
+        if A.shape[0] != dim or delta.shape != u.shape or B.shape != (batch, N, L) or \
+                C.shape != (batch, N, L):
+            raise RuntimeError("shape mismatch: u/delta (b,d,l), A (d,n), B/C (b,n,l)")
+        if N > _lib.MAX_DSTATE:
+            raise RuntimeError(f"selective_scan only supports state dimension <= {_lib.MAX_DSTATE}")
+        io = u.dtype
+        ctx.dtypes = tuple(None if t is None else t.dtype for t in (delta, A, B, C, D, z, delta_bias))
+        u = _unit_last_stride(u)
+        delta = _unit_last_stride(delta.to(io))
+        Bm = _unit_last_stride(B.to(io))
+        Cm = _unit_last_stride(C.to(io))
+        zz = None if z is None else _unit_last_stride(z.to(io))
+        A32, D32, db32 = _f32c(A), _f32c(D), _f32c(delta_bias)
+        h0 = _f32c(initial_state)
+        if h0 is not None and h0.shape != (batch, dim, N):
+            raise RuntimeError("initial_state must be (batch, dim, dstate)")
+
+        needs_grad = any(t is not None and t.requires_grad
+                         for t in (u, delta, A, B, C, D, z, delta_bias))
+        out = torch.empty((batch, dim, L), dtype=io, device=u.device)
+        last = torch.empty((batch, dim, N), dtype=torch.float32, device=u.device) \
+            if return_last_state else None
+        chk = torch.empty((batch, dim, max(scan_num_chunks(L), 1), N), dtype=torch.float32,
+                          device=u.device) if needs_grad else None
+        p = _lib.ScanFwdParams(
+            batch=batch, dim=dim, seqlen=L, dstate=N, io_dtype=_lib.io_dtype(u),
+            delta_softplus=int(bool(delta_softplus)),
+            u=ptr(u), u_batch_stride=u.stride(0), u_dim_stride=u.stride(1),
+            delta=ptr(delta), delta_batch_stride=delta.stride(0), delta_dim_stride=delta.stride(1),
+            A=ptr(A32),
+            B=ptr(Bm), B_batch_stride=Bm.stride(0), B_state_stride=Bm.stride(1),
+            C=ptr(Cm), C_batch_stride=Cm.stride(0), C_state_stride=Cm.stride(1),
+            D=ptr(D32), delta_bias=ptr(db32),
+            z=ptr(zz), z_batch_stride=0 if zz is None else zz.stride(0),
+            z_dim_stride=0 if zz is None else zz.stride(1),
+            initial_state=ptr(h0),
+            out=ptr(out), out_batch_stride=out.stride(0), out_dim_stride=out.stride(1),
+            last_state=ptr(last), checkpoints=ptr(chk))
+        _lib.call("mtts_selective_scan_fwd", p)
+
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.has = (D is not None, z is not None, delta_bias is not None)
+        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32, zz, db32, chk)
+        if return_last_state:
+            ctx.mark_non_differentiable(last)
+            return out, last
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        u, delta, A32, Bm, Cm, D32, zz, db32, chk = ctx.saved_tensors
+        batch, dim, L = u.shape
+        N = A32.shape[1]
+        dev = u.device
+        dout = _unit_last_stride(dout.to(u.dtype))
+        du = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
+        ddelta = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
+        dz = torch.empty((batch, dim, L), dtype=u.dtype, device=dev) if zz is not None else None
+        dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
+        dB = torch.zeros((batch, N, L), dtype=torch.float32, device=dev)
+        dC = torch.zeros((batch, N, L), dtype=torch.float32, device=dev)
+        dD = torch.zeros(dim, dtype=torch.float32, device=dev) if D32 is not None else None
+        ddb = torch.zeros(dim, dtype=torch.float32, device=dev) if db32 is not None else None
+        p = _lib.ScanBwdParams(
+            batch=batch, dim=dim, seqlen=L, dstate=N, io_dtype=_lib.io_dtype(u),
+            delta_softplus=int(ctx.delta_softplus),
+            u=ptr(u), u_batch_stride=u.stride(0), u_dim_stride=u.stride(1),
+            delta=ptr(delta), delta_batch_stride=delta.stride(0), delta_dim_stride=delta.stride(1),
+            A=ptr(A32),
+            B=ptr(Bm), B_batch_stride=Bm.stride(0), B_state_stride=Bm.stride(1),
+            C=ptr(Cm), C_batch_stride=Cm.stride(0), C_state_stride=Cm.stride(1),
+            D=ptr(D32), delta_bias=ptr(db32),
+            z=ptr(zz), z_batch_stride=0 if zz is None else zz.stride(0),
+            z_dim_stride=0 if zz is None else zz.stride(1),
+            dout=ptr(dout), dout_batch_stride=dout.stride(0), dout_dim_stride=dout.stride(1),
+            checkpoints=ptr(chk),
+            du=ptr(du), du_batch_stride=du.stride(0), du_dim_stride=du.stride(1),
+            ddelta=ptr(ddelta), ddelta_batch_stride=ddelta.stride(0),
+            ddelta_dim_stride=ddelta.stride(1),
+            dz=ptr(dz), dz_batch_stride=0 if dz is None else dz.stride(0),
+            dz_dim_stride=0 if dz is None else dz.stride(1),
+            dA=ptr(dA), dB=ptr(dB), dC=ptr(dC), dD=ptr(dD), ddelta_bias=ptr(ddb))
+        _lib.call("mtts_selective_scan_bwd", p)
+        t_delta, t_A, t_B, t_C, t_D, t_z, t_db = ctx.dtypes
+        return (du, ddelta.to(t_delta), dA.to(t_A), dB.to(t_B), dC.to(t_C),
+                None if dD is None else dD.to(t_D), None if dz is None else dz.to(t_z),
+                None if ddb is None else ddb.to(t_db), None, None, None)
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False, initial_state=None):
+    """Upstream signature (+ ``initial_state``, needed by the reference's stateful ``Mamba`` contract).
+
+    u, delta, z: (batch, dim, seqlen); A: (dim, dstate); B, C: (batch, dstate, seqlen);
+    D, delta_bias: (dim,).  Returns out [, last_state (batch, dim, dstate) fp32]."""
+    return _SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                  return_last_state, initial_state)
+
+
+def selective_state_update(state, x, dt, A, B, C, D=None, z=None, dt_bias=None, dt_softplus=False):
+    """state (batch, dim, dstate) fp32, updated IN PLACE; x, dt, z (batch, dim); A (dim, dstate);
+    B, C (batch, dstate); D, dt_bias (dim,).  Returns out (batch, dim)."""
+    _lib.require_cuda(state, x, dt, A, B, C, D, z, dt_bias)
+    if x.dim() != 2 or B.dim() != 2:
+        raise NotImplementedError("only the single-head (batch, dim) layout is on this path")
+    batch, dim = x.shape
+    N = A.shape[1]
+    if state.shape != (batch, dim, N) or state.dtype != torch.float32 or not state.is_contiguous():
+        raise RuntimeError("state must be contiguous fp32 (batch, dim, dstate)")
+    io = x.dtype
+    x, dt = _unit_last_stride(x), _unit_last_stride(dt.to(io))
+    Bm, Cm = _unit_last_stride(B.to(io)), _unit_last_stride(C.to(io))
+    zz = None if z is None else _unit_last_stride(z.to(io))
+    A32, D32, b32 = _f32c(A), _f32c(D), _f32c(dt_bias)
+    out = torch.empty(batch, dim, dtype=io, device=x.device)
+    p = _lib.StateUpdateParams(
+        batch=batch, dim=dim, dstate=N, io_dtype=_lib.io_dtype(x), dt_softplus=int(bool(dt_softplus)),
+        state=ptr(state), x=ptr(x), x_batch_stride=x.stride(0), dt=ptr(dt),
+        dt_batch_stride=dt.stride(0), A=ptr(A32), B=ptr(Bm), B_batch_stride=Bm.stride(0),
+        C=ptr(Cm), C_batch_stride=Cm.stride(0), D=ptr(D32), z=ptr(zz),
+        z_batch_stride=0 if zz is None else zz.stride(0), dt_bias=ptr(b32), out=ptr(out),
+        out_batch_stride=out.stride(0))
+    _lib.call("mtts_selective_state_update", p)
+    return out
+
+
+def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                   out_proj_weight, out_proj_bias, A, B=None, C=None, D=None, delta_bias=None,
+                   B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """Upstream's fused block body: conv -> x_proj -> dt_proj -> scan -> out_proj.
+    xz: (batch, 2*dim, seqlen).  The projections are library GEMMs; conv and scan are ours."""
+    if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
+        raise NotImplementedError("only input-dependent B and C")
+    x, z = xz.chunk(2, dim=1)
+    w2d = conv1d_weight.squeeze(1) if conv1d_weight.dim() == 3 else conv1d_weight
+    x = causal_conv1d_fn(x, w2d, conv1d_bias, activation="silu")
+    R = delta_proj_weight.shape[1]
+    N = A.shape[1]
+    x_dbl = torch.matmul(x_proj_weight.to(x.dtype), x)              # (batch, R + 2N, L)
+    delta = torch.matmul(delta_proj_weight.to(x.dtype), x_dbl[:, :R])
+    y = selective_scan_fn(x, delta, A, x_dbl[:, R:R + N], x_dbl[:, R + N:], D, z=z,
+                          delta_bias=delta_bias, delta_softplus=delta_softplus)
+    return F.linear(y.transpose(1, 2), out_proj_weight.to(y.dtype),
+                    None if out_proj_bias is None else out_proj_bias.to(y.dtype))
+
+
+# ------------------------------------------------------------------------------------------------
+# decode-step kernels (inference only)
+# ------------------------------------------------------------------------------------------------
+def mamba_decode_step(xz, conv_state, ssm_state, conv_weight, conv_bias, x_proj_w, dt_proj_w,
+                      dt_bias, A, D, out=None):
+    """The inner part of ``Mamba.step`` in one launch; both states updated IN PLACE.
+    xz (batch, 2*dim); conv_state (batch, dim, width) same dtype; ssm_state (batch, dim, dstate)
+    fp32; conv_weight (dim, width) / conv_bias / dt_bias / A / D fp32; x_proj_w (R + 2N, dim) and
+    dt_proj_w (dim, R) in xz's dtype.  Returns y (batch, dim)."""
+    _lib.require_cuda(xz, conv_state, ssm_state)
+    batch, two_dim = xz.shape
+    dim = two_dim // 2
+    N = ssm_state.shape[2]
+    R = dt_proj_w.shape[1]
+    width = conv_state.shape[2]
+    io = xz.dtype
+    for name, t, shape, dt in (("conv_state", conv_state, (batch, dim, width), io),
+                               ("ssm_state", ssm_state, (batch, dim, N), torch.float32),
+                               ("x_proj_w", x_proj_w, (R + 2 * N, dim), io),
+                               ("dt_proj_w", dt_proj_w, (dim, R), io),
+                               ("conv_weight", conv_weight, (dim, width), torch.float32),
+                               ("dt_bias", dt_bias, (dim,), torch.float32),
+                               ("A", A, (dim, N), torch.float32), ("D", D, (dim,), torch.float32)):
+        if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous {shape} {dt}, got {tuple(t.shape)} {t.dtype}")
+    xz = _unit_last_stride(xz)
+    y = out if out is not None else torch.empty(batch, dim, dtype=io, device=xz.device)
+    p = _lib.DecodeStepParams(
+        batch=batch, dim=dim, dstate=N, dt_rank=R, width=width, io_dtype=_lib.io_dtype(xz),
+        xz=ptr(xz), xz_batch_stride=xz.stride(0), conv_state=ptr(conv_state),
+        ssm_state=ptr(ssm_state), conv_weight=ptr(conv_weight), conv_bias=ptr(conv_bias),
+        x_proj_w=ptr(x_proj_w), dt_proj_w=ptr(dt_proj_w), dt_bias=ptr(dt_bias), A=ptr(A), D=ptr(D),
+        y=ptr(y), y_batch_stride=y.stride(0))
+    _lib.call("mtts_mamba_decode_step", p)
+    return y
+
+
+def cross_attn_decode(q, k, v, heads, mask=None, out=None):
+    """q (batch, d_model) projected, unscaled; k, v (batch, t_kv, d_model) contiguous;
+    mask (batch, t_kv) bool/uint8, True = attend.  Returns (batch, d_model)."""
+    _lib.require_cuda(q, k, v, mask)
+    batch, dm = q.shape
+    if k.shape != v.shape or k.shape[0] != batch or k.shape[2] != dm or dm % heads:
+        raise RuntimeError("k, v must be (batch, t_kv, d_model); d_model divisible by heads")
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise RuntimeError("q, k, v must be contiguous")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise RuntimeError("q, k, v must share a dtype")
+    m8 = None
+    if mask is not None:
+        m8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+    o = out if out is not None else torch.empty_like(q)
+    p = _lib.CrossAttnDecodeParams(batch=batch, heads=heads, head_dim=dm // heads, t_kv=k.shape[1],
+                                   io_dtype=_lib.io_dtype(q), q=ptr(q), k=ptr(k), v=ptr(v),
+                                   mask=ptr(m8), out=ptr(o))
+    _lib.call("mtts_cross_attn_decode", p)
+    return o
+
+
+def layernorm_film(x, ln_weight, ln_bias, eps=1e-5, residual=None, sum_out=None, gamma=None,
+                   beta=None, rows_per_batch=1, out=None):
+    """out = LN(x + residual) [* gamma_b + beta_b]; x (rows, dim) contiguous; gamma/beta
+    (rows / rows_per_batch, dim) fp32.  ``sum_out`` (may alias x) receives x + residual."""
+    _lib.require_cuda(x, ln_weight, ln_bias, residual, gamma, beta)
+    rows, dim = x.shape
+    if not x.is_contiguous() or (residual is not None and not residual.is_contiguous()):
+        raise RuntimeError("x and residual must be contiguous (rows, dim)")
+    o = out if out is not None else torch.empty_like(x)
+    p = _lib.LayerNormFilmParams(
+        rows=rows, dim=dim, rows_per_batch=rows_per_batch, io_dtype=_lib.io_dtype(x), eps=eps,
+        x=ptr(x), residual=ptr(residual), sum_out=ptr(sum_out), ln_weight=ptr(ln_weight),
+        ln_bias=ptr(ln_bias), film_gamma=ptr(gamma), film_beta=ptr(beta), out=ptr(o))
+    _lib.call("mtts_layernorm_film", p)
+    return o

@@ -1,0 +1,113 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; host-side logic."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+import mamba_tts_project_b200 as mt
+from mamba_tts_project_b200 import _lib
+from oracle.decoder_ref import MambaTTSDecoderRef
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mamba_tts_b200.h")).read()
+    return sorted(set(re.findall(r"\b(mtts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert set(syms) == set(_lib.ENTRY_POINTS), "python binding and header disagree on entry points"
+
+
+def test_struct_layouts_match_and_metadata():
+    lib = _lib.load()  # raises on any sizeof mismatch
+    assert lib.mtts_abi_version() == 1
+    assert lib.mtts_target_sm() == 100
+    assert lib.mtts_sizeof_params(len(_lib.PARAM_STRUCTS)) == -1
+    assert lib.mtts_error_string(2).decode().startswith("a dimension")
+    hdr = open(os.path.join(ROOT, "include", "mamba_tts_b200.h")).read()
+    assert f"#define MTTS_SCAN_CHUNK {_lib.SCAN_CHUNK}" in hdr
+    assert f"#define MTTS_MAX_DSTATE {_lib.MAX_DSTATE}" in hdr
+
+
+def test_argument_errors_need_no_gpu():
+    """Argument validation happens before any launch, so it is testable without a device."""
+    lib = _lib.load()
+    p = _lib.ScanFwdParams()  # all NULL
+    assert lib.mtts_selective_scan_fwd(ctypes.byref(p), None) == 1  # MTTS_ERR_NULL
+    c = _lib.Conv1dFwdParams(batch=1, dim=1, seqlen=1, width=7, x=1, weight=1, out=1)
+    assert lib.mtts_causal_conv1d_fwd(ctypes.byref(c), None) == 2   # MTTS_ERR_SHAPE
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing somewhere else."""
+    blk = mt.Mamba(32)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        blk(torch.randn(1, 4, 32))
+    with pytest.raises(RuntimeError, match="CUDA-only|no CPU path"):
+        mt.selective_scan_fn(torch.randn(1, 4, 8), torch.randn(1, 4, 8), -torch.rand(4, 2),
+                             torch.randn(1, 2, 8), torch.randn(1, 2, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mt.causal_conv1d_fn(torch.randn(1, 4, 8), torch.randn(4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mamba_tts_project_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./]", txt, re.M), \
+                    f"{f} reaches into the oracle"
+
+
+def test_state_dict_keys_match_reference_tree():
+    g = load_golden("oracle_decoder_small.pt")
+    dec = mt.MambaTTSDecoder(**g["config"])
+    ref = MambaTTSDecoderRef(**g["config"])
+    assert list(dec.state_dict().keys()) == list(ref.state_dict().keys())
+    res = dec.load_state_dict(g["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # the names SURVEY.md 8b lists for the reference module tree
+    keys = set(dec.state_dict())
+    for k in ["token_embed.weight", "pos_embed.weight", "quant_embed.weight",
+              "layers.0.norm_mamba.weight", "layers.0.mamba.in_proj.weight",
+              "layers.0.mamba.conv1d.weight", "layers.0.mamba.conv1d.bias",
+              "layers.0.mamba.x_proj.weight", "layers.0.mamba.dt_proj.weight",
+              "layers.0.mamba.dt_proj.bias", "layers.0.mamba.A_log", "layers.0.mamba.D",
+              "layers.0.mamba.out_proj.weight", "layers.0.cross_attn.in_proj_weight",
+              "layers.0.cross_attn.in_proj_bias", "layers.0.cross_attn.out_proj.weight",
+              "layers.0.cross_attn.out_proj.bias", "layers.0.ff.0.weight", "layers.0.ff.2.bias",
+              "layers.0.style_mlp.0.weight", "norm_out.bias", "head.weight"]:
+        assert k in keys
+    mha = torch.nn.MultiheadAttention(64, 4, batch_first=True)
+    assert set(mha.state_dict()) == {k.split("cross_attn.")[1] for k in keys
+                                     if k.startswith("layers.0.cross_attn.")}
+
+
+def test_mamba_init_matches_upstream_recipe():
+    torch.manual_seed(0)
+    m = mt.Mamba(64)
+    assert m.d_inner == 128 and m.dt_rank == 4 and m.d_state == 16 and m.d_conv == 4
+    assert torch.allclose(m.A_log[5], torch.log(torch.arange(1, 17.0)))
+    assert torch.all(m.D == 1)
+    dt = torch.nn.functional.softplus(m.dt_proj.bias)
+    assert dt.min() >= 1e-4 - 1e-7 and dt.max() <= 0.1 + 1e-6
+    assert m.dt_proj.weight.abs().max() <= 4 ** -0.5 + 1e-6
+
+
+def test_decoder_argument_errors_match_reference():
+    dec = mt.MambaTTSDecoder(16, d_model=32, n_layers=1, n_heads=2, d_ff=64, d_style=8, max_len=32)
+    with pytest.raises(ValueError, match="audio_tokens must be"):
+        dec(torch.zeros(3, dtype=torch.long), torch.randn(3, 2, 32), torch.randn(3, 8))
+    with pytest.raises(AssertionError, match="text_mask"):
+        dec(torch.zeros(3, 4, dtype=torch.long), torch.randn(3, 2, 32), torch.randn(3, 8),
+            text_mask=torch.ones(2, 2, dtype=torch.bool))

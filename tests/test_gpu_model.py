@@ -1,0 +1,195 @@
+"""GPU parity of the Mamba block and of the whole decoder (forward, backward, decode_step,
+generate) against the CPU oracle and the committed golden vectors."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle.decoder_ref import MambaTTSDecoderRef
+from oracle.mamba_ref import MambaRef
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+def check(name, got, ref, t):
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got.float()).all(), f"{name}: non-finite values"
+    e = rel_err(got, ref)
+    assert e < t, f"{name}: rel err {e:.3e} >= {t:.1e}"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def test_block_forward_backward_golden():
+    from mamba_tts_project_b200 import Mamba
+    g = load_golden("oracle_block_d64.pt")
+    blk = Mamba(64).cuda()
+    blk.load_state_dict(g["state_dict"])
+    h = g["input"].cuda().requires_grad_()
+    out, (cs, ss) = blk(h)
+    check("out", out, g["out"], FP32_TOL)
+    check("conv_state", cs, g["conv_state"], 1e-6)
+    check("ssm_state", ss, g["ssm_state"], FP32_TOL)
+    params = dict(blk.named_parameters())
+    grads = torch.autograd.grad(out, [h] + list(params.values()), g["dout"].cuda())
+    check("dinput", grads[0], g["dinput"], FP32_TOL)
+    for (k, _), gr in zip(params.items(), grads[1:]):
+        check("d" + k, gr, g["dparams"][k], 2e-4)
+
+
+def test_block_matches_hf_pin_directly():
+    """The CUDA block against the independent HF MambaMixer vectors (not via the oracle)."""
+    from mamba_tts_project_b200 import Mamba
+    for name in ("hf_mixer_d64.pt", "hf_mixer_d128_n64.pt"):
+        g = load_golden(name)
+        blk = Mamba(g["d_model"], d_state=g["d_state"]).cuda()
+        blk.load_state_dict(g["state_dict"])
+        with torch.no_grad():
+            out, _ = blk(g["input"].cuda())
+        check(name, out, g["output"], FP32_TOL)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_block_step_and_continue_vs_oracle(dtype):
+    from mamba_tts_project_b200 import Mamba
+    torch.manual_seed(3)
+    ref = MambaRef(128).eval()
+    with torch.no_grad():
+        ref.A_log.add_(0.2 * torch.randn_like(ref.A_log))
+        if dtype != torch.float32:  # same rounded weights on both sides
+            for p in ref.parameters():
+                if p.dim() > 1:
+                    p.copy_(p.to(dtype).float())
+    blk = Mamba(128).cuda()
+    blk.load_state_dict(ref.state_dict())
+    blk = blk.to(dtype) if dtype != torch.float32 else blk
+    h = torch.randn(3, 45, 128).to(dtype).float()
+    with torch.no_grad():
+        full_ref, (cs_ref, ss_ref) = ref(h)
+        hg = h.cuda().to(dtype)
+        o1, st = blk(hg[:, :24])                  # prompt
+        o2, st = blk(hg[:, 24:33], st)            # continue, T > 1
+        outs = [o1, o2]
+        for t in range(33, 45):                   # single steps (fused kernel), states in place
+            o, st = blk(hg[:, t:t + 1], st)
+            outs.append(o)
+        got = torch.cat(outs, 1)
+    t = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    check("prompt+continue+steps", got, full_ref, t)
+    check("ssm_state", st[1], ss_ref, t)
+    check("conv_state", st[0], cs_ref, t)
+
+
+def _make_pair(cfg, seed, dtype=torch.float32):
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    torch.manual_seed(seed)
+    ref = MambaTTSDecoderRef(**cfg).eval()
+    with torch.no_grad():
+        for layer in ref.layers:
+            layer.mamba.A_log.add_(0.2 * torch.randn_like(layer.mamba.A_log))
+    dec = MambaTTSDecoder(**cfg).cuda().eval()
+    dec.load_state_dict(ref.state_dict())
+    return ref, dec
+
+
+def test_decoder_golden_logits_and_greedy_ids():
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    g = load_golden("oracle_decoder_small.pt")
+    dec = MambaTTSDecoder(**g["config"]).cuda().eval()
+    dec.load_state_dict(g["state_dict"])
+    c = lambda k: g[k].cuda()
+    with torch.no_grad():
+        logits = dec(c("tokens"), c("text_hidden"), c("z_style"), text_mask=c("text_mask"),
+                     ref_hidden=c("ref_hidden"))
+    check("logits", logits, g["logits"], FP32_TOL)
+    # reference-signature decode_step loop: identical greedy ids on the fp32 path
+    tok = torch.ones(2, 1, dtype=torch.long, device="cuda")
+    states, ids, lgs = None, [], []
+    for i in range(24):
+        lg, states = dec.decode_step(tok, c("text_hidden"), c("z_style"), states, i,
+                                     text_mask=c("text_mask"), ref_hidden=c("ref_hidden"))
+        assert lg.shape == (2, 1, 64) and len(states) == 2
+        tok = lg.argmax(-1)
+        ids.append(tok)
+        lgs.append(lg)
+    check("step logits", torch.cat(lgs, 1), g["step_logits"], FP32_TOL)
+    assert torch.equal(torch.cat(ids, 1).cpu(), g["greedy_ids"]), "greedy ids differ on the fp32 path"
+    # generate(): eager and CUDA-graph replay give the same ids
+    for graph in (False, True):
+        out = dec.generate(torch.ones(2, 1, dtype=torch.long, device="cuda"), 24, c("text_hidden"),
+                           c("z_style"), text_mask=c("text_mask"), ref_hidden=c("ref_hidden"),
+                           use_cuda_graph=graph)
+        assert torch.equal(out.cpu(), g["greedy_ids"]), f"generate(use_cuda_graph={graph}) ids differ"
+
+
+def test_decoder_c1_config_forward_backward_vs_oracle():
+    """BASELINE config C1: 2 layers, d_model 256, d_state 16, expand 2, B 2, T 512, T_text 64."""
+    cfg = dict(vocab_size_audio=1024, d_model=256, n_layers=2, n_heads=8, d_ff=2048, d_style=256,
+               max_len=8192, num_quantizers=1)
+    ref, dec = _make_pair(cfg, seed=0)
+    torch.manual_seed(1)
+    tokens = torch.randint(0, 1024, (2, 512))
+    text = torch.randn(2, 64, 256)
+    z = torch.randn(2, 256)
+    target = torch.randint(0, 1024, (2, 512))
+    lr = ref(tokens, text, z)
+    loss_r = torch.nn.functional.cross_entropy(lr.reshape(-1, 1024), target.reshape(-1))
+    loss_r.backward()
+    lg = dec(tokens.cuda(), text.cuda(), z.cuda())
+    check("C1 logits", lg, lr, FP32_TOL)
+    loss_g = torch.nn.functional.cross_entropy(lg.reshape(-1, 1024), target.cuda().reshape(-1))
+    loss_g.backward()
+    assert abs(loss_g.item() - loss_r.item()) < 1e-4 * abs(loss_r.item())
+    pr = dict(ref.named_parameters())
+    worst = 0.0
+    for k, p in dec.named_parameters():
+        if pr[k].grad is None:
+            assert p.grad is None or p.grad.abs().max() == 0, k
+            continue
+        e = rel_err(p.grad, pr[k].grad)
+        worst = max(worst, e)
+        assert e < 5e-4, f"grad {k}: rel err {e:.3e}"
+    # bf16 autocast path (C2's precision mode) stays within the bf16 tolerance of the fp32 oracle
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        lb = dec(tokens.cuda(), text.cuda(), z.cuda())
+    check("C1 logits bf16 autocast", lb.float(), lr.detach(), 3e-2)
+
+
+def test_decoder_bf16_decode_tracks_fp32():
+    cfg = dict(vocab_size_audio=256, d_model=128, n_layers=3, n_heads=8, d_ff=256, d_style=64,
+               max_len=512, num_quantizers=1)
+    ref, dec = _make_pair(cfg, seed=5)
+    torch.manual_seed(2)
+    text, z = torch.randn(4, 20, 128), torch.randn(4, 64)
+    tok0 = torch.randint(0, 256, (4, 1))
+    with torch.no_grad():
+        states, tok, ref_lg = None, tok0, []
+        toks = [tok0]
+        for i in range(12):
+            lg, states = ref.decode_step(tok, text, z, states, i)
+            tok = lg.argmax(-1)
+            toks.append(tok)
+            ref_lg.append(lg)
+        ctx = dec.prepare_generation(text.cuda(), z.cuda(), dtype=torch.bfloat16)
+        st = dec.allocate_states(4, torch.bfloat16)
+        got = []
+        for i in range(12):  # teacher-forced on the oracle's tokens so the comparison is per step
+            x = ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]
+            got.append(dec._step_core(ctx, x.contiguous(), st)[:, None])
+    check("bf16 step logits", torch.cat(got, 1), torch.cat(ref_lg, 1), 4e-2)
+
+
+def test_decoder_multi_quantizer_tokens():
+    cfg = dict(vocab_size_audio=32, d_model=64, n_layers=1, n_heads=4, d_ff=64, d_style=16,
+               max_len=64, num_quantizers=3)
+    ref, dec = _make_pair(cfg, seed=9)
+    tok = torch.randint(0, 32, (2, 3, 8))
+    text, z = torch.randn(2, 5, 64), torch.randn(2, 16)
+    with torch.no_grad():
+        check("3-D tokens", dec(tok.cuda(), text.cuda(), z.cuda()), ref(tok, text, z), FP32_TOL)
