@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the MambaTTSDecoder hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload at every N: BASELINE.json configs[1] ("C2"): 12-layer d_model 512 MambaTTSDecoder, bf16
+(fp32 master weights, bf16 activations/GEMMs, fp32 scan state), teacher-forced forward + backward,
+B = 16 per GPU, T_audio 2048, T_text 256, cross-attn + FiLM.  N > 1 is batch-sharded data
+parallelism (weak scaling: 16 samples per GPU) with a bucketed NCCL gradient all-reduce overlapped
+with backward.  A "step" = forward + loss + backward (+ all-reduce) over one batch.
+
+One JSON line on stdout (rank 0).  Besides the contract keys it carries
+  roofline      the dominant hand-written kernel (selective-scan backward) against the measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference path) timed on this box's host cores
+  e2e           same metric through the public API with host (pinned) inputs copied in every step
+  extra         the other two headline quantities of BASELINE.json's metric: isolated scan GB/s
+                (config C4) and decode_step tokens/s (config C3)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(vocab=1024, d_model=512, n_layers=12, n_heads=8, d_ff=2048, d_style=256, d_state=16,
+          batch=16, t_audio=2048, t_text=256)
+METRIC = "decoder_train_tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def make_inputs(cfg, batch, device, pinned=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    t = dict(
+        tokens=torch.randint(0, cfg["vocab"], (batch, cfg["t_audio"]), generator=g),
+        targets=torch.randint(0, cfg["vocab"], (batch, cfg["t_audio"]), generator=g),
+        text=torch.randn(batch, cfg["t_text"], cfg["d_model"], generator=g),
+        z=torch.randn(batch, cfg["d_style"], generator=g))
+    if pinned:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(device) for k, v in t.items()}
+
+
+def build_decoder(cfg, device):
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    torch.manual_seed(0)
+    return MambaTTSDecoder(cfg["vocab"], d_model=cfg["d_model"], n_layers=cfg["n_layers"],
+                           n_heads=cfg["n_heads"], d_ff=cfg["d_ff"], d_style=cfg["d_style"],
+                           max_len=8192, num_quantizers=1, d_state=cfg["d_state"]).to(device)
+
+
+def train_step(model, inp, reducer=None):
+    model.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = model(inp["tokens"], inp["text"], inp["z"])
+    loss = F.cross_entropy(logits.float().view(-1, logits.shape[-1]), inp["targets"].view(-1))
+    loss.backward()
+    if reducer is not None:
+        reducer.finish()
+    return loss
+
+
+def scan_alg_bytes(B, Di, T, N, e, bwd):
+    fwd = e * (4 * B * Di * T + 2 * B * N * T) + 4 * (Di * N + 2 * Di)
+    if not bwd:
+        return fwd
+    return (e * (4 * B * Di * T + 2 * B * N * T) + e * 3 * B * Di * T + 4 * 2 * B * N * T
+            + 4 * (2 * Di * N + 4 * Di))
+
+
+def conv_alg_bytes(B, Di, T, e, bwd):
+    return e * (4 if bwd else 2) * B * Di * T
+
+
+# ---------------------------------------------------------------------------------------------
+# extras: isolated scan (C4) and decode (C3)
+# ---------------------------------------------------------------------------------------------
+def extra_scan(peak):
+    from mamba_tts_project_b200 import selective_scan_fn
+    dev, dt = "cuda", torch.bfloat16
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for N in (16, 64):
+        B, Di, T = 32, 2048, 4096
+        u = torch.randn(B, Di, T, device=dev, dtype=dt).requires_grad_()
+        delta = (0.5 * torch.rand(B, Di, T, device=dev)).to(dt).requires_grad_()
+        A = (-0.5 * torch.rand(Di, N, device=dev)).requires_grad_()
+        Bm = torch.randn(B, N, T, device=dev, dtype=dt).requires_grad_()
+        Cm = torch.randn(B, N, T, device=dev, dtype=dt).requires_grad_()
+        D = torch.randn(Di, device=dev).requires_grad_()
+        z = torch.randn(B, Di, T, device=dev, dtype=dt).requires_grad_()
+        bias = (0.5 * torch.rand(Di, device=dev)).requires_grad_()
+        dout = torch.randn(B, Di, T, device=dev, dtype=dt)
+        from mamba_tts_project_b200 import _lib
+        hook = {"mtts_selective_scan_fwd": [], "mtts_selective_scan_bwd": []}
+        for it in range(3 + 5):
+            if it == 3:
+                _lib.event_hook = hook
+            flush.zero_()
+            y = selective_scan_fn(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias, delta_softplus=True)
+            flush.zero_()
+            torch.autograd.grad(y, [u, delta, A, Bm, Cm, D, z, bias], dout)
+        torch.cuda.synchronize()
+        _lib.event_hook = {}
+        for name, bwd in (("mtts_selective_scan_fwd", False), ("mtts_selective_scan_bwd", True)):
+            ms = statistics.median(a.elapsed_time(b) for a, b in hook[name])
+            gbs = scan_alg_bytes(B, Di, T, N, 2, bwd) / ms / 1e6
+            out[f"scan_{'bwd' if bwd else 'fwd'}_N{N}"] = {
+                "ms": round(ms, 4), "GBs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
+                "state_updates_per_s": round(B * Di * T * N / ms * 1e3, -6)}
+        del u, delta, Bm, Cm, z, dout, y
+    out["shape"] = "C4: d_inner 2048, B*T = 32*4096, bf16, L2 flushed between launches"
+    return out
+
+
+def extra_decode(cfg, steps=256):
+    model = build_decoder(cfg, "cuda").eval()
+    B = 64
+    g = torch.Generator().manual_seed(1)
+    text = torch.randn(B, cfg["t_text"], cfg["d_model"], generator=g).cuda()
+    z = torch.randn(B, cfg["d_style"], generator=g).cuda()
+    first = torch.ones(B, 1, dtype=torch.long, device="cuda")
+    from mamba_tts_project_b200 import _lib
+    res = {}
+    for name, dt in (("bf16", torch.bfloat16),):
+        model.generate(first, 8, text, z, dtype=dt)  # warm-up (captures its own graph)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count
+        t0 = time.perf_counter()
+        toks = model.generate(first, steps, text, z, dtype=dt)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        res[name] = {"tokens_per_s": round(B * steps / dtm, 1), "ms_per_step": round(dtm / steps * 1e3, 4),
+                     "steps": steps, "batch": B, "includes": "K/V + FiLM precompute, graph capture",
+                     "captured_launches_per_step": (_lib.launch_count - n0)}
+    del model
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (port of the reference path) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_tokens_per_s(cfg, steps, warmup, t_sample, batch=1):
+    from oracle.decoder_ref import MambaTTSDecoderRef
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    dec = MambaTTSDecoderRef(cfg["vocab"], d_model=cfg["d_model"], n_layers=cfg["n_layers"],
+                             n_heads=cfg["n_heads"], d_ff=cfg["d_ff"], d_style=cfg["d_style"],
+                             max_len=8192, num_quantizers=1, d_state=cfg["d_state"])
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, cfg["vocab"], (batch, t_sample), generator=g)
+    tgt = torch.randint(0, cfg["vocab"], (batch, t_sample), generator=g)
+    text = torch.randn(batch, cfg["t_text"], cfg["d_model"], generator=g)
+    z = torch.randn(batch, cfg["d_style"], generator=g)
+
+    def step():
+        dec.zero_grad(set_to_none=True)
+        lg = dec(tok, text, z)
+        F.cross_entropy(lg.view(-1, lg.shape[-1]), tgt.view(-1)).backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    sample = (f"oracle (fp32 port of mamba_decoder.py + selective_scan_ref), same {cfg['n_layers']}-layer "
+              f"d{cfg['d_model']} model, B={batch} T_audio={t_sample} T_text={cfg['t_text']}, fwd+bwd, "
+              f"{steps} steps of {dt:.2f}s")
+    return batch * t_sample / dt, dt, cores, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    warm = min(args.warmup, 1)
+    tps, dt, cores, sample = cpu_oracle_tokens_per_s(C2, steps, warm, t_sample=64)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(tps, 2), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2: 12-layer d_model 512 MambaTTSDecoder fwd+bwd, T_text 256 "
+                               "(CPU reference path on a bounded sample: B=1, T_audio=64 per step)"},
+        "cpu_baseline": {"value": round(tps, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(tps, 2), "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from mamba_tts_project_b200 import _lib
+    from mamba_tts_project_b200.dp import GradAllReducer, broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU path for the product")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    cfg = C2
+    B, T = cfg["batch"], cfg["t_audio"]
+    peak, peak_src = measured_peaks()
+
+    model = build_decoder(cfg, dev).train()
+    reducer = None
+    if world > 1:
+        broadcast_parameters(model)
+        reducer = GradAllReducer(model, bucket_bytes=32 << 20)
+    inp = make_inputs(cfg, B, dev, seed=rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(model, inp, reducer)
+    barrier()
+
+    # ---- device-timed region: inputs resident in HBM ----
+    hook = {"mtts_selective_scan_fwd": [], "mtts_selective_scan_bwd": [],
+            "mtts_causal_conv1d_fwd": [], "mtts_causal_conv1d_bwd": []}
+    _lib.event_hook = hook
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(model, inp, reducer)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    _lib.event_hook = {}
+    launches = _lib.launch_count - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = tms.item()
+    value = world * B * T / ms * 1e3
+
+    # ---- per-kernel roofline from the events recorded inside the timed region ----
+    Di, N, e = 2 * cfg["d_model"], cfg["d_state"], 2
+    kern = {}
+    for name, recs in hook.items():
+        if recs:
+            kern[name] = statistics.mean(a.elapsed_time(b) for a, b in recs)
+    alg = {"mtts_selective_scan_fwd": scan_alg_bytes(B, Di, T, N, e, False),
+           "mtts_selective_scan_bwd": scan_alg_bytes(B, Di, T, N, e, True),
+           "mtts_causal_conv1d_fwd": conv_alg_bytes(B, Di, T, e, False),
+           "mtts_causal_conv1d_bwd": conv_alg_bytes(B, Di, T, e, True)}
+    dom = max(kern, key=lambda k: kern[k])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    ach = alg[dom] / kern[dom] / 1e6
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": round(kern[dom], 4),
+                "launches_per_step": len(hook[dom]) // args.steps,
+                "share_of_step": round(kern[dom] * (len(hook[dom]) / args.steps) / ms, 4),
+                "co_bound": "SIMT issue / MUFU.EX2 (16 per clk per SM): one exp per (b, d, t, n) state "
+                            "update; see DESIGN.md",
+                "state_updates_per_s": round(B * Di * T * N / kern[dom] * 1e3, -6),
+                "others": {k: {"ms_per_launch": round(v, 4), "GBs": round(alg[k] / v / 1e6, 1),
+                               "frac": round(alg[k] / v / 1e6 / peak, 4),
+                               "share_of_step": round(v * (len(hook[k]) / args.steps) / ms, 4)}
+                           for k, v in kern.items() if k != dom}}
+
+    # ---- e2e: public API, host (pinned) inputs copied in every step, loss read back ----
+    pinned = make_inputs(cfg, B, dev, pinned=True, seed=rank)
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_inp = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        loss_val = train_step(model, dev_inp, reducer).item()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": round(world * B * T / e2e_s.item(), 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_s.item() * 1e3, 3),
+           "api": "MambaTTSDecoder.forward + cross_entropy + backward, pinned host inputs"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "C2: 12-layer d_model 512 MambaTTSDecoder, bf16 autocast, teacher-forced "
+                               "fwd+bwd, B=16 per GPU, T_audio=2048, T_text=256, cross-attn + FiLM",
+                   "global_batch": world * B, "seq_len": T, "d_state": N, "vocab": cfg["vocab"],
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "working set (>10 GB of activations per step) is far larger than the 126 MB L2",
+                   "loss": round(float(loss_val), 4)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        del model, inp
+        torch.cuda.empty_cache()
+        extra = {}
+        try:
+            extra["scan_isolated"] = extra_scan(peak)
+        except Exception as ex:  # extras never invalidate the headline line
+            extra["scan_isolated"] = {"error": repr(ex)}
+        try:
+            extra["decode_c3"] = extra_decode(cfg)
+        except Exception as ex:
+            extra["decode_c3"] = {"error": repr(ex)}
+        line["extra"] = extra
+        tps, dt, cores, sample = cpu_oracle_tokens_per_s(cfg, steps=2, warmup=1, t_sample=128)
+        line["cpu_baseline"] = {"value": round(tps, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

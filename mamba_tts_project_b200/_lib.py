@@ -122,6 +122,9 @@ ENTRY_POINTS = {
 
 _lib = None
 launch_count = 0  # kernels launched through this binding (bench.py's ``gpu_launches``)
+# bench.py only: {entry point name: [(start_event, end_event), ...]} -- when a name is present, every
+# call of that entry point is bracketed by CUDA events on the launching stream.
+event_hook = {}
 
 
 def load():
@@ -177,7 +180,15 @@ def call(name: str, params) -> None:
     global launch_count
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream
+    rec = event_hook.get(name) if event_hook else None
+    if rec is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(C.byref(params), C.c_void_p(stream))
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.mtts_error_string(rc).decode()}")
+    if rec is not None:
+        ev1.record()
+        rec.append((ev0, ev1))
     launch_count += 1

@@ -62,6 +62,12 @@ class _CausalConv1dFn(torch.autograd.Function):
                 raise RuntimeError("initial_states must be (batch, dim, width - 1)")
         out = torch.empty_like(x, memory_format=torch.contiguous_format)
         B, Dm, L = x.shape
+        ctx.save_for_backward(x, w32, b32, init)
+        ctx.activation = activation
+        ctx.wdtype = weight.dtype
+        ctx.bdtype = None if bias is None else bias.dtype
+        if x.numel() == 0:  # empty input: nothing to launch (data_ptr() would be NULL)
+            return out
         p = _lib.Conv1dFwdParams(
             batch=B, dim=Dm, seqlen=L, width=weight.shape[1], io_dtype=_lib.io_dtype(x),
             silu=int(activation is not None), x=ptr(x), x_batch_stride=x.stride(0),
@@ -70,10 +76,6 @@ class _CausalConv1dFn(torch.autograd.Function):
             init_dim_stride=0 if init is None else init.stride(1),
             out=ptr(out), out_batch_stride=out.stride(0), out_dim_stride=out.stride(1))
         _lib.call("mtts_causal_conv1d_fwd", p)
-        ctx.save_for_backward(x, w32, b32, init)
-        ctx.activation = activation
-        ctx.wdtype = weight.dtype
-        ctx.bdtype = None if bias is None else bias.dtype
         return out
 
     @staticmethod
@@ -84,6 +86,9 @@ class _CausalConv1dFn(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=torch.contiguous_format)
         dw = torch.zeros_like(w32)
         db = torch.zeros(Dm, dtype=torch.float32, device=x.device)
+        if x.numel() == 0:
+            return (dx, dw.to(ctx.wdtype), None if ctx.bdtype is None else db.to(ctx.bdtype),
+                    None, None)
         p = _lib.Conv1dBwdParams(
             batch=B, dim=Dm, seqlen=L, width=w32.shape[1], io_dtype=_lib.io_dtype(x),
             silu=int(ctx.activation is not None), x=ptr(x), x_batch_stride=x.stride(0),
@@ -183,6 +188,14 @@ class _SelectiveScanFn(torch.autograd.Function):
             if return_last_state else None
         chk = torch.empty((batch, dim, max(scan_num_chunks(L), 1), N), dtype=torch.float32,
                           device=u.device) if needs_grad else None
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32, zz, db32, chk)
+        if u.numel() == 0:  # empty input: the state passes through, nothing to launch
+            if return_last_state:
+                last = h0.clone() if h0 is not None else last.zero_()
+                ctx.mark_non_differentiable(last)
+                return out, last
+            return out
         p = _lib.ScanFwdParams(
             batch=batch, dim=dim, seqlen=L, dstate=N, io_dtype=_lib.io_dtype(u),
             delta_softplus=int(bool(delta_softplus)),
@@ -198,10 +211,6 @@ class _SelectiveScanFn(torch.autograd.Function):
             out=ptr(out), out_batch_stride=out.stride(0), out_dim_stride=out.stride(1),
             last_state=ptr(last), checkpoints=ptr(chk))
         _lib.call("mtts_selective_scan_fwd", p)
-
-        ctx.delta_softplus = bool(delta_softplus)
-        ctx.has = (D is not None, z is not None, delta_bias is not None)
-        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32, zz, db32, chk)
         if return_last_state:
             ctx.mark_non_differentiable(last)
             return out, last
@@ -222,6 +231,11 @@ class _SelectiveScanFn(torch.autograd.Function):
         dC = torch.zeros((batch, N, L), dtype=torch.float32, device=dev)
         dD = torch.zeros(dim, dtype=torch.float32, device=dev) if D32 is not None else None
         ddb = torch.zeros(dim, dtype=torch.float32, device=dev) if db32 is not None else None
+        t_delta, t_A, t_B, t_C, t_D, t_z, t_db = ctx.dtypes
+        if u.numel() == 0:
+            return (du, ddelta.to(t_delta), dA.to(t_A), dB.to(t_B), dC.to(t_C),
+                    None if dD is None else dD.to(t_D), None if dz is None else dz.to(t_z),
+                    None if ddb is None else ddb.to(t_db), None, None, None)
         p = _lib.ScanBwdParams(
             batch=batch, dim=dim, seqlen=L, dstate=N, io_dtype=_lib.io_dtype(u),
             delta_softplus=int(ctx.delta_softplus),
@@ -242,7 +256,6 @@ class _SelectiveScanFn(torch.autograd.Function):
             dz_dim_stride=0 if dz is None else dz.stride(1),
             dA=ptr(dA), dB=ptr(dB), dC=ptr(dC), dD=ptr(dD), ddelta_bias=ptr(ddb))
         _lib.call("mtts_selective_scan_bwd", p)
-        t_delta, t_A, t_B, t_C, t_D, t_z, t_db = ctx.dtypes
         return (du, ddelta.to(t_delta), dA.to(t_A), dB.to(t_B), dC.to(t_C),
                 None if dD is None else dD.to(t_D), None if dz is None else dz.to(t_z),
                 None if ddb is None else ddb.to(t_db), None, None, None)
