@@ -266,26 +266,51 @@ typedef struct {
 int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * layernorm_film -- LayerNorm (eps 1e-5, affine) optionally followed by FiLM and optionally
- * preceded by a residual add; the memory-bound glue of mamba_decoder.py:59,67,81-86.
- *   s   = x + residual          (residual optional; s is written to sum_out when non-NULL)
- *   out = LN(s) * gamma_b + beta_b     (gamma/beta (batch, dim) optional FiLM terms, fp32)
- * x, residual, sum_out, out: (rows, dim) contiguous io dtype, rows = batch * rows_per_batch.
+ * add_layernorm_fwd / add_layernorm_bwd -- residual add + LayerNorm (eps, affine) + optional FiLM:
+ * the memory-bound glue of mamba_decoder.py:59,64,67,78,81-86,89 in one pass per tensor.
+ *   x_out = x + delta                 (x, x_out: fp32 residual stream; delta: io dtype, optional)
+ *   out   = LN(x_out) * w + b ; out = gamma_b * out + beta_b   (gamma/beta (batch, dim) fp32, optional)
+ * rows = batch * rows_per_batch; all (rows, dim) tensors contiguous; dim % 4 == 0, dim <= 2048
+ * (backward: dim <= 1024).  x_out may alias x.  mean / rstd (rows) fp32 are saved for the backward.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t rows, dim, rows_per_batch;
   int32_t io_dtype;
   float eps;
-  const void* x;
-  const void* residual; /* or NULL */
-  void* sum_out;        /* or NULL */
+  const float* x;
+  const void* delta; /* or NULL */
+  float* x_out;      /* or NULL (then x_out == x is implied and nothing is written) */
   const float* ln_weight;
   const float* ln_bias;
-  const float* film_gamma; /* (rows / rows_per_batch, dim) or NULL */
+  const float* film_gamma; /* both or neither */
   const float* film_beta;
   void* out;
-} mtts_layernorm_film_params;
-int mtts_layernorm_film(const mtts_layernorm_film_params* p, mtts_stream_t stream);
+  float* mean; /* or NULL */
+  float* rstd; /* or NULL */
+} mtts_add_layernorm_fwd_params;
+int mtts_add_layernorm_fwd(const mtts_add_layernorm_fwd_params* p, mtts_stream_t stream);
+
+/* Backward of the above.  dout (io dtype) = grad of `out`; dx_out (fp32, optional) = grad that
+ * reaches x_out from the rest of the residual stream.  Writes dx (fp32) = grad of x, and ddelta
+ * (io dtype, optional) = the same values for the branch.  colsum (batch, 2, dim) fp32 is ACCUMULATED
+ * INTO with S1 = sum_t dout * xhat and S2 = sum_t dout per batch element; the parameter gradients
+ * are linear combinations of S1/S2 the caller forms on (batch, dim)-sized tensors:
+ *   dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b, dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b. */
+typedef struct {
+  int32_t rows, dim, rows_per_batch;
+  int32_t io_dtype;
+  const float* x_out;
+  const float* mean;
+  const float* rstd;
+  const float* ln_weight;
+  const float* film_gamma; /* or NULL */
+  const void* dout;
+  const float* dx_out; /* or NULL */
+  float* dx;
+  void* ddelta; /* or NULL */
+  float* colsum;
+} mtts_add_layernorm_bwd_params;
+int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -94,14 +94,18 @@ CrossAttnDecodeParams = _struct("CrossAttnDecodeParams", """
     i:batch i:heads i:head_dim i:t_kv i:io_dtype
     p:q p:k p:v p:mask p:out""")
 
-LayerNormFilmParams = _struct("LayerNormFilmParams", """
+AddLayerNormFwdParams = _struct("AddLayerNormFwdParams", """
     i:rows i:dim i:rows_per_batch i:io_dtype f:eps
-    p:x p:residual p:sum_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:out""")
+    p:x p:delta p:x_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:out p:mean p:rstd""")
+
+AddLayerNormBwdParams = _struct("AddLayerNormBwdParams", """
+    i:rows i:dim i:rows_per_batch i:io_dtype
+    p:x_out p:mean p:rstd p:ln_weight p:film_gamma p:dout p:dx_out p:dx p:ddelta p:colsum""")
 
 # declaration order of the header == argument of mtts_sizeof_params
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
-                 LayerNormFilmParams]
+                 AddLayerNormFwdParams, AddLayerNormBwdParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -117,7 +121,8 @@ ENTRY_POINTS = {
     "mtts_selective_state_update": StateUpdateParams,
     "mtts_mamba_decode_step": DecodeStepParams,
     "mtts_cross_attn_decode": CrossAttnDecodeParams,
-    "mtts_layernorm_film": LayerNormFilmParams,
+    "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
+    "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
 }
 
 _lib = None

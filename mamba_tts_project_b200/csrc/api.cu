@@ -32,7 +32,8 @@ extern "C" int mtts_sizeof_params(int which) {
     case 5: return (int)sizeof(mtts_state_update_params);
     case 6: return (int)sizeof(mtts_decode_step_params);
     case 7: return (int)sizeof(mtts_cross_attn_decode_params);
-    case 8: return (int)sizeof(mtts_layernorm_film_params);
+    case 8: return (int)sizeof(mtts_add_layernorm_fwd_params);
+    case 9: return (int)sizeof(mtts_add_layernorm_bwd_params);
     default: return -1;
   }
 }

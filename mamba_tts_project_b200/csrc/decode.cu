@@ -2,7 +2,6 @@
 //   mtts_selective_state_update -- replaces mamba_ssm's Triton selective_state_update
 //   mtts_mamba_decode_step      -- conv-update + x_proj + dt_proj + state update + gate, ONE launch
 //   mtts_cross_attn_decode      -- 1-query attention against the cached K/V of [ref || text]
-//   mtts_layernorm_film         -- residual add + LayerNorm + FiLM glue
 // All reached from MambaTTSDecoder.decode_step (mamba_decoder.py:188-256) -> layer (:59-89).
 #include <cooperative_groups.h>
 
@@ -171,12 +170,13 @@ __global__ void __launch_bounds__(kStepThreads) decode_step_kernel(const mtts_de
 
 // ------------------------------------------------------------------------------------------------
 // Cross-attention for one query token per batch element.  CTA = (batch, head).
+// Generic fallback (any head_dim); the vectorised kernel below is the hot one.
 // ------------------------------------------------------------------------------------------------
 constexpr int kAttnThreads = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(kAttnThreads)
-cross_attn_decode_kernel(const mtts_cross_attn_decode_params p) {
+cross_attn_decode_generic_kernel(const mtts_cross_attn_decode_params p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int kWarps = kAttnThreads / 32;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -246,55 +246,137 @@ cross_attn_decode_kernel(const mtts_cross_attn_decode_params p) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// (residual add) + LayerNorm + (FiLM): one warp per row.
-// ------------------------------------------------------------------------------------------------
+// Vectorised variant: head_dim = kLPR * (16 bytes of T); a group of kLPR lanes reads one K/V row with
+// one 16-byte load each, so a warp load instruction covers 32 / kLPR whole rows (full sectors).
+constexpr int kAttnVecThreads = 128;
+
+template <typename T, int kLPR>
+__global__ void __launch_bounds__(kAttnVecThreads)
+cross_attn_decode_vec_kernel(const mtts_cross_attn_decode_params p) {
+  constexpr int VE = Io<T>::kVecElems;
+  constexpr int kWarps = kAttnVecThreads / 32;
+  constexpr int kRPW = 32 / kLPR;          // rows per warp load
+  constexpr int kDh = kLPR * VE;
+  extern __shared__ __align__(16) float sm[];
+  float* sc = sm;                          // [Tk]
+  float* acc_s = sc + p.t_kv;              // [kWarps][kDh]
+  __shared__ float red_s[kWarps];
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int Tk = p.t_kv, Dm = p.heads * kDh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % kLPR, rsel = lane / kLPR;
+  const float scale = rsqrtf((float)kDh);
+
+  float qv[VE];
+  {
+    const T* q = reinterpret_cast<const T*>(p.q) + (int64_t)b * Dm + h * kDh + sub * VE;
+    Io<T>::unpack(ldg16(q), qv);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) qv[j] = Io<T>::to_f(Io<T>::from_f(qv[j] * scale));
+  }
+  const T* Kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const T* Vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * Tk : nullptr;
+
+  float lmax = -INFINITY;
+#pragma unroll 4
+  for (int t0 = warp * kRPW; t0 < Tk; t0 += kWarps * kRPW) {
+    const int t = t0 + rsel;
+    float s = 0.f;
+    if (t < Tk) {
+      float kv[VE];
+      Io<T>::unpack(ldg16_stream(Kb + (int64_t)t * Dm), kv);
+#pragma unroll
+      for (int j = 0; j < VE; ++j) s = fmaf(kv[j], qv[j], s);
+    }
+#pragma unroll
+    for (int o = kLPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t < Tk) {
+      if (mk && !mk[t]) s = -INFINITY;
+      if (sub == 0) sc[t] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) red_s[warp] = lmax;
+  __syncthreads();
+  float gmax = red_s[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) gmax = fmaxf(gmax, red_s[w]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int t = threadIdx.x; t < Tk; t += kAttnVecThreads) {
+    const float e = ex2f((sc[t] - gmax) * kLog2e);
+    sc[t] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red_s[warp] = lsum;
+  __syncthreads();
+  float gsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) gsum += red_s[w];
+  const float inv = 1.f / gsum;
+
+  float acc[VE];
+#pragma unroll
+  for (int j = 0; j < VE; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int t0 = warp * kRPW; t0 < Tk; t0 += kWarps * kRPW) {
+    const int t = t0 + rsel;
+    if (t < Tk) {
+      float vv[VE];
+      Io<T>::unpack(ldg16_stream(Vb + (int64_t)t * Dm), vv);
+      const float pt = sc[t];
+#pragma unroll
+      for (int j = 0; j < VE; ++j) acc[j] = fmaf(pt, vv[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int o = kLPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (rsel == 0) {
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc_s[warp * kDh + sub * VE + j] = acc[j];
+  }
+  __syncthreads();
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t)b * Dm + h * kDh;
+  for (int e = threadIdx.x; e < kDh; e += kAttnVecThreads) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) a += acc_s[w * kDh + e];
+    out[e] = Io<T>::from_f(a * inv);
+  }
+}
+
+template <typename T, int kLPR>
+static int launch_attn_vec(const mtts_cross_attn_decode_params& p, cudaStream_t s) {
+  constexpr int kDh = kLPR * Io<T>::kVecElems;
+  const size_t smem = sizeof(float) * ((size_t)p.t_kv + (kAttnVecThreads / 32) * kDh);
+  auto kern = cross_attn_decode_vec_kernel<T, kLPR>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+  }
+  kern<<<dim3(p.heads, p.batch), kAttnVecThreads, smem, s>>>(p);
+  return launch_status();
+}
+
+// returns 1 when no vectorised variant matches
 template <typename T>
-__global__ void __launch_bounds__(256) layernorm_film_kernel(const mtts_layernorm_film_params p) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= p.rows) return;
-  const int Dm = p.dim;
-  const T* x = reinterpret_cast<const T*>(p.x) + (int64_t)row * Dm;
-  const T* r = p.residual ? reinterpret_cast<const T*>(p.residual) + (int64_t)row * Dm : nullptr;
-  T* so = p.sum_out ? reinterpret_cast<T*>(p.sum_out) + (int64_t)row * Dm : nullptr;
-  float s = 0.f;
-  for (int e = lane; e < Dm; e += 32) {
-    float v = Io<T>::to_f(x[e]);
-    if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
-    if (so) so[e] = Io<T>::from_f(v);
-    s += v;
-  }
-  const float mean = warp_sum(s) / (float)Dm;
-  float q = 0.f;
-  for (int e = lane; e < Dm; e += 32) {
-    float v;
-    if (so) v = Io<T>::to_f(so[e]);  // sum_out may alias x: never re-add the residual
-    else {
-      v = Io<T>::to_f(x[e]);
-      if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
-    }
-    const float dlt = v - mean;
-    q = fmaf(dlt, dlt, q);
-  }
-  const float rstd = rsqrtf(warp_sum(q) / (float)Dm + p.eps);
-  const int bidx = row / p.rows_per_batch;
-  const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
-  const float* bet = p.film_beta ? p.film_beta + (int64_t)bidx * Dm : nullptr;
-  T* out = reinterpret_cast<T*>(p.out) + (int64_t)row * Dm;
-  for (int e = lane; e < Dm; e += 32) {
-    float v;
-    if (so) v = Io<T>::to_f(so[e]);
-    else {
-      v = Io<T>::to_f(x[e]);
-      if (r) v = Io<T>::to_f(Io<T>::from_f(v + Io<T>::to_f(r[e])));
-    }
-    float o = fmaf((v - mean) * rstd, p.ln_weight[e], p.ln_bias[e]);
-    if (gam) {
-      o = Io<T>::to_f(Io<T>::from_f(o));  // the reference materialises LN(x) before FiLM
-      o = fmaf(gam[e], o, bet ? bet[e] : 0.f);
-    }
-    out[e] = Io<T>::from_f(o);
+static int dispatch_attn_vec(const mtts_cross_attn_decode_params& p, cudaStream_t s, int* rc) {
+  constexpr int VE = Io<T>::kVecElems;
+  if (p.head_dim % VE != 0 || !aligned16(p.q) || !aligned16(p.k) || !aligned16(p.v)) return 1;
+  switch (p.head_dim / VE) {
+    case 4: *rc = launch_attn_vec<T, 4>(p, s); return 0;
+    case 8: *rc = launch_attn_vec<T, 8>(p, s); return 0;
+    case 16: *rc = launch_attn_vec<T, 16>(p, s); return 0;
+    case 32: *rc = launch_attn_vec<T, 32>(p, s); return 0;
+    default: return 1;
   }
 }
 
@@ -370,39 +452,28 @@ extern "C" int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mt
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = sizeof(float) * ((size_t)p->t_kv + p->head_dim + (mtts::kAttnThreads / 32) * p->head_dim);
   if (smem > 200 * 1024) return MTTS_ERR_SHAPE;
+  int rc = 0;
+  if (p->io_dtype == MTTS_F32) {
+    if (mtts::dispatch_attn_vec<float>(*p, s, &rc) == 0) return rc;
+  } else if (p->io_dtype == MTTS_BF16) {
+    if (mtts::dispatch_attn_vec<__nv_bfloat16>(*p, s, &rc) == 0) return rc;
+  } else {
+    return MTTS_ERR_DTYPE;
+  }
   const dim3 grid(p->heads, p->batch);
   cudaError_t e;
-  switch (p->io_dtype) {
-    case MTTS_F32:
-      if (smem > 48 * 1024 &&
-          (e = cudaFuncSetAttribute(mtts::cross_attn_decode_kernel<float>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-        return -static_cast<int>(e);
-      mtts::cross_attn_decode_kernel<float><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
-      break;
-    case MTTS_BF16:
-      if (smem > 48 * 1024 &&
-          (e = cudaFuncSetAttribute(mtts::cross_attn_decode_kernel<__nv_bfloat16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
-        return -static_cast<int>(e);
-      mtts::cross_attn_decode_kernel<__nv_bfloat16><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
-      break;
-    default: return MTTS_ERR_DTYPE;
-  }
-  return mtts::launch_status();
-}
-
-extern "C" int mtts_layernorm_film(const mtts_layernorm_film_params* p, mtts_stream_t stream) {
-  if (!p || !p->x || !p->ln_weight || !p->ln_bias || !p->out) return MTTS_ERR_NULL;
-  if (p->rows < 0 || p->dim < 1 || p->rows_per_batch < 1) return MTTS_ERR_SHAPE;
-  if (p->rows == 0) return MTTS_OK;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rows_per_cta = 8;
-  const dim3 grid((p->rows + rows_per_cta - 1) / rows_per_cta);
-  switch (p->io_dtype) {
-    case MTTS_F32: mtts::layernorm_film_kernel<float><<<grid, 256, 0, s>>>(*p); break;
-    case MTTS_BF16: mtts::layernorm_film_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(*p); break;
-    default: return MTTS_ERR_DTYPE;
+  if (p->io_dtype == MTTS_F32) {
+    if (smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(mtts::cross_attn_decode_generic_kernel<float>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return -static_cast<int>(e);
+    mtts::cross_attn_decode_generic_kernel<float><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
+  } else {
+    if (smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(mtts::cross_attn_decode_generic_kernel<__nv_bfloat16>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return -static_cast<int>(e);
+    mtts::cross_attn_decode_generic_kernel<__nv_bfloat16><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
   }
   return mtts::launch_status();
 }

@@ -1,0 +1,283 @@
+// Fused residual-add + LayerNorm + FiLM, forward and backward, for sm_100a.
+//
+// The reference layer (mamba_decoder.py:59-89) is three times  x = x + branch(...) ; h = LN(x)
+// [; h = gamma * h + beta].  Each "x + branch" is folded into the LayerNorm that consumes it:
+//     x_out = x + delta            (fp32 residual stream, delta = previous branch output, io dtype)
+//     out   = FiLM(LN(x_out))      (io dtype: the next GEMM's operand)
+// One warp owns one row; a lane owns 4-element column groups {lane, lane+32, ...}, so every row
+// statistic is a shuffle reduction and every column statistic (backward) stays in the lane's
+// registers across the rows the warp walks.  HBM-bound: each tensor is touched exactly once.
+#include "common.cuh"
+
+namespace mtts {
+
+constexpr int kLnWarps = 4;
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float* o);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  o[0] = __uint_as_float(r.x << 16);
+  o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16);
+  o[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float* v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&a);
+  r.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// kG = 4-element column groups per lane (dim <= 128 * kG)
+template <typename T, int kG>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const int Dm = p.dim;
+  const float* x = p.x + (int64_t)row * Dm;
+  const T* dl = p.delta ? reinterpret_cast<const T*>(p.delta) + (int64_t)row * Dm : nullptr;
+  float v[kG][4];
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const int e = (g * 32 + lane) * 4;
+    if (e < Dm) {
+      load4<float>(x + e, v[g]);
+      if (dl) {
+        float d[4];
+        load4<T>(dl + e, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[g][j] += d[j];
+      }
+      if (p.x_out) store4<float>(p.x_out + (int64_t)row * Dm + e, v[g]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += v[g][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[g][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)Dm;
+  float q = 0.f;
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const int e = (g * 32 + lane) * 4;
+    if (e < Dm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float c = v[g][j] - mean;
+        q = fmaf(c, c, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)Dm + p.eps);
+  if (lane == 0) {
+    if (p.mean) p.mean[row] = mean;
+    if (p.rstd) p.rstd[row] = rstd;
+  }
+  const int bidx = row / p.rows_per_batch;
+  const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
+  const float* bet = p.film_beta ? p.film_beta + (int64_t)bidx * Dm : nullptr;
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t)row * Dm;
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const int e = (g * 32 + lane) * 4;
+    if (e < Dm) {
+      float w[4], b[4], o[4];
+      load4<float>(p.ln_weight + e, w);
+      load4<float>(p.ln_bias + e, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaf((v[g][j] - mean) * rstd, w[j], b[j]);
+      if (gam) {
+        float gm[4], bt[4];
+        load4<float>(gam + e, gm);
+        load4<float>(bet + e, bt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(gm[j], o[j], bt[j]);
+      }
+      store4<T>(out + e, o);
+    }
+  }
+}
+
+// Backward.  With xhat = (x_out - mean) rstd, y = xhat w + b, out = gamma y + beta:
+//   g      = dout * gamma * w                       (d/d xhat)
+//   dx     = dx_out + rstd (g - mean_e(g) - xhat mean_e(g xhat))
+//   S1[b]  = sum_t dout xhat,  S2[b] = sum_t dout   (per batch element and column, accumulated into
+//            `colsum` (batch, 2, dim)); the host finishes dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b,
+//            dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b  on (batch, dim)-sized tensors.
+template <typename T, int kG>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_per_warp) {
+  __shared__ float red[kLnWarps][2][kG * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Dm = p.dim;
+  // a CTA never straddles two batch elements: grid.x tiles rows_per_batch, grid.y = batch
+  const int bidx = blockIdx.y;
+  const int r_begin = blockIdx.x * kLnWarps * rows_per_warp + warp * rows_per_warp;
+  const int r_end = min(p.rows_per_batch, r_begin + rows_per_warp);
+  const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
+
+  float w[kG][4], s1[kG][4], s2[kG][4];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const int e = (g * 32 + lane) * 4;
+    if (e < Dm) {
+      load4<float>(p.ln_weight + e, w[g]);
+      if (gam) {
+        float gm[4];
+        load4<float>(gam + e, gm);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[g][j] *= gm[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[g][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s1[g][j] = s2[g][j] = 0.f;
+  }
+
+  for (int r = r_begin; r < r_end; ++r) {
+    const int64_t row = (int64_t)bidx * p.rows_per_batch + r;
+    const float mean = p.mean[row], rstd = p.rstd[row];
+    const float* xo = p.x_out + row * Dm;
+    const T* go = reinterpret_cast<const T*>(p.dout) + row * Dm;
+    float xh[kG][4], gg[kG][4];
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int e = (g * 32 + lane) * 4;
+      if (e < Dm) {
+        float xv[4], dv[4];
+        load4<float>(xo + e, xv);
+        load4<T>(go + e, dv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xh[g][j] = (xv[j] - mean) * rstd;
+          s1[g][j] = fmaf(dv[j], xh[g][j], s1[g][j]);
+          s2[g][j] += dv[j];
+          gg[g][j] = dv[j] * w[g][j];
+          a += gg[g][j];
+          bsum = fmaf(gg[g][j], xh[g][j], bsum);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xh[g][j] = gg[g][j] = 0.f;
+      }
+    }
+    a = warp_sum(a) / (float)Dm;
+    bsum = warp_sum(bsum) / (float)Dm;
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int e = (g * 32 + lane) * 4;
+      if (e < Dm) {
+        float dx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dx[j] = rstd * (gg[g][j] - a - xh[g][j] * bsum);
+        if (p.dx_out) {
+          float up[4];
+          load4<float>(p.dx_out + row * Dm + e, up);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dx[j] += up[j];
+        }
+        store4<float>(p.dx + row * Dm + e, dx);
+        if (p.ddelta) store4<T>(reinterpret_cast<T*>(p.ddelta) + row * Dm + e, dx);
+      }
+    }
+  }
+
+  // column sums: warps -> CTA (smem) -> one RED per column per CTA
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[warp][0][(g * 32 + lane) * 4 + j] = s1[g][j];
+      red[warp][1][(g * 32 + lane) * 4 + j] = s2[g][j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * Dm; idx += kLnWarps * 32) {
+    const int which = idx / Dm, e = idx - which * Dm;
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kLnWarps; ++wv) t += red[wv][which][e];
+    atomicAdd(p.colsum + ((int64_t)bidx * 2 + which) * Dm + e, t);
+  }
+}
+
+template <typename T>
+static int dispatch_ln_fwd(const mtts_add_layernorm_fwd_params& p, cudaStream_t s) {
+  const dim3 grid((p.rows + kLnWarps - 1) / kLnWarps);
+  const int groups = (p.dim + 127) / 128;
+  if (groups <= 2) add_layernorm_fwd_kernel<T, 2><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (groups <= 4) add_layernorm_fwd_kernel<T, 4><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else if (groups <= 8) add_layernorm_fwd_kernel<T, 8><<<grid, kLnWarps * 32, 0, s>>>(p);
+  else add_layernorm_fwd_kernel<T, 16><<<grid, kLnWarps * 32, 0, s>>>(p);
+  return launch_status();
+}
+
+template <typename T>
+static int dispatch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t s) {
+  const int batch = p.rows / p.rows_per_batch;
+  // ~4 waves of CTAs; every warp walks `rows_per_warp` consecutive rows of one batch element
+  int rows_per_warp = (p.rows + 4 * kNumSMs * 4 * kLnWarps - 1) / (4 * kNumSMs * 4 * kLnWarps);
+  rows_per_warp = max(1, min(rows_per_warp, 64));
+  const int per_cta = rows_per_warp * kLnWarps;
+  const dim3 grid((p.rows_per_batch + per_cta - 1) / per_cta, batch);
+  const int groups = (p.dim + 127) / 128;
+  if (groups <= 2) add_layernorm_bwd_kernel<T, 2><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
+  else if (groups <= 4) add_layernorm_bwd_kernel<T, 4><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
+  else if (groups <= 8) add_layernorm_bwd_kernel<T, 8><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
+  else return MTTS_ERR_SHAPE;
+  return launch_status();
+}
+
+}  // namespace mtts
+
+extern "C" int mtts_add_layernorm_fwd(const mtts_add_layernorm_fwd_params* p, mtts_stream_t stream) {
+  if (!p || !p->x || !p->ln_weight || !p->ln_bias || !p->out) return MTTS_ERR_NULL;
+  if ((p->film_gamma == nullptr) != (p->film_beta == nullptr)) return MTTS_ERR_NULL;
+  if (p->rows < 0 || p->dim < 4 || p->dim % 4 != 0 || p->dim > 2048 || p->rows_per_batch < 1)
+    return MTTS_ERR_SHAPE;
+  if (p->rows == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->io_dtype) {
+    case MTTS_F32: return mtts::dispatch_ln_fwd<float>(*p, s);
+    case MTTS_BF16: return mtts::dispatch_ln_fwd<__nv_bfloat16>(*p, s);
+    default: return MTTS_ERR_DTYPE;
+  }
+}
+
+extern "C" int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream) {
+  if (!p || !p->x_out || !p->dout || !p->mean || !p->rstd || !p->ln_weight || !p->dx || !p->colsum)
+    return MTTS_ERR_NULL;
+  if (p->rows < 0 || p->dim < 4 || p->dim % 4 != 0 || p->dim > 1024 || p->rows_per_batch < 1 ||
+      p->rows % p->rows_per_batch != 0 || p->rows / p->rows_per_batch > 65535)
+    return MTTS_ERR_SHAPE;
+  if (p->rows == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->io_dtype) {
+    case MTTS_F32: return mtts::dispatch_ln_bwd<float>(*p, s);
+    case MTTS_BF16: return mtts::dispatch_ln_bwd<__nv_bfloat16>(*p, s);
+    default: return MTTS_ERR_DTYPE;
+  }
+}

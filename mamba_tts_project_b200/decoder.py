@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .mamba import Mamba
+from .mamba import Mamba, compute_dtype
 
 
 def _join_memory(text_hidden, text_mask, ref_hidden, ref_mask):
@@ -62,9 +62,8 @@ class CrossAttention(nn.Module):
         w, b = self.in_proj_weight, self.in_proj_bias
         if dtype is not None:
             w, b, memory = w.to(dtype), b.to(dtype), memory.to(dtype)
-        k = F.linear(memory, w[E:2 * E], b[E:2 * E])
-        v = F.linear(memory, w[2 * E:], b[2 * E:])
-        return k, v
+        kv = F.linear(memory, w[E:], b[E:])     # one GEMM for both projections
+        return kv[..., :E], kv[..., E:]
 
     def forward(self, query, memory, key_padding_mask=None):
         """query (B, T, E); memory (B, T_kv, E); key_padding_mask (B, T_kv) True = IGNORE."""
@@ -95,23 +94,31 @@ class MambaTTSDecoderLayer(nn.Module):
         self.ff = nn.Sequential(nn.Linear(d_model, d_ff), nn.GELU(), nn.Linear(d_ff, d_model))
         self.style_mlp = nn.Sequential(nn.Linear(d_style, 2 * d_model), nn.Tanh())
 
-    def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):
-        h = self.norm_mamba(x)
-        if mamba_state is None:
-            h_mamba, new_state = self.mamba(h)
-        else:
-            h_mamba, new_state = self.mamba(h, mamba_state)
-        x = x + h_mamba
+    def forward_fused(self, x, delta, text_hidden, z_style, text_mask=None, mamba_state=None):
+        """The layer with every ``x = x + branch`` folded into the LayerNorm that follows it.
 
-        h = self.norm_cross(x)
+        x: fp32 residual stream (B, T, D); delta: branch output still to be added to x (or None).
+        Returns (x, delta_out, new_state) with the layer's result being ``x + delta_out``."""
+        cdt = compute_dtype(x)
+        x, h = ops.add_layernorm(x, delta, self.norm_mamba.weight, self.norm_mamba.bias,
+                                 self.norm_mamba.eps, out_dtype=cdt)
+        h_mamba, new_state = self.mamba(h) if mamba_state is None else self.mamba(h, mamba_state)
+
+        x, h = ops.add_layernorm(x, h_mamba, self.norm_cross.weight, self.norm_cross.bias,
+                                 self.norm_cross.eps, out_dtype=cdt)
         key_padding_mask = None if text_mask is None else ~text_mask
-        x = x + self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask)
+        attn_out = self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask)
 
-        h = self.norm_ff(x)
         gamma, beta = torch.chunk(self.style_mlp(z_style), 2, dim=-1)
-        h = gamma.unsqueeze(1) * h + beta.unsqueeze(1)
-        x = x + self.ff(h)
-        return x, new_state
+        x, h = ops.add_layernorm(x, attn_out, self.norm_ff.weight, self.norm_ff.bias,
+                                 self.norm_ff.eps, gamma=gamma, beta=beta, out_dtype=cdt)
+        return x, self.ff(h), new_state
+
+    def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):
+        """Reference signature (``mamba_decoder.py:50-91``): returns (x, new_state)."""
+        xs, delta, new_state = self.forward_fused(x.float(), None, text_hidden, z_style, text_mask,
+                                                  mamba_state)
+        return (xs + delta.float()).to(x.dtype), new_state
 
 
 class _LayerStepWeights:
@@ -161,8 +168,8 @@ class GenerationContext:
                            decoder.norm_out.bias.detach().to(f32).contiguous(), decoder.norm_out.eps)
             self.head_w = decoder.head.weight.detach().to(dtype).contiguous()
             self.head_b = decoder.head.bias.detach().to(dtype).contiguous()
-            self.tok = decoder.token_embed.weight.detach().to(dtype).contiguous()
-            self.pos = decoder.pos_embed.weight.detach().to(dtype).contiguous()
+            self.tok = decoder.token_embed.weight.detach().float().contiguous()
+            self.pos = decoder.pos_embed.weight.detach().float().contiguous()
 
 
 class MambaTTSDecoder(nn.Module):
@@ -202,9 +209,12 @@ class MambaTTSDecoder(nn.Module):
         memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
 
         x = self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None] + self.quant_embed(quant_ids)
+        x, delta = x.float(), None
         for layer in self.layers:
-            x, _ = layer(x=x, text_hidden=memory, z_style=z_style, text_mask=mask, mamba_state=None)
-        return self.head(self.norm_out(x))
+            x, delta, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask)
+        _, h = ops.add_layernorm(x, delta, self.norm_out.weight, self.norm_out.bias,
+                                 self.norm_out.eps, out_dtype=compute_dtype(x))
+        return self.head(h)
 
     # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------
     def prepare_generation(self, text_hidden, z_style, text_mask=None, ref_hidden=None,
@@ -224,26 +234,28 @@ class MambaTTSDecoder(nn.Module):
         return self._gen_ctx
 
     def _step_core(self, ctx: GenerationContext, x, states):
-        """x (B, d_model) residual stream of the new token -> logits (B, V); states in place."""
-        delta = None  # pending residual branch, folded into the next LayerNorm launch
+        """x (B, d_model) fp32 residual stream of the new token -> logits (B, V); states in place."""
+        delta = None  # pending branch output, folded into the next LayerNorm launch
+        dt = ctx.dtype
         for lw, (conv_state, ssm_state) in zip(ctx.layers, states):
-            h = ops.layernorm_film(x, lw.ln1[0], lw.ln1[1], lw.ln1[2], residual=delta,
-                                   sum_out=x if delta is not None else None)
+            x, h = ops.add_layernorm(x, delta, lw.ln1[0], lw.ln1[1], lw.ln1[2], out_dtype=dt,
+                                     inplace=True)
             xz = F.linear(h, lw.mamba["in_proj"], lw.mamba["in_bias"])
             y = ops.mamba_decode_step(xz, conv_state, ssm_state, lw.mamba["conv_w"],
                                       lw.mamba["conv_b"], lw.mamba["x_proj"], lw.mamba["dt_proj"],
                                       lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"])
             m = F.linear(y, lw.mamba["out_proj"], lw.mamba["out_bias"])
-            h = ops.layernorm_film(x, lw.ln2[0], lw.ln2[1], lw.ln2[2], residual=m, sum_out=x)
+            x, h = ops.add_layernorm(x, m, lw.ln2[0], lw.ln2[1], lw.ln2[2], out_dtype=dt,
+                                     inplace=True)
             q = F.linear(h, lw.wq, lw.bq)
             a = ops.cross_attn_decode(q, lw.k, lw.v, lw.heads, mask=ctx.mask)
             o = F.linear(a, lw.wo, lw.bo)
-            h = ops.layernorm_film(x, lw.ln3[0], lw.ln3[1], lw.ln3[2], residual=o, sum_out=x,
-                                   gamma=lw.gamma, beta=lw.beta)
+            x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
+                                     beta=lw.beta, out_dtype=dt, inplace=True)
             f = F.gelu(F.linear(h, lw.w1, lw.b1))
             delta = F.linear(f, lw.w2, lw.b2)
-        h = ops.layernorm_film(x, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], residual=delta,
-                               sum_out=x if delta is not None else None)
+        _, h = ops.add_layernorm(x, delta, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], out_dtype=dt,
+                                 inplace=True)
         return F.linear(h, ctx.head_w, ctx.head_b)
 
     @torch.no_grad()
@@ -261,7 +273,7 @@ class MambaTTSDecoder(nn.Module):
             states.append(st if st is not None else
                           layer.mamba.allocate_inference_cache(B, dtype=ctx.dtype))
         x = ctx.tok[last_token[:, 0]] + ctx.pos[step_index]   # no quant_embed here (reference D5)
-        logits = self._step_core(ctx, x.contiguous(), states)
+        logits = self._step_core(ctx, x.float().contiguous(), states)
         return logits.unsqueeze(1), states
 
     @torch.no_grad()
@@ -286,7 +298,7 @@ class MambaTTSDecoder(nn.Module):
             use_cuda_graph = False  # sampling draws host-side RNG state per step
 
         def one_step():
-            x = ctx.tok.index_select(0, tok) + ctx.pos.index_select(0, pos)
+            x = (ctx.tok.index_select(0, tok) + ctx.pos.index_select(0, pos)).float()
             logits = self._step_core(ctx, x, states)
             if greedy:
                 nxt = logits.argmax(dim=-1)

@@ -26,6 +26,69 @@ import torch.nn.functional as F
 from . import ops
 
 
+def compute_dtype(t):
+    """Activation / GEMM-operand dtype: the autocast dtype when autocast is on, else t's dtype."""
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return t.dtype
+
+
+class _ChannelMajorLinear(torch.autograd.Function):
+    """y[b] = W @ x[b]:  W (O, I), x (B, I, T) in any cuBLAS-addressable striding -> y (B, O, T)
+    contiguous.  One strided-batched GEMM (W broadcast with batch stride 0): the projection lands
+    directly in the channel-major layout conv/scan want, with no transposing copy in either
+    direction (``torch.matmul`` would fold the batch and hand back a transposed view)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, weight, x, dtype):
+        Wc = weight.to(dtype)
+        xc = x if x.dtype == dtype else x.to(dtype)
+        ctx.save_for_backward(Wc, xc)
+        ctx.wdtype = weight.dtype
+        ctx.xdtype = x.dtype
+        with torch.autocast("cuda", enabled=False):
+            return torch.bmm(Wc.unsqueeze(0).expand(xc.shape[0], -1, -1), xc)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        Wc, xc = ctx.saved_tensors
+        B = xc.shape[0]
+        dy = dy.to(Wc.dtype)
+        with torch.autocast("cuda", enabled=False):
+            dx = torch.bmm(Wc.t().unsqueeze(0).expand(B, -1, -1), dy)
+            dW = torch.bmm(dy, xc.transpose(1, 2)).sum(0)
+        return dW.to(ctx.wdtype), dx.to(ctx.xdtype), None
+
+
+class _TokenMajorLinear(torch.autograd.Function):
+    """out[b] = y[b]^T @ W^T:  y (B, I, T) channel-major, W (O, I) -> out (B, T, O) contiguous;
+    the backward hands dy back channel-major.  Again one strided-batched GEMM each, no copies."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, weight, y, dtype):
+        Wc = weight.to(dtype)
+        yc = y if y.dtype == dtype else y.to(dtype)
+        ctx.save_for_backward(Wc, yc)
+        ctx.wdtype = weight.dtype
+        ctx.ydtype = y.dtype
+        with torch.autocast("cuda", enabled=False):
+            return torch.bmm(yc.transpose(1, 2), Wc.t().unsqueeze(0).expand(yc.shape[0], -1, -1))
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        Wc, yc = ctx.saved_tensors
+        B = yc.shape[0]
+        dout = dout.to(Wc.dtype)
+        with torch.autocast("cuda", enabled=False):
+            dy = torch.bmm(Wc.t().unsqueeze(0).expand(B, -1, -1), dout.transpose(1, 2))
+            dW = torch.bmm(dout.transpose(1, 2), yc.transpose(1, 2)).sum(0)
+        return dW.to(ctx.wdtype), dy.to(ctx.ydtype), None
+
+
 class Mamba(nn.Module):
     def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001,
                  dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True,
@@ -112,8 +175,9 @@ class Mamba(nn.Module):
     def _forward_sequence(self, h, state):
         Bsz, T, _ = h.shape
         R, N, W = self.dt_rank, self.d_state, self.d_conv
-        # channel-major projection: (2Di, D) @ (B, D, T) -> (B, 2Di, T), no transpose copy
-        xz = torch.matmul(self.in_proj.weight, h.transpose(1, 2))
+        cdt = compute_dtype(h)
+        # channel-major projection: (2Di, D) @ (B, D, T) -> (B, 2Di, T), no transposing copy
+        xz = _ChannelMajorLinear.apply(self.in_proj.weight, h.transpose(1, 2), cdt)
         if self.in_proj.bias is not None:
             xz = xz + self.in_proj.bias.to(xz.dtype)[:, None]
         x, z = xz.chunk(2, dim=1)
@@ -130,14 +194,16 @@ class Mamba(nn.Module):
         init = None if prev_conv is None else prev_conv[..., 1:]
         xc = ops.causal_conv1d_fn(x, w2d, self.conv1d.bias, initial_states=init,
                                   activation=self.activation)
-        x_dbl = torch.matmul(self.x_proj.weight, xc)                       # (B, R + 2N, T)
-        delta = torch.matmul(self.dt_proj.weight, x_dbl[:, :R])            # (B, Di, T)
+        x_dbl = _ChannelMajorLinear.apply(self.x_proj.weight, xc, cdt)           # (B, R + 2N, T)
+        delta = _ChannelMajorLinear.apply(self.dt_proj.weight, x_dbl[:, :R], cdt)  # (B, Di, T)
         A = -torch.exp(self.A_log.float())
         y, last = ops.selective_scan_fn(xc, delta, A, x_dbl[:, R:R + N], x_dbl[:, R + N:],
                                         self.D.float(), z=z, delta_bias=self.dt_proj.bias.float(),
                                         delta_softplus=True, return_last_state=True,
                                         initial_state=h0)
-        out = F.linear(y.transpose(1, 2), self.out_proj.weight, self.out_proj.bias)
+        out = _TokenMajorLinear.apply(self.out_proj.weight, y, cdt)               # (B, T, D)
+        if self.out_proj.bias is not None:
+            out = out + self.out_proj.bias.to(out.dtype)
         return out, (new_conv, last)
 
     def step(self, hidden_states, conv_state, ssm_state):

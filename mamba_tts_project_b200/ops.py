@@ -22,7 +22,7 @@ from ._lib import ptr
 
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
-           "layernorm_film"]
+           "add_layernorm"]
 
 
 def _unit_last_stride(t):
@@ -377,18 +377,106 @@ def cross_attn_decode(q, k, v, heads, mask=None, out=None):
     return o
 
 
-def layernorm_film(x, ln_weight, ln_bias, eps=1e-5, residual=None, sum_out=None, gamma=None,
-                   beta=None, rows_per_batch=1, out=None):
-    """out = LN(x + residual) [* gamma_b + beta_b]; x (rows, dim) contiguous; gamma/beta
-    (rows / rows_per_batch, dim) fp32.  ``sum_out`` (may alias x) receives x + residual."""
-    _lib.require_cuda(x, ln_weight, ln_bias, residual, gamma, beta)
-    rows, dim = x.shape
-    if not x.is_contiguous() or (residual is not None and not residual.is_contiguous()):
-        raise RuntimeError("x and residual must be contiguous (rows, dim)")
-    o = out if out is not None else torch.empty_like(x)
-    p = _lib.LayerNormFilmParams(
-        rows=rows, dim=dim, rows_per_batch=rows_per_batch, io_dtype=_lib.io_dtype(x), eps=eps,
-        x=ptr(x), residual=ptr(residual), sum_out=ptr(sum_out), ln_weight=ptr(ln_weight),
-        ln_bias=ptr(ln_bias), film_gamma=ptr(gamma), film_beta=ptr(beta), out=ptr(o))
-    _lib.call("mtts_layernorm_film", p)
-    return o
+class _AddLayerNormFn(torch.autograd.Function):
+    """(x_out, out) = add_layernorm(x, delta, w, b, gamma, beta): see ``mtts_add_layernorm_fwd``."""
+
+    @staticmethod
+    def forward(ctx, x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace):
+        _lib.require_cuda(x, delta, weight, bias, gamma, beta)
+        if x.dtype != torch.float32:
+            raise RuntimeError("the residual stream x must be fp32")
+        shape = x.shape
+        dim = shape[-1]
+        x2 = x.reshape(-1, dim)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        rpb = 1
+        if gamma is not None:
+            if gamma.dim() != 2 or gamma.shape[1] != dim or rows % gamma.shape[0]:
+                raise RuntimeError("gamma/beta must be (batch, dim) with batch dividing the rows")
+            rpb = rows // gamma.shape[0]
+        d2 = None
+        if delta is not None:
+            d2 = delta.reshape(-1, dim)
+            if d2.dtype != out_dtype:
+                d2 = d2.to(out_dtype)
+            if not d2.is_contiguous():
+                d2 = d2.contiguous()
+        w32, b32, g32, be32 = _f32c(weight), _f32c(bias), _f32c(gamma), _f32c(beta)
+        need = any(t is not None and t.requires_grad for t in (x, delta, weight, bias, gamma, beta))
+        out = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
+        if d2 is None:
+            x_out = x2
+        else:
+            x_out = x2 if inplace else torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        if rows:
+            p = _lib.AddLayerNormFwdParams(
+                rows=rows, dim=dim, rows_per_batch=rpb, io_dtype=_lib.io_dtype(out), eps=eps,
+                x=ptr(x2), delta=ptr(d2), x_out=None if d2 is None else ptr(x_out),
+                ln_weight=ptr(w32), ln_bias=ptr(b32), film_gamma=ptr(g32), film_beta=ptr(be32),
+                out=ptr(out), mean=ptr(mean), rstd=ptr(rstd))
+            _lib.call("mtts_add_layernorm_fwd", p)
+        ctx.save_for_backward(x_out, mean, rstd, w32, b32, g32)
+        ctx.meta = (rows, dim, rpb, shape, delta is not None,
+                    None if delta is None else delta.dtype, weight.dtype, bias.dtype,
+                    None if gamma is None else gamma.dtype)
+        if inplace and d2 is not None:
+            if x2.data_ptr() != x.data_ptr():
+                raise RuntimeError("inplace add_layernorm needs a contiguous x")
+            ctx.mark_dirty(x)
+            return x, out.view(shape)
+        return x_out.view(shape), out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dx_out, dout):
+        x_out, mean, rstd, w32, b32, g32 = ctx.saved_tensors
+        rows, dim, rpb, shape, has_delta, t_delta, t_w, t_b, t_g = ctx.meta
+        dev = x_out.device
+        batch = rows // rpb
+        io = dout.dtype if dout is not None else torch.float32
+        if dout is None:
+            dout = torch.zeros((rows, dim), dtype=io, device=dev)
+        dout2 = dout.reshape(-1, dim)
+        if not dout2.is_contiguous():
+            dout2 = dout2.contiguous()
+        dxo = None
+        if dx_out is not None:
+            dxo = dx_out.reshape(-1, dim).to(torch.float32)
+            if not dxo.is_contiguous():
+                dxo = dxo.contiguous()
+        dx = torch.empty((rows, dim), dtype=torch.float32, device=dev)
+        ddelta = torch.empty((rows, dim), dtype=t_delta, device=dev) \
+            if has_delta and t_delta == io else None
+        colsum = torch.zeros((batch, 2, dim), dtype=torch.float32, device=dev)
+        if rows:
+            p = _lib.AddLayerNormBwdParams(
+                rows=rows, dim=dim, rows_per_batch=rpb, io_dtype=_lib.io_dtype(dout2),
+                x_out=ptr(x_out), mean=ptr(mean), rstd=ptr(rstd), ln_weight=ptr(w32),
+                film_gamma=ptr(g32), dout=ptr(dout2), dx_out=ptr(dxo), dx=ptr(dx),
+                ddelta=ptr(ddelta), colsum=ptr(colsum))
+            _lib.call("mtts_add_layernorm_bwd", p)
+        s1, s2 = colsum[:, 0], colsum[:, 1]
+        if g32 is None:
+            dw, db, dgamma, dbeta = s1.sum(0), s2.sum(0), None, None
+        else:
+            dw, db = (g32 * s1).sum(0), (g32 * s2).sum(0)
+            dgamma, dbeta = (w32 * s1 + b32 * s2).to(t_g), s2.to(t_g)
+        if has_delta and ddelta is None:
+            ddelta = dx.to(t_delta)
+        return (dx.view(shape), None if not has_delta else ddelta.view(shape), dw.to(t_w),
+                db.to(t_b), dgamma, dbeta, None, None, None)
+
+
+def add_layernorm(x, delta, weight, bias, eps=1e-5, gamma=None, beta=None, out_dtype=None,
+                  inplace=False):
+    """Fused ``x_out = x + delta ; out = LN(x_out) [* gamma_b + beta_b]`` (``mamba_decoder.py:59-89``).
+
+    x: (..., dim) fp32 residual stream; delta: same shape, activation dtype, or None; weight/bias:
+    LayerNorm affine; gamma/beta: (batch, dim) FiLM terms or None.  Returns (x_out fp32, out in
+    ``out_dtype``).  ``inplace`` writes x_out over x (inference only)."""
+    if out_dtype is None:
+        out_dtype = delta.dtype if delta is not None else x.dtype
+    return _AddLayerNormFn.apply(x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace)

@@ -180,7 +180,7 @@ def test_decoder_bf16_decode_tracks_fp32():
         st = dec.allocate_states(4, torch.bfloat16)
         got = []
         for i in range(12):  # teacher-forced on the oracle's tokens so the comparison is per step
-            x = ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]
+            x = (ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]).float()
             got.append(dec._step_core(ctx, x.contiguous(), st)[:, None])
     check("bf16 step logits", torch.cat(got, 1), torch.cat(ref_lg, 1), 4e-2)
 

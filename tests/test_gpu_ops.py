@@ -301,21 +301,45 @@ def test_cross_attn_decode_vs_torch(shape, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
-def test_layernorm_film_vs_torch(dtype):
-    from mamba_tts_project_b200 import layernorm_film
-    g = torch.Generator().manual_seed(3)
-    rows, dim, rpb = 12, 200, 3
-    x = torch.randn(rows, dim, generator=g).to(dtype)
-    r = torch.randn(rows, dim, generator=g).to(dtype)
+@pytest.mark.parametrize("shape", [(4, 3, 200), (2, 64, 512), (3, 5, 1024), (1, 7, 64)],
+                         ids=["d200", "d512", "d1024", "d64"])
+@pytest.mark.parametrize("film", [False, True], ids=["plain", "film"])
+def test_add_layernorm_fwd_bwd_vs_torch(shape, dtype, film):
+    """Fused residual add + LayerNorm (+ FiLM) against the unfused torch ops of mamba_decoder.py:59-86."""
+    from mamba_tts_project_b200 import add_layernorm
+    batch, T, dim = shape
+    g = torch.Generator().manual_seed(dim + T)
+    x = torch.randn(batch, T, dim, generator=g)
+    delta = torch.randn(batch, T, dim, generator=g).to(dtype).float()
     w, b = torch.randn(dim, generator=g), torch.randn(dim, generator=g)
-    gam, bet = torch.randn(rows // rpb, dim, generator=g), torch.randn(rows // rpb, dim, generator=g)
-    s = (x.float() + r.float()).to(dtype).float()
-    ln = torch.nn.functional.layer_norm(s, (dim,), w, b, 1e-5)
-    ref = gam.repeat_interleave(rpb, 0) * ln + bet.repeat_interleave(rpb, 0)
-    xs = x.cuda().clone()
-    out = layernorm_film(xs, w.cuda(), b.cuda(), 1e-5, residual=r.cuda(), sum_out=xs,
-                         gamma=gam.cuda(), beta=bet.cuda(), rows_per_batch=rpb)
-    check("ln+film", out, ref, tol(dtype))
-    check("sum_out", xs, s, 1e-6)
-    out2 = layernorm_film(x.cuda(), w.cuda(), b.cuda())
-    check("plain ln", out2, torch.nn.functional.layer_norm(x.float(), (dim,), w, b, 1e-5), tol(dtype))
+    gam = torch.randn(batch, dim, generator=g) if film else None
+    bet = torch.randn(batch, dim, generator=g) if film else None
+    dxo = torch.randn(batch, T, dim, generator=g)
+    dh = torch.randn(batch, T, dim, generator=g).to(dtype).float()
+
+    leaves = [t.clone().requires_grad_() for t in (x, delta, w, b)] + \
+             ([gam.clone().requires_grad_(), bet.clone().requires_grad_()] if film else [])
+    xs = leaves[0] + leaves[1]
+    h = torch.nn.functional.layer_norm(xs, (dim,), leaves[2], leaves[3], 1e-5)
+    if film:
+        h = leaves[4][:, None] * h + leaves[5][:, None]
+    ref_g = torch.autograd.grad([xs, h], leaves, [dxo, dh])
+
+    cl = [t.clone().cuda().requires_grad_() for t in (x, delta.to(dtype), w, b)] + \
+         ([gam.clone().cuda().requires_grad_(), bet.clone().cuda().requires_grad_()] if film else [])
+    xo, ho = add_layernorm(cl[0], cl[1], cl[2], cl[3], 1e-5, gamma=cl[4] if film else None,
+                           beta=cl[5] if film else None, out_dtype=dtype)
+    got_g = torch.autograd.grad([xo, ho], cl, [dxo.cuda(), dh.cuda().to(dtype)])
+    t = tol(dtype)
+    check("x_out", xo, xs, 1e-6)
+    check("out", ho, h, t)
+    names = ["dx", "ddelta", "dweight", "dbias", "dgamma", "dbeta"]
+    for n, a, r in zip(names, got_g, ref_g):
+        check(n, a, r, t)
+    # no-delta / inference form, in place
+    x2 = x.cuda().clone()
+    xo2, ho2 = add_layernorm(x2, delta.cuda().to(dtype), w.cuda(), b.cuda(), out_dtype=dtype, inplace=True)
+    assert xo2.data_ptr() == x2.data_ptr()
+    check("inplace x", x2, xs, 1e-6)
+    _, ho3 = add_layernorm(x.cuda(), None, w.cuda(), b.cuda(), out_dtype=dtype)
+    check("plain ln", ho3, torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5), t)

@@ -1,0 +1,32 @@
+"""Summarise an ncu --set full report's raw CSV page: python tools/ncu_summary.py raw.csv"""
+import csv
+import sys
+
+KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'launch__waves_per_multiprocessor', 'launch__grid_size', 'launch__block_size',
+        'sm__inst_executed.sum', 'smsp__inst_executed.avg.per_cycle_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max',
+        'smsp__cycles_active.avg', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_alu.sum',
+        'sm__inst_executed_pipe_lsu.sum', 'sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__average_warp_latency_per_inst_issued.ratio', 'smsp__warps_eligible.avg.per_cycle_active',
+        'smsp__cycles_elapsed.avg.per_second']
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    print('-----')
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"{k} = {r[i]} {units[i]}")
+    # stall breakdown
+    st = [(float(r[i].replace(',', '')), h) for i, h in enumerate(hdr)
+          if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio') and r[i]]
+    for v, h in sorted(st, reverse=True)[:8]:
+        print(f"   stall {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]}: {v:.2f}")
