@@ -275,6 +275,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: park the real stdout and send everything else that
+    # writes to fd 1 (e.g. NCCL's version banner) to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU path for the product")
     torch.cuda.set_device(local)
@@ -404,7 +409,8 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": round(tps, 2), "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

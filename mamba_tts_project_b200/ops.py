@@ -391,7 +391,7 @@ class _AddLayerNormFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         rows = x2.shape[0]
-        rpb = 1
+        rpb = max(rows, 1)  # no FiLM: the whole tensor is one "batch element" for the column sums
         if gamma is not None:
             if gamma.dim() != 2 or gamma.shape[1] != dim or rows % gamma.shape[0]:
                 raise RuntimeError("gamma/beta must be (batch, dim) with batch dividing the rows")
