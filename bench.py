@@ -183,7 +183,7 @@ def extra_scan(peak):
     return out
 
 
-def extra_decode(cfg, steps=256):
+def extra_decode(cfg, steps=512):
     model = build_decoder(cfg, "cuda").eval()
     B = 64
     g = torch.Generator().manual_seed(1)
@@ -200,9 +200,14 @@ def extra_decode(cfg, steps=256):
         toks = model.generate(first, steps, text, z, dtype=dt)
         torch.cuda.synchronize()
         dtm = time.perf_counter() - t0
+        e0, e1, ns = model.last_generate_events
+        loop_ms = e0.elapsed_time(e1) / ns
         res[name] = {"tokens_per_s": round(B * steps / dtm, 1), "ms_per_step": round(dtm / steps * 1e3, 4),
-                     "steps": steps, "batch": B, "includes": "K/V + FiLM precompute, graph capture",
-                     "captured_launches_per_step": (_lib.launch_count - n0)}
+                     "steps": steps, "batch": B,
+                     "includes": "whole generate(): K/V + FiLM precompute, warm-up step, graph capture, replay",
+                     "steady_state_ms_per_step": round(loop_ms, 4),
+                     "steady_state_tokens_per_s": round(B / loop_ms * 1e3, 1),
+                     "library_launches_captured_per_step": (_lib.launch_count - n0) // 2}
     del model
     return res
 

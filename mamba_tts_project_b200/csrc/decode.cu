@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(kStepThreads) decode_step_kernel(const mtts_de
   constexpr int kWarps = kStepThreads / 32;
 
   extern __shared__ __align__(16) float sm[];
+  // 4-element vector access is possible when every slice start and length is a multiple of 4
+  const bool vec4 = (cpc % 4 == 0) && (p.dim % 4 == 0) && (R % 4 == 0);
   float* xs = sm;           // [cpc]  conv output of the own channels
   float* part = xs + cpc;   // [J]    own split-K partial of x_proj
   float* xdbl = part + J;   // [J]    full x_proj output (dt_low | B | C)
@@ -108,12 +110,35 @@ __global__ void __launch_bounds__(kStepThreads) decode_step_kernel(const mtts_de
 
   // 2. split-K x_proj: part[j] = sum_{d own} Wx[j, d] * xs[d]
   const T* Wx = reinterpret_cast<const T*>(p.x_proj_w);
-  for (int j = warp; j < J; j += kWarps) {
-    const T* wr = Wx + (int64_t)j * p.dim + c_lo;
-    float acc = 0.f;
-    for (int i = lane; i < nown; i += 32) acc = fmaf(Io<T>::to_f(wr[i]), xs[i], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) part[j] = acc;
+  if (vec4) {
+    // 4 rows per warp iteration, 4 elements per lane per load: all loads of a row group in flight
+    for (int j0 = warp * 4; j0 < J; j0 += kWarps * 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = lane * 4; i < nown; i += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + i);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (j0 + r < J) {
+            float wv[4];
+            load4<T>(Wx + (int64_t)(j0 + r) * p.dim + c_lo + i, wv);
+            acc[r] = fmaf(wv[0], xv.x, fmaf(wv[1], xv.y, fmaf(wv[2], xv.z, fmaf(wv[3], xv.w, acc[r]))));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float t = warp_sum(acc[r]);
+        if (lane == 0 && j0 + r < J) part[j0 + r] = t;
+      }
+    }
+  } else {
+    for (int j = warp; j < J; j += kWarps) {
+      const T* wr = Wx + (int64_t)j * p.dim + c_lo;
+      float acc = 0.f;
+      for (int i = lane; i < nown; i += 32) acc = fmaf(Io<T>::to_f(wr[i]), xs[i], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) part[j] = acc;
+    }
   }
   cluster.sync();
 
@@ -132,7 +157,16 @@ __global__ void __launch_bounds__(kStepThreads) decode_step_kernel(const mtts_de
     const int d = c_lo + i;
     float dt = 0.f;
     const T* wr = Wdt + (int64_t)d * R;
-    for (int r = 0; r < R; ++r) dt = fmaf(Io<T>::to_f(wr[r]), xdbl[r], dt);
+    if (vec4) {
+#pragma unroll 4
+      for (int r = 0; r < R; r += 4) {
+        float wv[4];
+        load4<T>(wr + r, wv);
+        dt = fmaf(wv[0], xdbl[r], fmaf(wv[1], xdbl[r + 1], fmaf(wv[2], xdbl[r + 2], fmaf(wv[3], xdbl[r + 3], dt))));
+      }
+    } else {
+      for (int r = 0; r < R; ++r) dt = fmaf(Io<T>::to_f(wr[r]), xdbl[r], dt);
+    }
     dt = Io<T>::to_f(Io<T>::from_f(dt));
     dt = softplus_f(dt + p.dt_bias[d]);
     const float x = xs[i];
@@ -353,9 +387,126 @@ cross_attn_decode_vec_kernel(const mtts_cross_attn_decode_params p) {
   }
 }
 
+// Register-cached variant for t_kv <= kIt * (rows per CTA pass): every K and V row this lane will
+// ever touch is loaded up front (one memory round trip for the whole kernel), scores and V stay in
+// registers, two block reductions (max, then sum + output) finish the softmax.
+constexpr int kAttnCachedThreads = 256;
+
+template <typename T, int kLPR, int kIt>
+__global__ void __launch_bounds__(kAttnCachedThreads)
+cross_attn_decode_cached_kernel(const mtts_cross_attn_decode_params p) {
+  constexpr int VE = Io<T>::kVecElems;
+  constexpr int kWarps = kAttnCachedThreads / 32;
+  constexpr int kRPW = 32 / kLPR;
+  constexpr int kDh = kLPR * VE;
+  __shared__ float red_s[kWarps];
+  __shared__ float sum_s[kWarps];
+  __shared__ __align__(16) float acc_s[kWarps * kDh];
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int Tk = p.t_kv, Dm = p.heads * kDh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % kLPR, rsel = lane / kLPR;
+  const float scale = rsqrtf((float)kDh);
+
+  const T* Kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const T* Vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * Tk : nullptr;
+
+  uint4 kraw[kIt], vraw[kIt];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    if (t < Tk) {
+      kraw[it] = ldg16_stream(Kb + (int64_t)t * Dm);
+      vraw[it] = ldg16_stream(Vb + (int64_t)t * Dm);
+    } else {
+      kraw[it] = make_uint4(0, 0, 0, 0);
+      vraw[it] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  float qv[VE];
+  {
+    const T* q = reinterpret_cast<const T*>(p.q) + (int64_t)b * Dm + h * kDh + sub * VE;
+    Io<T>::unpack(ldg16(q), qv);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) qv[j] = Io<T>::to_f(Io<T>::from_f(qv[j] * scale));
+  }
+  float sc[kIt];
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    float kv[VE];
+    Io<T>::unpack(kraw[it], kv);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VE; ++j) s = fmaf(kv[j], qv[j], s);
+#pragma unroll
+    for (int o = kLPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t >= Tk || (mk && !mk[t])) s = -INFINITY;
+    sc[it] = s;
+    lmax = fmaxf(lmax, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) red_s[warp] = lmax;
+  __syncthreads();
+  float gmax = red_s[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) gmax = fmaxf(gmax, red_s[w]);
+
+  float acc[VE];
+#pragma unroll
+  for (int j = 0; j < VE; ++j) acc[j] = 0.f;
+  float lsum = 0.f;
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    // rows past t_kv contribute nothing; an all-masked row gives exp(nan) = nan like torch
+    const float pt = (t < Tk) ? ex2f((sc[it] - gmax) * kLog2e) : 0.f;
+    float vv[VE];
+    Io<T>::unpack(vraw[it], vv);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc[j] = fmaf(pt, vv[j], acc[j]);
+    lsum += pt;  // identical on the kLPR lanes of a row group
+  }
+  // reduce over the row groups of the warp (lanes with equal `sub`)
+#pragma unroll
+  for (int o = kLPR; o < 32; o <<= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (rsel == 0) {
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc_s[warp * kDh + sub * VE + j] = acc[j];
+  }
+  if (lane == 0) sum_s[warp] = lsum;
+  __syncthreads();
+  float gsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) gsum += sum_s[w];
+  const float inv = 1.f / gsum;
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t)b * Dm + h * kDh;
+  for (int e = threadIdx.x; e < kDh; e += kAttnCachedThreads) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) a += acc_s[w * kDh + e];
+    out[e] = Io<T>::from_f(a * inv);
+  }
+}
+
 template <typename T, int kLPR>
 static int launch_attn_vec(const mtts_cross_attn_decode_params& p, cudaStream_t s) {
   constexpr int kDh = kLPR * Io<T>::kVecElems;
+  constexpr int kIt = 8;
+  constexpr int kRowsCached = kIt * (kAttnCachedThreads / 32) * (32 / kLPR);
+  if (p.t_kv <= kRowsCached) {
+    cross_attn_decode_cached_kernel<T, kLPR, kIt>
+        <<<dim3(p.heads, p.batch), kAttnCachedThreads, 0, s>>>(p);
+    return launch_status();
+  }
   const size_t smem = sizeof(float) * ((size_t)p.t_kv + (kAttnVecThreads / 32) * kDh);
   auto kern = cross_attn_decode_vec_kernel<T, kLPR>;
   if (smem > 48 * 1024) {

@@ -4,9 +4,10 @@
 //   CTA   = one batch element x a group of G channels, walking the sequence tile by tile;
 //   warp  = one channel at a time; its 32 lanes split a tile of 32*kItems timesteps, each lane owning
 //           kItems CONSECUTIVE timesteps (recurrence in registers), lanes are stitched together with a
-//           warp-shuffle scan of the affine pairs (decay, state);
-//   smem  = the B/C tile of the batch element (dstate rows x tile timesteps, fp32), staged once and
-//           shared by every channel of the group -- upstream re-reads it from L2 per channel.
+//           warp-shuffle scan of the affine pairs (decay, state); two dstate rows are processed per
+//           instruction with packed fp32x2 arithmetic;
+//   smem  = the B/C tile of the batch element (dstate row pairs x tile timesteps, fp32), staged once
+//           and shared by every channel of the group -- upstream re-reads it from L2 per channel.
 #pragma once
 
 #include "common.cuh"
@@ -15,89 +16,131 @@ namespace mtts {
 
 constexpr int kScanNChunk = 16;  // dstate rows resident in shared memory at a time
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) -----
+// A make_float2(s, s) operand folds into a scalar-broadcast register operand (R.F32) in SASS.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 dup2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 ex2f2(float2 x) { return make_float2(ex2f(x.x), ex2f(x.y)); }
+__device__ __forceinline__ float2 shfl_up2(float2 v, int d) {
+  return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float2 shfl_down2(float2 v, int d) {
+  return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+
+// ---- pair-interleaved tile: two dstate rows (2p, 2p+1) share one smem row ---------------------------
+// element (n, t) lives at  (n/2)*kRow + (t/kItems)*kSeg + (t%kItems)*2 + (n&1):  a lane reads its
+// kItems timesteps of BOTH rows as kItems float2 with LDS.128; kSeg = 2*kItems + 4 keeps the eight
+// lanes of a quarter-warp on distinct 16-byte bank groups.
 template <int kItems>
-struct ScanTile {
-  // A lane reads its kItems consecutive floats with LDS.128; padding every lane segment by 4 words
-  // makes the 8 lanes of each quarter-warp phase hit 8 distinct 16-byte bank groups.
-  static constexpr int kSeg = kItems + 4;
-  static constexpr int kRow = 32 * kSeg;   // words per dstate row
-  static constexpr int kLen = 32 * kItems; // timesteps per tile
-  static_assert(MTTS_SCAN_CHUNK % kItems == 0 && kLen % MTTS_SCAN_CHUNK == 0,
-                "tile must be a whole number of checkpoint chunks");
+struct PairTile {
+  static constexpr int kSeg = 2 * kItems + 4;
+  static constexpr int kRow = 32 * kSeg;
+  static constexpr int kLen = 32 * kItems;
+  static constexpr int kPairs = kScanNChunk / 2;  // dstate row pairs resident at a time
+  static_assert(MTTS_SCAN_CHUNK % kItems == 0 && kLen % MTTS_SCAN_CHUNK == 0, "tile vs chunk");
 };
 
-// Stage rows [n0, n0+ncnt) x timesteps [t0, t0+kLen) of a (dstate, seqlen) matrix into `dst` as fp32
-// in the padded layout above; timesteps >= len are zero-filled (0 is the identity of the scan).
+// Stage dstate rows [n0, n0+ncnt) (ncnt <= kScanNChunk) x timesteps [t0, t0+kLen) interleaved by
+// pairs, as fp32; missing rows / timesteps >= len are zero (the scan's identity).
 template <typename T, int kItems, bool kVec, int kThreads>
-__device__ __forceinline__ void stage_rows(const T* __restrict__ src, int64_t row_stride, int n0,
-                                           int ncnt, int t0, int len, float* __restrict__ dst) {
-  using Tile = ScanTile<kItems>;
+__device__ __forceinline__ void stage_pairs(const T* __restrict__ src, int64_t row_stride, int n0,
+                                            int ncnt, int t0, int len, float* __restrict__ dst) {
+  using Tile = PairTile<kItems>;
+  const int npairs = (ncnt + 1) >> 1;
   if constexpr (kVec) {
     constexpr int VE = Io<T>::kVecElems;
     constexpr int kVecPerRow = Tile::kLen / VE;
-    const int total = ncnt * kVecPerRow;
+    const int total = npairs * kVecPerRow;
     for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-      const int r = idx / kVecPerRow;
-      const int tt = (idx - r * kVecPerRow) * VE;
-      float v[VE];
-      if (t0 + tt < len) {
-        const uint4 raw = ldg16(src + (int64_t)(n0 + r) * row_stride + t0 + tt);
-        Io<T>::unpack(raw, v);
+      const int pr = idx / kVecPerRow;
+      const int tt = (idx - pr * kVecPerRow) * VE;
+      float lo[VE], hi[VE];
+      const bool in_t = t0 + tt < len;
+      if (in_t) {
+        Io<T>::unpack(ldg16(src + (int64_t)(n0 + 2 * pr) * row_stride + t0 + tt), lo);
       } else {
 #pragma unroll
-        for (int j = 0; j < VE; ++j) v[j] = 0.f;
+        for (int j = 0; j < VE; ++j) lo[j] = 0.f;
       }
-      float* d = dst + r * Tile::kRow + (tt / kItems) * Tile::kSeg + (tt % kItems);
+      if (in_t && 2 * pr + 1 < ncnt) {
+        Io<T>::unpack(ldg16(src + (int64_t)(n0 + 2 * pr + 1) * row_stride + t0 + tt), hi);
+      } else {
 #pragma unroll
-      for (int j = 0; j < VE; j += 4)
-        *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < VE; ++j) hi[j] = 0.f;
+      }
+      float* d = dst + pr * Tile::kRow + (tt / kItems) * Tile::kSeg + (tt % kItems) * 2;
+#pragma unroll
+      for (int j = 0; j < VE; j += 2)
+        *reinterpret_cast<float4*>(d + 2 * j) = make_float4(lo[j], hi[j], lo[j + 1], hi[j + 1]);
     }
   } else {
-    const int total = ncnt * Tile::kLen;
+    const int total = npairs * 2 * Tile::kLen;
     for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-      const int r = idx / Tile::kLen;
+      const int r = idx / Tile::kLen;  // row within the chunk (may be one past ncnt for odd ncnt)
       const int tt = idx - r * Tile::kLen;
       float v = 0.f;
-      if (t0 + tt < len) v = Io<T>::to_f(src[(int64_t)(n0 + r) * row_stride + t0 + tt]);
-      dst[r * Tile::kRow + (tt / kItems) * Tile::kSeg + (tt % kItems)] = v;
+      if (r < ncnt && t0 + tt < len) v = Io<T>::to_f(src[(int64_t)(n0 + r) * row_stride + t0 + tt]);
+      dst[(r >> 1) * Tile::kRow + (tt / kItems) * Tile::kSeg + (tt % kItems) * 2 + (r & 1)] = v;
     }
   }
 }
 
-// Read this lane's kItems staged values of one dstate row.
+// This lane's kItems float2 (row 2p, row 2p+1) values of one staged pair row.
 template <int kItems>
-__device__ __forceinline__ void lane_row(const float* __restrict__ row_lane, float* out) {
+__device__ __forceinline__ void lane_pairs(const float* __restrict__ p, float2* out) {
 #pragma unroll
-  for (int j = 0; j < kItems; j += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(row_lane + j);
-    out[j] = v.x;
-    out[j + 1] = v.y;
-    out[j + 2] = v.z;
-    out[j + 3] = v.w;
+  for (int j = 0; j < kItems; j += 2) {
+    const float4 v = *reinterpret_cast<const float4*>(p + 2 * j);
+    out[j] = make_float2(v.x, v.y);
+    out[j + 1] = make_float2(v.z, v.w);
   }
 }
 
-// Inclusive warp scan (lane 0 first) of affine maps s -> P*s + h.
-__device__ __forceinline__ void warp_scan_affine_up(float& P, float& h, int lane) {
+// Inclusive warp scans of affine maps, two independent rows at once.
+__device__ __forceinline__ void warp_scan_affine_up2(float2& P, float2& h, int lane) {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const float Pp = __shfl_up_sync(0xffffffffu, P, off);
-    const float hp = __shfl_up_sync(0xffffffffu, h, off);
+    const float2 Pp = shfl_up2(P, off);
+    const float2 hp = shfl_up2(h, off);
     if (lane >= off) {
-      h = fmaf(P, hp, h);
-      P *= Pp;
+      h = ffma2(P, hp, h);
+      P = fmul2(P, Pp);
     }
   }
 }
-// Same, running from lane 31 down (for the reverse-time recurrence of the backward pass).
-__device__ __forceinline__ void warp_scan_affine_down(float& P, float& g, int lane) {
+__device__ __forceinline__ void warp_scan_affine_down2(float2& P, float2& g, int lane) {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    const float Pn = __shfl_down_sync(0xffffffffu, P, off);
-    const float gn = __shfl_down_sync(0xffffffffu, g, off);
+    const float2 Pn = shfl_down2(P, off);
+    const float2 gn = shfl_down2(g, off);
     if (lane + off < 32) {
-      g = fmaf(P, gn, g);
-      P *= Pn;
+      g = ffma2(P, gn, g);
+      P = fmul2(P, Pn);
     }
   }
 }

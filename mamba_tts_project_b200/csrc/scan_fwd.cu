@@ -1,9 +1,10 @@
 // selective_scan forward for sm_100a.  Replaces selective_scan_cuda.fwd (mamba_ssm), which the
 // reference reaches through Mamba.forward at mamba_decoder.py:61.  Math: see mamba_tts_b200.h.
 //
-// Per (lane, dstate row): one MUFU.EX2 per timestep-state (the binding unit on B200: 16/clk/SM),
-// sweep 1 builds the lane-local affine map, a 5-step shuffle scan stitches the 32 lanes, sweep 2
-// replays the recurrence from the true incoming state and contracts with C.
+// Per (lane, pair of dstate rows): one MUFU.EX2 per timestep-state (the binding unit on B200:
+// 16/clk/SM); everything else is packed fp32x2 (FFMA2/FMUL2: the two rows of a pair share an issue
+// slot).  Sweep 1 builds the lane-local affine map, a 5-step shuffle scan stitches the 32 lanes,
+// sweep 2 replays the recurrence from the true incoming state and contracts with C.
 #include "scan_common.cuh"
 
 namespace mtts {
@@ -11,7 +12,7 @@ namespace mtts {
 template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
-  using Tile = ScanTile<kItems>;
+  using Tile = PairTile<kItems>;
   constexpr int kThreads = kWarps * 32;
   constexpr int G = kWarps * kCPW;
   constexpr int kLanesPerChunk = MTTS_SCAN_CHUNK / kItems;
@@ -19,25 +20,26 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
 
   extern __shared__ __align__(16) float smem[];
   const int N = p.dstate, L = p.seqlen;
+  const int NP = (N + 1) >> 1;  // dstate row pairs
   float* Bs = smem;
-  float* Cs = Bs + kScanNChunk * Tile::kRow;
-  float* A2s = Cs + kScanNChunk * Tile::kRow;  // A * log2(e), [G][N]
-  float* hs = A2s + G * N;                     // running state,  [G][N]
+  float* Cs = Bs + Tile::kPairs * Tile::kRow;
+  float2* A2s = reinterpret_cast<float2*>(Cs + Tile::kPairs * Tile::kRow);  // A*log2(e), [G][NP]
+  float2* hs = A2s + G * NP;                                                // running state [G][NP]
 
   const int b = blockIdx.y, c0 = blockIdx.x * G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int idx = threadIdx.x; idx < G * N; idx += kThreads) {
-    const int cl = idx / N, n = idx - cl * N, c = c0 + cl;
+  for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
+    const int cl = idx / (2 * NP), n = idx - cl * 2 * NP, c = c0 + cl;
     float a2 = 0.f, h = 0.f;
-    if (c < p.dim) {
+    if (c < p.dim && n < N) {
       a2 = p.A[(int64_t)c * N + n] * kLog2e;
       const int64_t bc = (int64_t)b * p.dim + c;
       if (p.initial_state) h = p.initial_state[bc * N + n];
       if (p.checkpoints) p.checkpoints[bc * nchunks * N + n] = h;
     }
-    A2s[idx] = a2;
-    hs[idx] = h;
+    reinterpret_cast<float*>(A2s)[idx] = a2;
+    reinterpret_cast<float*>(hs)[idx] = h;
   }
   __syncthreads();
 
@@ -49,6 +51,7 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   for (int tile = 0; tile < ntiles; ++tile) {
     const int t0 = tile * Tile::kLen;
     const int tl = t0 + lane * kItems;
+    const bool partial = t0 + Tile::kLen > L;
 #pragma unroll 1
     for (int pass = 0; pass < kCPW; ++pass) {
       const int cl = pass * kWarps + warp;
@@ -70,7 +73,7 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
         for (int i = 0; i < kItems; ++i) {
           float x = dl[i] + bias;
           if (p.delta_softplus) x = softplus_f(x);
-          if (tl + i >= L) x = 0.f;  // padding: decay 1, input 0 = identity step
+          if (partial && tl + i >= L) x = 0.f;  // padding: decay 1, input 0 = identity step
           const float uu = du[i];
           dl[i] = x;
           y[i] = Dv * uu;
@@ -86,46 +89,55 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
         const int ncnt = min(kScanNChunk, N - n0);
         if (restage_per_pass || pass == 0) {
           __syncthreads();  // every warp is done reading the previous B/C tile
-          stage_rows<T, kItems, kVec, kThreads>(Bb, p.B_state_stride, n0, ncnt, t0, L, Bs);
-          stage_rows<T, kItems, kVec, kThreads>(Cb, p.C_state_stride, n0, ncnt, t0, L, Cs);
+          stage_pairs<T, kItems, kVec, kThreads>(Bb, p.B_state_stride, n0, ncnt, t0, L, Bs);
+          stage_pairs<T, kItems, kVec, kThreads>(Cb, p.C_state_stride, n0, ncnt, t0, L, Cs);
           __syncthreads();
         }
         if (!cvalid) continue;
+        const int npairs = (ncnt + 1) >> 1;
 #pragma unroll 1
-        for (int nn = 0; nn < ncnt; ++nn) {
-          const int n = n0 + nn;
-          const float A2 = A2s[cl * N + n];
-          const float h_in = hs[cl * N + n];
-          float a[kItems], bx[kItems], tmp[kItems];
-          lane_row<kItems>(Bs + nn * Tile::kRow + lane * Tile::kSeg, tmp);
-          float hl = 0.f;
+        for (int pp = 0; pp < npairs; ++pp) {
+          const int pg = (n0 >> 1) + pp;  // global pair index
+          const float2 A2 = A2s[cl * NP + pg];
+          const float2 h_in = hs[cl * NP + pg];
+          const float* Bl = Bs + pp * Tile::kRow + lane * Tile::kSeg;
+          const float* Cl = Cs + pp * Tile::kRow + lane * Tile::kSeg;
+          float2 a[kItems], tmp[kItems];
+          lane_pairs<kItems>(Bl, tmp);
+          float2 hl = make_float2(0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < kItems; ++i) {
-            a[i] = ex2f(dl[i] * A2);
-            bx[i] = du[i] * tmp[i];
-            hl = fmaf(a[i], hl, bx[i]);
+            a[i] = ex2f2(fmul2(dup2(dl[i]), A2));
+            hl = ffma2(a[i], hl, fmul2(dup2(du[i]), tmp[i]));
           }
-          float P = ex2f(A2 * dsum);  // product of the lane's decays
-          warp_scan_affine_up(P, hl, lane);
-          float Pe = __shfl_up_sync(0xffffffffu, P, 1);
-          float he = __shfl_up_sync(0xffffffffu, hl, 1);
+          float2 P = ex2f2(fmul2(dup2(dsum), A2));  // product of the lane's decays
+          warp_scan_affine_up2(P, hl, lane);
+          float2 Pe = shfl_up2(P, 1);
+          float2 he = shfl_up2(hl, 1);
           if (lane == 0) {
-            Pe = 1.f;
-            he = 0.f;
+            Pe = make_float2(1.f, 1.f);
+            he = make_float2(0.f, 0.f);
           }
-          float h = fmaf(Pe, h_in, he);  // state entering this lane's first timestep
-          lane_row<kItems>(Cs + nn * Tile::kRow + lane * Tile::kSeg, tmp);
+          float2 h = ffma2(Pe, h_in, he);  // state entering this lane's first timestep
+          {
+            float2 cv[kItems];
+            lane_pairs<kItems>(Bl, tmp);  // b is recomputed rather than kept: 32 registers saved
+            lane_pairs<kItems>(Cl, cv);
 #pragma unroll
-          for (int i = 0; i < kItems; ++i) {
-            h = fmaf(a[i], h, bx[i]);
-            y[i] = fmaf(h, tmp[i], y[i]);
+            for (int i = 0; i < kItems; ++i) {
+              h = ffma2(a[i], h, fmul2(dup2(du[i]), tmp[i]));
+              y[i] = fmaf(h.y, cv[i].y, fmaf(h.x, cv[i].x, y[i]));
+            }
           }
           // h = state after this lane's last timestep
-          if (lane == 31) hs[cl * N + n] = h;
+          if (lane == 31) hs[cl * NP + pg] = h;
           if (p.checkpoints && ((lane + 1) % kLanesPerChunk) == 0) {
             const int k = tile * kChunksPerTile + (lane + 1) / kLanesPerChunk;
-            if (k < nchunks)
-              p.checkpoints[(((int64_t)b * p.dim + c) * nchunks + k) * N + n] = h;
+            if (k < nchunks) {
+              float* ck = p.checkpoints + (((int64_t)b * p.dim + c) * nchunks + k) * N + 2 * pg;
+              ck[0] = h.x;
+              if (2 * pg + 1 < N) ck[1] = h.y;
+            }
           }
         }
         __syncwarp();
@@ -149,19 +161,21 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
 
   if (p.last_state) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < G * N; idx += kThreads) {
-      const int cl = idx / N, n = idx - cl * N, c = c0 + cl;
-      if (c < p.dim) p.last_state[((int64_t)b * p.dim + c) * N + n] = hs[idx];
+    for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
+      const int cl = idx / (2 * NP), n = idx - cl * 2 * NP, c = c0 + cl;
+      if (c < p.dim && n < N)
+        p.last_state[((int64_t)b * p.dim + c) * N + n] = reinterpret_cast<const float*>(hs)[idx];
     }
   }
 }
 
 template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
 static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
-  using Tile = ScanTile<kItems>;
+  using Tile = PairTile<kItems>;
   constexpr int G = kWarps * kCPW;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
-  const size_t smem = sizeof(float) * (2 * kScanNChunk * Tile::kRow + 2 * (size_t)G * p.dstate);
+  const int NP = (p.dstate + 1) / 2;
+  const size_t smem = sizeof(float) * (2 * Tile::kPairs * Tile::kRow + 4 * (size_t)G * NP);
   auto kern = scan_fwd_kernel<T, kItems, kWarps, kCPW, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);

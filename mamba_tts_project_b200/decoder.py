@@ -187,6 +187,7 @@ class MambaTTSDecoder(nn.Module):
         self.head = nn.Linear(d_model, vocab_size_audio)
         self._gen_key = None
         self._gen_ctx = None
+        self.last_generate_events = None
 
     # ---- teacher-forced path (mamba_decoder.py:120-186) -----------------------------------------
     def forward(self, audio_tokens, text_hidden, z_style, text_mask=None, ref_hidden=None,
@@ -310,9 +311,14 @@ class MambaTTSDecoder(nn.Module):
             pos.add_(1)
             col.add_(1)
 
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
         if not use_cuda_graph:
+            ev0.record()
             for _ in range(n_steps):
                 one_step()
+            ev1.record()
+            self.last_generate_events = (ev0, ev1, n_steps)
             return out
 
         # warm up on a side stream (cuBLAS workspaces, lazy module loads), then restore the state
@@ -332,6 +338,9 @@ class MambaTTSDecoder(nn.Module):
         with torch.cuda.graph(graph):
             one_step()
         # capture does not execute: state is still the initial one
+        ev0.record()
         for _ in range(n_steps):
             graph.replay()
+        ev1.record()
+        self.last_generate_events = (ev0, ev1, n_steps)  # steady-state loop only (bench.py)
         return out
