@@ -66,7 +66,16 @@ class GradAllReducer:
         self._pending = [0] * len(self.buckets)
         self._work = [None] * len(self.buckets)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self._paused = False
         self.reset()
+
+    def pause(self):
+        """Gradient accumulation: ignore gradient hooks until ``resume()`` (micro-batches before the
+        last one must not trigger the all-reduce)."""
+        self._paused = True
+
+    def resume(self):
+        self._paused = False
 
     def reset(self):
         self._pending = [len(b) for b in self.buckets]
@@ -88,6 +97,8 @@ class GradAllReducer:
                                              async_op=True)
 
     def _on_grad(self, p):
+        if self._paused:
+            return
         bi = self._bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:

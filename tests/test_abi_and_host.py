@@ -111,3 +111,22 @@ def test_decoder_argument_errors_match_reference():
     with pytest.raises(AssertionError, match="text_mask"):
         dec(torch.zeros(3, 4, dtype=torch.long), torch.randn(3, 2, 32), torch.randn(3, 8),
             text_mask=torch.ones(2, 2, dtype=torch.bool))
+
+
+def test_caller_contract_helpers_cpu():
+    """embed_codec_tokens / codec_ce_loss restate train.py:115-131 / :31-42 (pure host logic)."""
+    torch.manual_seed(0)
+    dec = mt.MambaTTSDecoder(16, d_model=32, n_layers=1, n_heads=2, d_ff=64, d_style=8, max_len=32,
+                             num_quantizers=3)
+    tok = torch.randint(0, 16, (2, 3, 5))
+    ref_hidden, mask = mt.embed_codec_tokens(tok, dec)
+    assert ref_hidden.shape == (2, 15, 32) and mask.shape == (2, 15)
+    # element (b, q, t) = token_embed[tok] + pos_embed[t] + quant_embed[q]
+    b, q, t = 1, 2, 3
+    want = dec.token_embed.weight[tok[b, q, t]] + dec.pos_embed.weight[t] + dec.quant_embed.weight[q]
+    assert torch.allclose(ref_hidden[b, q * 5 + t], want)
+    assert torch.equal(mask, (tok == 0).reshape(2, 15))
+    logits, tgt = torch.randn(2, 7, 16), torch.randint(0, 16, (2, 7))
+    tgt[0, :3] = 0
+    want = torch.nn.functional.cross_entropy(logits.view(14, 16), tgt.view(14), ignore_index=0)
+    assert torch.allclose(mt.codec_ce_loss(logits, tgt), want)

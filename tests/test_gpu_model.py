@@ -193,3 +193,33 @@ def test_decoder_multi_quantizer_tokens():
     text, z = torch.randn(2, 5, 64), torch.randn(2, 16)
     with torch.no_grad():
         check("3-D tokens", dec(tok.cuda(), text.cuda(), z.cuda()), ref(tok, text, z), FP32_TOL)
+
+
+def test_train_step_microbatching_and_ref_hidden():
+    """TrainStep (fwd + CE + bwd + clip + Adam, train.py:220-235): two micro-batches of 2 give the
+    same update as one batch of 4, with ref_hidden built by embed_codec_tokens (train.py:115-131)."""
+    from mamba_tts_project_b200 import MambaTTSDecoder, TrainStep
+    cfg = dict(vocab_size_audio=48, d_model=64, n_layers=2, n_heads=4, d_ff=128, d_style=16,
+               max_len=128, num_quantizers=2)
+    torch.manual_seed(0)
+    base = MambaTTSDecoder(**cfg).cuda()
+    tok = torch.randint(1, 48, (4, 40)).cuda()
+    tok[0, -5:] = 0                                   # padding is ignored by the loss
+    text, z = torch.randn(4, 9, 64).cuda(), torch.randn(4, 16).cuda()
+    voice = torch.randint(0, 48, (4, 2, 6)).cuda()
+    voice[:, :, 0] = 1                                # at least one attendable reference token
+    results = []
+    for mb in (None, 2):
+        dec = MambaTTSDecoder(**cfg).cuda()
+        dec.load_state_dict(base.state_dict())
+        step = TrainStep(dec, lr=1e-3, amp_dtype=None, micro_batch=mb)
+        tmask = torch.ones(4, 9, dtype=torch.bool, device="cuda")
+        loss = step(tok, text, z, text_mask=tmask, ref_tokens=voice)
+        results.append((loss.item(), {k: v.detach().clone() for k, v in dec.named_parameters()}))
+    assert abs(results[0][0] - results[1][0]) < 1e-5 * abs(results[0][0])
+    changed = 0
+    for k in results[0][1]:
+        a, b = results[0][1][k], results[1][1][k]
+        assert (a - b).abs().max() <= 2e-5 * max(1.0, a.abs().max().item()), k
+        changed += int((a - dict(base.named_parameters())[k]).abs().max() > 0)
+    assert changed > 10
