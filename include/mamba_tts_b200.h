@@ -312,6 +312,36 @@ typedef struct {
 } mtts_add_layernorm_bwd_params;
 int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * skinny_linear -- decode_step's projections for m <= 64 rows in one launch:
+ *     out = act( A @ W^T + bias ),  A = a                                   (ln_mode == 0)
+ *                                   A = FiLM(LN(x + delta))                 (ln_mode == 1)
+ * replaces nn.LayerNorm + residual add + nn.Linear (+ nn.GELU) of mamba_decoder.py:59-89 when the
+ * sequence length is 1.  a (m, k) io dtype; x / x_out (m, k) fp32 residual stream (x_out receives
+ * x + delta and must NOT alias x); delta (m, k) io dtype or NULL; film_gamma/beta (m, k) fp32 per-row
+ * terms or NULL; w (n, k) and bias (n) io dtype; out (m, n) io dtype.  io dtype must be MTTS_BF16;
+ * k % 16 == 0, and k <= 1024 when ln_mode.  gelu != 0 applies the exact (erf) GELU.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t m, n, k;
+  int32_t io_dtype;
+  int32_t ln_mode;
+  int32_t gelu;
+  float eps;
+  const void* a;
+  const float* x;
+  const void* delta;
+  float* x_out;
+  const float* ln_weight;
+  const float* ln_bias;
+  const float* film_gamma;
+  const float* film_beta;
+  const void* w;
+  const void* bias;
+  void* out;
+} mtts_skinny_linear_params;
+int mtts_skinny_linear(const mtts_skinny_linear_params* p, mtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

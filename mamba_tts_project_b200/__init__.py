@@ -14,11 +14,12 @@ from .decoder import (CrossAttention, GenerationContext, MambaTTSDecoder, MambaT
 from .mamba import Mamba
 from .training import TrainStep, codec_ce_loss, embed_codec_tokens
 from .ops import (causal_conv1d_fn, causal_conv1d_update, cross_attn_decode, add_layernorm,
-                  mamba_decode_step, mamba_inner_fn, selective_scan_fn, selective_state_update)
+                  mamba_decode_step, mamba_inner_fn, selective_scan_fn, selective_state_update,
+                  skinny_linear)
 
 __all__ = ["TrainStep", "codec_ce_loss", "embed_codec_tokens", "Mamba", "MambaTTSDecoder", "MambaTTSDecoderLayer", "CrossAttention", "GenerationContext",
            "selective_scan_fn", "selective_state_update", "causal_conv1d_fn", "causal_conv1d_update",
-           "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode", "add_layernorm"]
+           "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode", "add_layernorm", "skinny_linear"]
 __version__ = "0.1.0"
 
 

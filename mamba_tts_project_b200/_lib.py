@@ -102,10 +102,14 @@ AddLayerNormBwdParams = _struct("AddLayerNormBwdParams", """
     i:rows i:dim i:rows_per_batch i:io_dtype
     p:x_out p:mean p:rstd p:ln_weight p:film_gamma p:dout p:dx_out p:dx p:ddelta p:colsum""")
 
+SkinnyLinearParams = _struct("SkinnyLinearParams", """
+    i:m i:n i:k i:io_dtype i:ln_mode i:gelu f:eps
+    p:a p:x p:delta p:x_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:w p:bias p:out""")
+
 # declaration order of the header == argument of mtts_sizeof_params
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
-                 AddLayerNormFwdParams, AddLayerNormBwdParams]
+                 AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -123,6 +127,7 @@ ENTRY_POINTS = {
     "mtts_cross_attn_decode": CrossAttnDecodeParams,
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
+    "mtts_skinny_linear": SkinnyLinearParams,
 }
 
 _lib = None

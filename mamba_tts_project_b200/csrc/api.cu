@@ -34,6 +34,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 7: return (int)sizeof(mtts_cross_attn_decode_params);
     case 8: return (int)sizeof(mtts_add_layernorm_fwd_params);
     case 9: return (int)sizeof(mtts_add_layernorm_bwd_params);
+    case 10: return (int)sizeof(mtts_skinny_linear_params);
     default: return -1;
   }
 }

@@ -155,9 +155,13 @@ class GenerationContext:
     """Everything that is constant over one generation (``decode_step``'s D9 recomputations)."""
 
     def __init__(self, decoder: "MambaTTSDecoder", text_hidden, z_style, text_mask=None,
-                 ref_hidden=None, ref_mask=None, dtype=None):
+                 ref_hidden=None, ref_mask=None, dtype=None, fused_projections=False):
         dtype = dtype if dtype is not None else text_hidden.dtype
         self.dtype = dtype
+        # opt-in: LN + projection (+GELU) as one skinny_linear launch (8 launches per layer instead
+        # of 14).  Measured on B200 at B = 64: 0.89 ms/step vs 0.74 ms/step for LayerNorm kernel +
+        # library GEMM, so it is off by default until the kernel's latency chain is shortened.
+        self.fused_projections = fused_projections
         with torch.no_grad():
             memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
             self.batch = memory.shape[0]
@@ -168,6 +172,11 @@ class GenerationContext:
                            decoder.norm_out.bias.detach().to(f32).contiguous(), decoder.norm_out.eps)
             self.head_w = decoder.head.weight.detach().to(dtype).contiguous()
             self.head_b = decoder.head.bias.detach().to(dtype).contiguous()
+            # skinny_linear needs every plain-mode K to be <= 512 or a multiple of 512
+            self.fused_ok = all(k <= 512 or k % 512 == 0 for k in
+                                (decoder.layers[0].mamba.d_inner, decoder.layers[0].ff[0].out_features)) \
+                and decoder.layers[0].mamba.d_inner % 16 == 0 \
+                and decoder.layers[0].ff[0].out_features % 16 == 0
             self.tok = decoder.token_embed.weight.detach().float().contiguous()
             self.pos = decoder.pos_embed.weight.detach().float().contiguous()
 
@@ -219,8 +228,9 @@ class MambaTTSDecoder(nn.Module):
 
     # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------
     def prepare_generation(self, text_hidden, z_style, text_mask=None, ref_hidden=None,
-                           ref_mask=None, dtype=None):
-        return GenerationContext(self, text_hidden, z_style, text_mask, ref_hidden, ref_mask, dtype)
+                           ref_mask=None, dtype=None, fused_projections=False):
+        return GenerationContext(self, text_hidden, z_style, text_mask, ref_hidden, ref_mask, dtype,
+                                 fused_projections)
 
     def allocate_states(self, batch, dtype):
         return [l.mamba.allocate_inference_cache(batch, dtype=dtype) for l in self.layers]
@@ -236,6 +246,9 @@ class MambaTTSDecoder(nn.Module):
 
     def _step_core(self, ctx: GenerationContext, x, states):
         """x (B, d_model) fp32 residual stream of the new token -> logits (B, V); states in place."""
+        if ctx.fused_projections and ctx.dtype == torch.bfloat16 and x.shape[0] <= 64 \
+                and x.shape[1] in (128, 256, 512, 1024) and ctx.fused_ok:
+            return self._step_core_fused(ctx, x, states)
         delta = None  # pending branch output, folded into the next LayerNorm launch
         dt = ctx.dtype
         for lw, (conv_state, ssm_state) in zip(ctx.layers, states):
@@ -258,6 +271,35 @@ class MambaTTSDecoder(nn.Module):
         _, h = ops.add_layernorm(x, delta, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], out_dtype=dt,
                                  inplace=True)
         return F.linear(h, ctx.head_w, ctx.head_b)
+
+    def _step_core_fused(self, ctx: GenerationContext, x, states):
+        """bf16, batch <= 64: every (residual add + LayerNorm [+ FiLM] + projection [+ GELU]) is ONE
+        skinny_linear launch -- 8 launches per layer instead of 14.  The fp32 residual stream
+        ping-pongs between two buffers (x_out must not alias x inside a launch)."""
+        cur, other = x, torch.empty_like(x)
+        delta = None
+
+        def ln_linear(ln, w, bias, gamma=None, beta=None, gelu=False):
+            nonlocal cur, other, delta
+            out = ops.skinny_linear(w, bias, x=cur, delta=delta, x_out=None if delta is None else other,
+                                    ln_weight=ln[0], ln_bias=ln[1], eps=ln[2], gamma=gamma, beta=beta,
+                                    gelu=gelu)
+            if delta is not None:
+                cur, other = other, cur
+            return out
+
+        for lw, (conv_state, ssm_state) in zip(ctx.layers, states):
+            xz = ln_linear(lw.ln1, lw.mamba["in_proj"], lw.mamba["in_bias"])
+            y = ops.mamba_decode_step(xz, conv_state, ssm_state, lw.mamba["conv_w"],
+                                      lw.mamba["conv_b"], lw.mamba["x_proj"], lw.mamba["dt_proj"],
+                                      lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"])
+            delta = ops.skinny_linear(lw.mamba["out_proj"], lw.mamba["out_bias"], a=y)
+            q = ln_linear(lw.ln2, lw.wq, lw.bq)
+            a = ops.cross_attn_decode(q, lw.k, lw.v, lw.heads, mask=ctx.mask)
+            delta = ops.skinny_linear(lw.wo, lw.bo, a=a)
+            f = ln_linear(lw.ln3, lw.w1, lw.b1, gamma=lw.gamma, beta=lw.beta, gelu=True)
+            delta = ops.skinny_linear(lw.w2, lw.b2, a=f)
+        return ln_linear(ctx.ln_out, ctx.head_w, ctx.head_b)
 
     @torch.no_grad()
     def decode_step(self, last_token, text_hidden, z_style, mamba_states, step_index: int,

@@ -22,7 +22,7 @@ from ._lib import ptr
 
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
-           "add_layernorm"]
+           "add_layernorm", "skinny_linear"]
 
 
 def _unit_last_stride(t):
@@ -480,3 +480,32 @@ def add_layernorm(x, delta, weight, bias, eps=1e-5, gamma=None, beta=None, out_d
     if out_dtype is None:
         out_dtype = delta.dtype if delta is not None else x.dtype
     return _AddLayerNormFn.apply(x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace)
+
+
+def skinny_linear(w, bias=None, a=None, x=None, delta=None, x_out=None, ln_weight=None, ln_bias=None,
+                  eps=1e-5, gamma=None, beta=None, gelu=False):
+    """decode_step projection for <= 64 rows (bf16): ``out = act(A @ w.T + bias)`` with ``A = a`` or
+    ``A = FiLM(LN(x + delta))`` (then ``x_out`` receives ``x + delta``; it must not alias ``x``).
+    w (n, k), bias (n), a / delta (m, k) bf16; x, x_out (m, k) fp32; gamma / beta (m, k) fp32."""
+    _lib.require_cuda(w, bias, a, x, delta, x_out, gamma, beta)
+    ln = a is None
+    src = x if ln else a
+    m, k = src.shape
+    n = w.shape[0]
+    if w.shape[1] != k or w.dtype != torch.bfloat16 or not w.is_contiguous():
+        raise RuntimeError("w must be contiguous bf16 (n, k)")
+    for t in (a, x, delta, x_out, gamma, beta, bias):
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError("skinny_linear operands must be contiguous")
+    if ln and (x.dtype != torch.float32 or (delta is not None and delta.dtype != torch.bfloat16)):
+        raise RuntimeError("x must be fp32 and delta bf16")
+    if not ln and a.dtype != torch.bfloat16:
+        raise RuntimeError("a must be bf16")
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=w.device)
+    p = _lib.SkinnyLinearParams(
+        m=m, n=n, k=k, io_dtype=_lib.BF16, ln_mode=int(ln), gelu=int(bool(gelu)), eps=eps,
+        a=ptr(a), x=ptr(x), delta=ptr(delta), x_out=ptr(x_out), ln_weight=ptr(ln_weight),
+        ln_bias=ptr(ln_bias), film_gamma=ptr(gamma), film_beta=ptr(beta), w=ptr(w), bias=ptr(bias),
+        out=ptr(out))
+    _lib.call("mtts_skinny_linear", p)
+    return out

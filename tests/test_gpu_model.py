@@ -176,13 +176,15 @@ def test_decoder_bf16_decode_tracks_fp32():
             tok = lg.argmax(-1)
             toks.append(tok)
             ref_lg.append(lg)
-        ctx = dec.prepare_generation(text.cuda(), z.cuda(), dtype=torch.bfloat16)
-        st = dec.allocate_states(4, torch.bfloat16)
-        got = []
-        for i in range(12):  # teacher-forced on the oracle's tokens so the comparison is per step
-            x = (ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]).float()
-            got.append(dec._step_core(ctx, x.contiguous(), st)[:, None])
-    check("bf16 step logits", torch.cat(got, 1), torch.cat(ref_lg, 1), 4e-2)
+        for fused in (False, True):   # library GEMMs / fused skinny_linear projections
+            ctx = dec.prepare_generation(text.cuda(), z.cuda(), dtype=torch.bfloat16,
+                                         fused_projections=fused)
+            st = dec.allocate_states(4, torch.bfloat16)
+            got = []
+            for i in range(12):  # teacher-forced on the oracle's tokens: per-step comparison
+                x = (ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]).float()
+                got.append(dec._step_core(ctx, x.contiguous(), st)[:, None])
+            check(f"bf16 step logits (fused={fused})", torch.cat(got, 1), torch.cat(ref_lg, 1), 4e-2)
 
 
 def test_decoder_multi_quantizer_tokens():

@@ -343,3 +343,46 @@ def test_add_layernorm_fwd_bwd_vs_torch(shape, dtype, film):
     check("inplace x", x2, xs, 1e-6)
     _, ho3 = add_layernorm(x.cuda(), None, w.cuda(), b.cuda(), out_dtype=dtype)
     check("plain ln", ho3, torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5), t)
+
+
+@pytest.mark.parametrize("shape", [(64, 512, 2048), (64, 2048, 512), (3, 128, 40), (17, 1024, 512),
+                                   (64, 512, 1024)], ids=["ff1", "ff2", "tiny", "k1024", "head"])
+def test_skinny_linear_vs_torch(shape):
+    """decode-step projection kernel (bf16, <= 64 rows): plain, and fused with residual add + LN +
+    FiLM + GELU (mamba_decoder.py:59-89 at T = 1)."""
+    from mamba_tts_project_b200 import skinny_linear
+    m, k, n = shape
+    g = torch.Generator().manual_seed(m + k + n)
+    bf = torch.bfloat16
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(bf)
+    b = torch.randn(n, generator=g).to(bf)
+    a = torch.randn(m, k, generator=g).to(bf)
+    ref = torch.nn.functional.linear(a.float(), w.float(), b.float())
+    out = skinny_linear(w.cuda(), b.cuda(), a=a.cuda())
+    check("plain", out, ref, BF16_TOL)
+    out = skinny_linear(w.cuda(), None, a=a.cuda())
+    check("no bias", out, torch.nn.functional.linear(a.float(), w.float()), BF16_TOL)
+    if k in (128, 256, 512, 1024):
+        x = torch.randn(m, k, generator=g)
+        dl = torch.randn(m, k, generator=g).to(bf)
+        lw, lb = torch.randn(k, generator=g), torch.randn(k, generator=g)
+        gam, bet = torch.randn(m, k, generator=g), torch.randn(m, k, generator=g)
+        xs = x + dl.float()
+        h = torch.nn.functional.layer_norm(xs, (k,), lw, lb, 1e-5)
+        ref_ln = torch.nn.functional.linear(h.to(bf).float(), w.float(), b.float())
+        xo = torch.empty(m, k, device="cuda")
+        out = skinny_linear(w.cuda(), b.cuda(), x=x.cuda(), delta=dl.cuda(), x_out=xo,
+                            ln_weight=lw.cuda(), ln_bias=lb.cuda())
+        check("ln", out, ref_ln, BF16_TOL)
+        check("x_out", xo, xs, 1e-6)
+        hf = (gam * h + bet)
+        ref_f = torch.nn.functional.gelu(
+            torch.nn.functional.linear(hf.to(bf).float(), w.float(), b.float()))
+        out = skinny_linear(w.cuda(), b.cuda(), x=x.cuda(), delta=dl.cuda(), x_out=xo,
+                            ln_weight=lw.cuda(), ln_bias=lb.cuda(), gamma=gam.cuda(), beta=bet.cuda(),
+                            gelu=True)
+        check("ln+film+gelu", out, ref_f, BF16_TOL)
+        out = skinny_linear(w.cuda(), b.cuda(), x=x.cuda(), ln_weight=lw.cuda(), ln_bias=lb.cuda())
+        ref0 = torch.nn.functional.linear(
+            torch.nn.functional.layer_norm(x, (k,), lw, lb, 1e-5).to(bf).float(), w.float(), b.float())
+        check("ln no delta", out, ref0, BF16_TOL)
