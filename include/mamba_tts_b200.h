@@ -342,6 +342,28 @@ typedef struct {
 } mtts_skinny_linear_params;
 int mtts_skinny_linear(const mtts_skinny_linear_params* p, mtts_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * gemm_bf16 -- the FFN contractions of mamba_decoder.py:39-43,88 on the tcgen05 tensor cores:
+ *     out[m, n] = act( sum_k a[m, k] * w[n, k] + bias[n] )      act = exact-erf GELU when gelu != 0
+ * a (m, k) and w (n, k) bf16, K contiguous (nn.Linear layout), leading dimensions lda / ldw / ldo in
+ * elements (multiples of 8); bias (n) fp32 or NULL; out (m, n) bf16; pre_out (m, n) bf16, optional:
+ * the pre-activation a backward pass needs.  fp32 accumulation in tensor memory.  k % 8 == 0, n % 8 == 0.
+ * Replaces nn.Linear (+ nn.GELU) = a cuBLASLt GEMM plus an elementwise kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t m, n, k;
+  int32_t gelu;
+  const void* a;
+  int64_t lda;
+  const void* w;
+  int64_t ldw;
+  const float* bias;
+  void* out;
+  int64_t ldo;
+  void* pre_out;
+} mtts_gemm_bf16_params;
+int mtts_gemm_bf16(const mtts_gemm_bf16_params* p, mtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

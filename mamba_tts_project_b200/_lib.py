@@ -106,10 +106,14 @@ SkinnyLinearParams = _struct("SkinnyLinearParams", """
     i:m i:n i:k i:io_dtype i:ln_mode i:gelu f:eps
     p:a p:x p:delta p:x_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:w p:bias p:out""")
 
+GemmBf16Params = _struct("GemmBf16Params", """
+    i:m i:n i:k i:gelu p:a l:lda p:w l:ldw p:bias p:out l:ldo p:pre_out""")
+
 # declaration order of the header == argument of mtts_sizeof_params
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
-                 AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams]
+                 AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
+                 GemmBf16Params]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -128,6 +132,7 @@ ENTRY_POINTS = {
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,
+    "mtts_gemm_bf16": GemmBf16Params,
 }
 
 _lib = None

@@ -35,6 +35,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 8: return (int)sizeof(mtts_add_layernorm_fwd_params);
     case 9: return (int)sizeof(mtts_add_layernorm_bwd_params);
     case 10: return (int)sizeof(mtts_skinny_linear_params);
+    case 11: return (int)sizeof(mtts_gemm_bf16_params);
     default: return -1;
   }
 }

@@ -22,7 +22,7 @@ from ._lib import ptr
 
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
-           "add_layernorm", "skinny_linear"]
+           "add_layernorm", "skinny_linear", "gemm_bf16"]
 
 
 def _unit_last_stride(t):
@@ -509,3 +509,27 @@ def skinny_linear(w, bias=None, a=None, x=None, delta=None, x_out=None, ln_weigh
         out=ptr(out))
     _lib.call("mtts_skinny_linear", p)
     return out
+
+
+def gemm_bf16(a, w, bias=None, gelu=False, return_pre=False):
+    """tcgen05 tensor-core GEMM with fused epilogue: ``act(a @ w.T + bias)``.
+    a (..., k) bf16 with unit stride along k; w (n, k) bf16; bias (n) fp32.  Returns out (..., n) bf16
+    [, pre-activation (..., n) bf16 when ``return_pre``]."""
+    _lib.require_cuda(a, w, bias)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise RuntimeError("gemm_bf16 takes bf16 operands")
+    k = a.shape[-1]
+    a2 = a.reshape(-1, k)
+    if a2.stride(-1) != 1:
+        a2 = a2.contiguous()
+    if w.stride(-1) != 1 or w.shape[1] != k:
+        raise RuntimeError("w must be (n, k) with unit stride along k")
+    m, n = a2.shape[0], w.shape[0]
+    b32 = _f32c(bias)
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    pre = torch.empty_like(out) if return_pre else None
+    p = _lib.GemmBf16Params(m=m, n=n, k=k, gelu=int(bool(gelu)), a=ptr(a2), lda=a2.stride(0), w=ptr(w),
+                            ldw=w.stride(0), bias=ptr(b32), out=ptr(out), ldo=n, pre_out=ptr(pre))
+    _lib.call("mtts_gemm_bf16", p)
+    out = out.view(*a.shape[:-1], n)
+    return (out, pre.view(*a.shape[:-1], n)) if return_pre else out
