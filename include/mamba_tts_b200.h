@@ -270,7 +270,8 @@ int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t
  * the memory-bound glue of mamba_decoder.py:59,64,67,78,81-86,89 in one pass per tensor.
  *   x_out = x + delta                 (x, x_out: fp32 residual stream; delta: io dtype, optional)
  *   out   = LN(x_out) * w + b ; out = gamma_b * out + beta_b   (gamma/beta (batch, dim) fp32, optional)
- * rows = batch * rows_per_batch; all (rows, dim) tensors contiguous; dim % 4 == 0, dim <= 2048
+ * rows = batch * rows_per_batch; all (rows, dim) tensors contiguous; delta_bias (dim) fp32 optional (the bias of the Linear that produced
+ * delta: x_out = x + delta + delta_bias); dim % 4 == 0, dim <= 2048
  * (backward: dim <= 1024).  x_out may alias x.  mean / rstd (rows) fp32 are saved for the backward.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -279,6 +280,7 @@ typedef struct {
   float eps;
   const float* x;
   const void* delta; /* or NULL */
+  const float* delta_bias; /* (dim) fp32 bias added together with delta, or NULL */
   float* x_out;      /* or NULL (then x_out == x is implied and nothing is written) */
   const float* ln_weight;
   const float* ln_bias;
@@ -292,8 +294,8 @@ int mtts_add_layernorm_fwd(const mtts_add_layernorm_fwd_params* p, mtts_stream_t
 
 /* Backward of the above.  dout (io dtype) = grad of `out`; dx_out (fp32, optional) = grad that
  * reaches x_out from the rest of the residual stream.  Writes dx (fp32) = grad of x, and ddelta
- * (io dtype, optional) = the same values for the branch.  colsum (batch, 2, dim) fp32 is ACCUMULATED
- * INTO with S1 = sum_t dout * xhat and S2 = sum_t dout per batch element; the parameter gradients
+ * (io dtype, optional) = the same values for the branch.  colsum (batch, 3, dim) fp32 is ACCUMULATED
+ * INTO with S1 = sum_t dout * xhat, S2 = sum_t dout and S3 = sum_t dx (= grad of delta_bias) per batch element; the parameter gradients
  * are linear combinations of S1/S2 the caller forms on (batch, dim)-sized tensors:
  *   dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b, dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b. */
 typedef struct {

@@ -96,7 +96,7 @@ CrossAttnDecodeParams = _struct("CrossAttnDecodeParams", """
 
 AddLayerNormFwdParams = _struct("AddLayerNormFwdParams", """
     i:rows i:dim i:rows_per_batch i:io_dtype f:eps
-    p:x p:delta p:x_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:out p:mean p:rstd""")
+    p:x p:delta p:delta_bias p:x_out p:ln_weight p:ln_bias p:film_gamma p:film_beta p:out p:mean p:rstd""")
 
 AddLayerNormBwdParams = _struct("AddLayerNormBwdParams", """
     i:rows i:dim i:rows_per_batch i:io_dtype

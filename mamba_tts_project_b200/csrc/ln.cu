@@ -35,6 +35,11 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
         load4<T>(dl + e, d);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[g][j] += d[j];
+        if (p.delta_bias) {  // bias of the Linear that produced delta, folded in here
+          load4<float>(p.delta_bias + e, d);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[g][j] += d[j];
+        }
       }
       if (p.x_out) store4<float>(p.x_out + (int64_t)row * Dm + e, v[g]);
 #pragma unroll
@@ -90,13 +95,13 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
 // Backward.  With xhat = (x_out - mean) rstd, y = xhat w + b, out = gamma y + beta:
 //   g      = dout * gamma * w                       (d/d xhat)
 //   dx     = dx_out + rstd (g - mean_e(g) - xhat mean_e(g xhat))
-//   S1[b]  = sum_t dout xhat,  S2[b] = sum_t dout   (per batch element and column, accumulated into
-//            `colsum` (batch, 2, dim)); the host finishes dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b,
+//   S1[b]  = sum_t dout xhat,  S2[b] = sum_t dout,  S3[b] = sum_t dx  (per batch element and column,
+//            accumulated into `colsum` (batch, 3, dim)); S3 is the gradient of delta's bias; the host finishes dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b,
 //            dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b  on (batch, dim)-sized tensors.
 template <typename T, int kG>
 __global__ void __launch_bounds__(kLnWarps * 32)
 add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_per_warp) {
-  __shared__ float red[kLnWarps][2][kG * 128];
+  __shared__ float red[kLnWarps][3][kG * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dm = p.dim;
   // a CTA never straddles two batch elements: grid.x tiles rows_per_batch, grid.y = batch
@@ -105,7 +110,7 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
   const int r_end = min(p.rows_per_batch, r_begin + rows_per_warp);
   const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
 
-  float w[kG][4], s1[kG][4], s2[kG][4];
+  float w[kG][4], s1[kG][4], s2[kG][4], s3[kG][4];
 #pragma unroll
   for (int g = 0; g < kG; ++g) {
     const int e = (g * 32 + lane) * 4;
@@ -122,7 +127,7 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
       for (int j = 0; j < 4; ++j) w[g][j] = 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) s1[g][j] = s2[g][j] = 0.f;
+    for (int j = 0; j < 4; ++j) s1[g][j] = s2[g][j] = s3[g][j] = 0.f;
   }
 
   for (int r = r_begin; r < r_end; ++r) {
@@ -168,6 +173,8 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
 #pragma unroll
           for (int j = 0; j < 4; ++j) dx[j] += up[j];
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s3[g][j] += dx[j];
         store4<float>(p.dx + row * Dm + e, dx);
         if (p.ddelta) store4<T>(reinterpret_cast<T*>(p.ddelta) + row * Dm + e, dx);
       }
@@ -181,15 +188,16 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
     for (int j = 0; j < 4; ++j) {
       red[warp][0][(g * 32 + lane) * 4 + j] = s1[g][j];
       red[warp][1][(g * 32 + lane) * 4 + j] = s2[g][j];
+      red[warp][2][(g * 32 + lane) * 4 + j] = s3[g][j];
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 2 * Dm; idx += kLnWarps * 32) {
+  for (int idx = threadIdx.x; idx < 3 * Dm; idx += kLnWarps * 32) {
     const int which = idx / Dm, e = idx - which * Dm;
     float t = 0.f;
 #pragma unroll
     for (int wv = 0; wv < kLnWarps; ++wv) t += red[wv][which][e];
-    atomicAdd(p.colsum + ((int64_t)bidx * 2 + which) * Dm + e, t);
+    atomicAdd(p.colsum + ((int64_t)bidx * 3 + which) * Dm + e, t);
   }
 }
 

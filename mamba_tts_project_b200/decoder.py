@@ -65,8 +65,10 @@ class CrossAttention(nn.Module):
         kv = F.linear(memory, w[E:], b[E:])     # one GEMM for both projections
         return kv[..., :E], kv[..., E:]
 
-    def forward(self, query, memory, key_padding_mask=None):
-        """query (B, T, E); memory (B, T_kv, E); key_padding_mask (B, T_kv) True = IGNORE."""
+    def forward(self, query, memory, key_padding_mask=None, add_out_bias=True):
+        """query (B, T, E); memory (B, T_kv, E); key_padding_mask (B, T_kv) True = IGNORE.
+        ``add_out_bias=False`` leaves out_proj.bias to the caller (it is folded into the next fused
+        residual-add + LayerNorm launch together with its gradient)."""
         B, T, E = query.shape
         H, dh = self.num_heads, self.head_dim
         q = F.linear(query, self.in_proj_weight[:E], self.in_proj_bias[:E])
@@ -80,7 +82,7 @@ class CrossAttention(nn.Module):
             bias.masked_fill_(key_padding_mask[:, None, None, :], float("-inf"))
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias)
         o = o.transpose(1, 2).reshape(B, T, E)
-        return self.out_proj(o)
+        return F.linear(o, self.out_proj.weight, self.out_proj.bias if add_out_bias else None)
 
 
 class MambaTTSDecoderLayer(nn.Module):
@@ -94,31 +96,36 @@ class MambaTTSDecoderLayer(nn.Module):
         self.ff = nn.Sequential(nn.Linear(d_model, d_ff), nn.GELU(), nn.Linear(d_ff, d_model))
         self.style_mlp = nn.Sequential(nn.Linear(d_style, 2 * d_model), nn.Tanh())
 
-    def forward_fused(self, x, delta, text_hidden, z_style, text_mask=None, mamba_state=None):
+    def forward_fused(self, x, delta, text_hidden, z_style, text_mask=None, mamba_state=None,
+                      delta_bias=None):
         """The layer with every ``x = x + branch`` folded into the LayerNorm that follows it.
 
-        x: fp32 residual stream (B, T, D); delta: branch output still to be added to x (or None).
-        Returns (x, delta_out, new_state) with the layer's result being ``x + delta_out``."""
+        x: fp32 residual stream (B, T, D); delta (+ delta_bias): branch output still to be added to x
+        (or None).  Returns (x, delta_out, delta_bias_out, new_state): the layer's result is
+        ``x + delta_out + delta_bias_out``."""
         cdt = compute_dtype(x)
         x, h = ops.add_layernorm(x, delta, self.norm_mamba.weight, self.norm_mamba.bias,
-                                 self.norm_mamba.eps, out_dtype=cdt)
+                                 self.norm_mamba.eps, out_dtype=cdt, delta_bias=delta_bias)
         h_mamba, new_state = self.mamba(h) if mamba_state is None else self.mamba(h, mamba_state)
 
         x, h = ops.add_layernorm(x, h_mamba, self.norm_cross.weight, self.norm_cross.bias,
                                  self.norm_cross.eps, out_dtype=cdt)
         key_padding_mask = None if text_mask is None else ~text_mask
-        attn_out = self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask)
+        attn_out = self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask,
+                                   add_out_bias=False)
 
         gamma, beta = torch.chunk(self.style_mlp(z_style), 2, dim=-1)
         x, h = ops.add_layernorm(x, attn_out, self.norm_ff.weight, self.norm_ff.bias,
-                                 self.norm_ff.eps, gamma=gamma, beta=beta, out_dtype=cdt)
-        return x, self.ff(h), new_state
+                                 self.norm_ff.eps, gamma=gamma, beta=beta, out_dtype=cdt,
+                                 delta_bias=self.cross_attn.out_proj.bias)
+        f = F.linear(self.ff[1](self.ff[0](h)), self.ff[2].weight)   # ff[2].bias rides with delta
+        return x, f, self.ff[2].bias, new_state
 
     def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):
         """Reference signature (``mamba_decoder.py:50-91``): returns (x, new_state)."""
-        xs, delta, new_state = self.forward_fused(x.float(), None, text_hidden, z_style, text_mask,
-                                                  mamba_state)
-        return (xs + delta.float()).to(x.dtype), new_state
+        xs, delta, dbias, new_state = self.forward_fused(x.float(), None, text_hidden, z_style,
+                                                         text_mask, mamba_state)
+        return (xs + delta.float() + dbias.float()).to(x.dtype), new_state
 
 
 class _LayerStepWeights:
@@ -219,11 +226,12 @@ class MambaTTSDecoder(nn.Module):
         memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
 
         x = self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None] + self.quant_embed(quant_ids)
-        x, delta = x.float(), None
+        x, delta, dbias = x.float(), None, None
         for layer in self.layers:
-            x, delta, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask)
+            x, delta, dbias, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask,
+                                                     delta_bias=dbias)
         _, h = ops.add_layernorm(x, delta, self.norm_out.weight, self.norm_out.bias,
-                                 self.norm_out.eps, out_dtype=compute_dtype(x))
+                                 self.norm_out.eps, out_dtype=compute_dtype(x), delta_bias=dbias)
         return self.head(h)
 
     # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------

@@ -381,8 +381,10 @@ class _AddLayerNormFn(torch.autograd.Function):
     """(x_out, out) = add_layernorm(x, delta, w, b, gamma, beta): see ``mtts_add_layernorm_fwd``."""
 
     @staticmethod
-    def forward(ctx, x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace):
-        _lib.require_cuda(x, delta, weight, bias, gamma, beta)
+    def forward(ctx, x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace, delta_bias):
+        _lib.require_cuda(x, delta, weight, bias, gamma, beta, delta_bias)
+        if delta_bias is not None and delta is None:
+            raise RuntimeError("delta_bias needs delta")
         if x.dtype != torch.float32:
             raise RuntimeError("the residual stream x must be fp32")
         shape = x.shape
@@ -404,7 +406,9 @@ class _AddLayerNormFn(torch.autograd.Function):
             if not d2.is_contiguous():
                 d2 = d2.contiguous()
         w32, b32, g32, be32 = _f32c(weight), _f32c(bias), _f32c(gamma), _f32c(beta)
-        need = any(t is not None and t.requires_grad for t in (x, delta, weight, bias, gamma, beta))
+        db32 = _f32c(delta_bias)
+        need = any(t is not None and t.requires_grad
+                   for t in (x, delta, weight, bias, gamma, beta, delta_bias))
         out = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
         if d2 is None:
             x_out = x2
@@ -415,14 +419,16 @@ class _AddLayerNormFn(torch.autograd.Function):
         if rows:
             p = _lib.AddLayerNormFwdParams(
                 rows=rows, dim=dim, rows_per_batch=rpb, io_dtype=_lib.io_dtype(out), eps=eps,
-                x=ptr(x2), delta=ptr(d2), x_out=None if d2 is None else ptr(x_out),
+                x=ptr(x2), delta=ptr(d2), delta_bias=ptr(db32),
+                x_out=None if d2 is None else ptr(x_out),
                 ln_weight=ptr(w32), ln_bias=ptr(b32), film_gamma=ptr(g32), film_beta=ptr(be32),
                 out=ptr(out), mean=ptr(mean), rstd=ptr(rstd))
             _lib.call("mtts_add_layernorm_fwd", p)
         ctx.save_for_backward(x_out, mean, rstd, w32, b32, g32)
         ctx.meta = (rows, dim, rpb, shape, delta is not None,
                     None if delta is None else delta.dtype, weight.dtype, bias.dtype,
-                    None if gamma is None else gamma.dtype)
+                    None if gamma is None else gamma.dtype,
+                    None if delta_bias is None else delta_bias.dtype)
         if inplace and d2 is not None:
             if x2.data_ptr() != x.data_ptr():
                 raise RuntimeError("inplace add_layernorm needs a contiguous x")
@@ -433,7 +439,7 @@ class _AddLayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx_out, dout):
         x_out, mean, rstd, w32, b32, g32 = ctx.saved_tensors
-        rows, dim, rpb, shape, has_delta, t_delta, t_w, t_b, t_g = ctx.meta
+        rows, dim, rpb, shape, has_delta, t_delta, t_w, t_b, t_g, t_db = ctx.meta
         dev = x_out.device
         batch = rows // rpb
         io = dout.dtype if dout is not None else torch.float32
@@ -450,7 +456,7 @@ class _AddLayerNormFn(torch.autograd.Function):
         dx = torch.empty((rows, dim), dtype=torch.float32, device=dev)
         ddelta = torch.empty((rows, dim), dtype=t_delta, device=dev) \
             if has_delta and t_delta == io else None
-        colsum = torch.zeros((batch, 2, dim), dtype=torch.float32, device=dev)
+        colsum = torch.zeros((batch, 3, dim), dtype=torch.float32, device=dev)
         if rows:
             p = _lib.AddLayerNormBwdParams(
                 rows=rows, dim=dim, rows_per_batch=rpb, io_dtype=_lib.io_dtype(dout2),
@@ -466,20 +472,24 @@ class _AddLayerNormFn(torch.autograd.Function):
             dgamma, dbeta = (w32 * s1 + b32 * s2).to(t_g), s2.to(t_g)
         if has_delta and ddelta is None:
             ddelta = dx.to(t_delta)
+        ddb = None if t_db is None else colsum[:, 2].sum(0).to(t_db)
         return (dx.view(shape), None if not has_delta else ddelta.view(shape), dw.to(t_w),
-                db.to(t_b), dgamma, dbeta, None, None, None)
+                db.to(t_b), dgamma, dbeta, None, None, None, ddb)
 
 
 def add_layernorm(x, delta, weight, bias, eps=1e-5, gamma=None, beta=None, out_dtype=None,
-                  inplace=False):
+                  inplace=False, delta_bias=None):
     """Fused ``x_out = x + delta ; out = LN(x_out) [* gamma_b + beta_b]`` (``mamba_decoder.py:59-89``).
 
     x: (..., dim) fp32 residual stream; delta: same shape, activation dtype, or None; weight/bias:
     LayerNorm affine; gamma/beta: (batch, dim) FiLM terms or None.  Returns (x_out fp32, out in
-    ``out_dtype``).  ``inplace`` writes x_out over x (inference only)."""
+    ``out_dtype``).  ``inplace`` writes x_out over x (inference only).  ``delta_bias`` (dim,): bias of the
+    Linear that produced delta, added here (x_out = x + delta + delta_bias) so that neither the add nor
+    its gradient (a column sum) needs a kernel of its own."""
     if out_dtype is None:
         out_dtype = delta.dtype if delta is not None else x.dtype
-    return _AddLayerNormFn.apply(x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace)
+    return _AddLayerNormFn.apply(x, delta, weight, bias, gamma, beta, eps, out_dtype, inplace,
+                                 delta_bias)
 
 
 def skinny_linear(w, bias=None, a=None, x=None, delta=None, x_out=None, ln_weight=None, ln_bias=None,

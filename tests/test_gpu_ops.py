@@ -317,30 +317,33 @@ def test_add_layernorm_fwd_bwd_vs_torch(shape, dtype, film):
     dxo = torch.randn(batch, T, dim, generator=g)
     dh = torch.randn(batch, T, dim, generator=g).to(dtype).float()
 
+    dbias = torch.randn(dim, generator=g)
     leaves = [t.clone().requires_grad_() for t in (x, delta, w, b)] + \
              ([gam.clone().requires_grad_(), bet.clone().requires_grad_()] if film else [])
-    xs = leaves[0] + leaves[1]
+    dbl = dbias.clone().requires_grad_()
+    xs = leaves[0] + leaves[1] + dbl
     h = torch.nn.functional.layer_norm(xs, (dim,), leaves[2], leaves[3], 1e-5)
     if film:
         h = leaves[4][:, None] * h + leaves[5][:, None]
-    ref_g = torch.autograd.grad([xs, h], leaves, [dxo, dh])
+    ref_g = torch.autograd.grad([xs, h], leaves + [dbl], [dxo, dh])
 
     cl = [t.clone().cuda().requires_grad_() for t in (x, delta.to(dtype), w, b)] + \
          ([gam.clone().cuda().requires_grad_(), bet.clone().cuda().requires_grad_()] if film else [])
+    dbc = dbias.clone().cuda().requires_grad_()
     xo, ho = add_layernorm(cl[0], cl[1], cl[2], cl[3], 1e-5, gamma=cl[4] if film else None,
-                           beta=cl[5] if film else None, out_dtype=dtype)
-    got_g = torch.autograd.grad([xo, ho], cl, [dxo.cuda(), dh.cuda().to(dtype)])
+                           beta=cl[5] if film else None, out_dtype=dtype, delta_bias=dbc)
+    got_g = torch.autograd.grad([xo, ho], cl + [dbc], [dxo.cuda(), dh.cuda().to(dtype)])
     t = tol(dtype)
     check("x_out", xo, xs, 1e-6)
     check("out", ho, h, t)
-    names = ["dx", "ddelta", "dweight", "dbias", "dgamma", "dbeta"]
+    names = ["dx", "ddelta", "dweight", "dbias"] + (["dgamma", "dbeta"] if film else []) + ["ddelta_bias"]
     for n, a, r in zip(names, got_g, ref_g):
         check(n, a, r, t)
     # no-delta / inference form, in place
     x2 = x.cuda().clone()
     xo2, ho2 = add_layernorm(x2, delta.cuda().to(dtype), w.cuda(), b.cuda(), out_dtype=dtype, inplace=True)
     assert xo2.data_ptr() == x2.data_ptr()
-    check("inplace x", x2, xs, 1e-6)
+    check("inplace x", x2, x + delta, 1e-6)
     _, ho3 = add_layernorm(x.cuda(), None, w.cuda(), b.cuda(), out_dtype=dtype)
     check("plain ln", ho3, torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5), t)
 
