@@ -49,7 +49,7 @@ enum {
 
 /* Timesteps between two saved scan states ("checkpoints"): selective_scan_fwd writes the state at
  * the START of every chunk of this many timesteps; selective_scan_bwd recomputes inside a chunk. */
-#define MTTS_SCAN_CHUNK 256
+#define MTTS_SCAN_CHUNK 32
 #define MTTS_MAX_DSTATE 256
 #define MTTS_MAX_CONV_WIDTH 4
 

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmamba_tts_b200.so")
 
 F32, BF16 = 0, 1
-SCAN_CHUNK = 256
+SCAN_CHUNK = 32
 MAX_DSTATE = 256
 MAX_CONV_WIDTH = 4
 

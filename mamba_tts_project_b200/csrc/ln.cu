@@ -135,8 +135,19 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
     const float mean = p.mean[row], rstd = p.rstd[row];
     const float* xo = p.x_out + row * Dm;
     const T* go = reinterpret_cast<const T*>(p.dout) + row * Dm;
-    float xh[kG][4], gg[kG][4];
+    float xh[kG][4], gg[kG][4], up[kG][4];
     float a = 0.f, bsum = 0.f;
+    // the upstream residual gradient is fetched together with x_out / dout (one round trip per row)
+#pragma unroll
+    for (int g = 0; g < kG; ++g) {
+      const int e = (g * 32 + lane) * 4;
+      if (p.dx_out && e < Dm) {
+        load4<float>(p.dx_out + row * Dm + e, up[g]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) up[g][j] = 0.f;
+      }
+    }
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
       const int e = (g * 32 + lane) * 4;
@@ -166,13 +177,7 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
       if (e < Dm) {
         float dx[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dx[j] = rstd * (gg[g][j] - a - xh[g][j] * bsum);
-        if (p.dx_out) {
-          float up[4];
-          load4<float>(p.dx_out + row * Dm + e, up);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dx[j] += up[j];
-        }
+        for (int j = 0; j < 4; ++j) dx[j] = rstd * (gg[g][j] - a - xh[g][j] * bsum) + up[g][j];
 #pragma unroll
         for (int j = 0; j < 4; ++j) s3[g][j] += dx[j];
         store4<float>(p.dx + row * Dm + e, dx);

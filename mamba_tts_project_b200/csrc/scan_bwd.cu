@@ -1,331 +1,521 @@
 // selective_scan backward for sm_100a.  Replaces selective_scan_cuda.bwd (mamba_ssm), reached from
 // loss.backward() at train.py:231 through MambaInnerFn.backward.
 //
-// Recompute-based: the forward saved only the state at the start of every MTTS_SCAN_CHUNK (=256)
-// timesteps.  Tiles are walked last-to-first; inside a tile each warp (one channel) re-runs the
-// forward recurrence for one dstate row, then runs the reverse-time recurrence
-//     g_t = a_t * (C_t dy_t + g_{t+1}),   dh_t = C_t dy_t + g_{t+1}
-// with the same lane-local sweep + warp-shuffle stitch as the forward, and accumulates
-//     dC_t += dy_t h_t          dB_t += dh_t (dl_t u_t)          (summed over channels)
-//     d(dl_t u_t) += dh_t B_t   d dl_t += g_t h_{t-1} A          dA += g_t h_{t-1} dl_t
-// The cross-channel sums for dB/dC are reduced over the CTA's channels in shared memory first
-// (one fp32 RED per (state, timestep) per CTA instead of upstream's one per channel).
+// Same decomposition as the forward (scan_fwd.cu): thread = one channel x 4 consecutive dstate rows,
+// walking time sequentially with the states in registers; a warp = 32/NG channels x NG state slices.
+// Recompute-based: the forward saved the state at the start of every MTTS_SCAN_CHUNK (= 32 = one tile)
+// timesteps.  Tiles are walked last to first; per tile
+//   P   dt = softplus(delta + bias), dt*u, gy = dout * silu(z) -> fp32 shared tiles; B / C tile -> fp32
+//       [t][n] (16-byte chunk XOR-swizzled);
+//   M   pre-pass: the recurrence over the first 28 timesteps from the checkpoint, leaving the state at the
+//       start of each group of 4 timesteps in shared memory (16 bytes per thread and group);
+//       then the groups last to first: re-run the 4 steps keeping decays a_t and states h_t in registers
+//       (y_t = <C_t, h_t> for dz falls out), then the reverse recurrence
+//           G_t = C_t gy_t + a_{t+1} G_{t+1}
+//           dC_t = gy_t h_t              dB_t = (dt_t u_t) G_t                   (summed over channels)
+//           sGB_t = <G_t, B_t>           w_t = G_t (h_t - dt_t u_t B_t) = G_t a_t h_{t-1}
+//           ddtA_t = <w_t, A>            dA += w_t dt_t
+//       y / sGB / ddtA are summed over the NG slice lanes with a transposing butterfly (3 SHFL per 4
+//       values at NG = 4); dB / dC over the warp's channel lanes with a halving butterfly (14 SHFL per
+//       16 values at 8 channel lanes) into a per-warp shared tile;
+//   E   du = gy D + dt sGB,  ddelta = (ddtA + u sGB) softplus'(.),  dz = dout y silu'(z), streamed out;
+//       the warps' dB / dC tiles are summed and added to global memory with 16-byte vector REDs.
+// Two MUFU.EX2 per state update (pre-pass + re-run), everything else packed fp32x2.
 #include "scan_common.cuh"
 
 namespace mtts {
 
-template <typename T, int kWarps, bool kVec>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
-  constexpr int kItems = 8;
-  using Tile = PairTile<kItems>;
-  static_assert(Tile::kLen == MTTS_SCAN_CHUNK, "backward tile == checkpoint chunk");
-  constexpr int kThreads = kWarps * 32;
-  constexpr int G = kWarps;
-  constexpr int kRed = 4 * Tile::kLen;  // per warp: {dB, dC} x {row 2p, row 2p+1} x timesteps
+int dispatch_scan_bwd_wide(const mtts_scan_bwd_params& p, cudaStream_t stream);  // scan_bwd_wide.cu
 
-  extern __shared__ __align__(16) float smem[];
-  const int N = p.dstate, L = p.seqlen;
-  const int NP = (N + 1) >> 1;
-  float* Bs = smem;
-  float* Cs = Bs + Tile::kPairs * Tile::kRow;
-  float* red = Cs + Tile::kPairs * Tile::kRow;                 // [kWarps][kRed]
-  float2* A2s = reinterpret_cast<float2*>(red + kWarps * kRed);  // [G][NP] A * log2(e)
-  float2* hs = A2s + G * NP;                                   // [G][NP] state at tile start
-  float2* gs = hs + G * NP;                                    // [G][NP] reverse carry
-  // dA partials: per lane ([G][NP][32]) when dstate <= 16, else already warp-reduced ([G][NP])
-  float2* dAs = gs + G * NP;
-  const bool lane_da = N <= kScanNChunk;
-  const int da_stride = lane_da ? 32 : 1;
+namespace {
 
-  const int b = blockIdx.y, c0 = blockIdx.x * G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = c0 + warp;
-  const bool cvalid = c < p.dim;
+constexpr int kTT = MTTS_SCAN_CHUNK;  // tile = checkpoint interval
+constexpr int kBwdThreads = 64;
+static_assert(kTT == 32, "tile bookkeeping below assumes 32-timestep tiles");
 
-  for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
-    const int cl = idx / (2 * NP), n = idx - cl * 2 * NP;
-    reinterpret_cast<float*>(A2s)[idx] =
-        (c0 + cl < p.dim && n < N) ? p.A[(int64_t)(c0 + cl) * N + n] * kLog2e : 0.f;
-    reinterpret_cast<float*>(gs)[idx] = 0.f;
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+template <typename T, bool kVec>
+__device__ __forceinline__ uint4 load_raw(const T* __restrict__ row, int t, int len) {
+  constexpr int VE = Io<T>::kVecElems;
+  if constexpr (kVec) {
+    if (t < len) return ldg16(row + t);
+    return make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    float v[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) v[i] = (t + i < len) ? Io<T>::to_f(row[t + i]) : 0.f;
+    return Io<T>::pack(v);
   }
-  for (int idx = threadIdx.x; idx < G * NP * da_stride; idx += kThreads) dAs[idx] = make_float2(0.f, 0.f);
-
-  const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
-  const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
-  const int64_t cc = cvalid ? c : 0;
-  const T* urow = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride + cc * p.u_dim_stride;
-  const T* drow = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride +
-                  cc * p.delta_dim_stride;
-  const T* gorow = reinterpret_cast<const T*>(p.dout) + (int64_t)b * p.dout_batch_stride +
-                   cc * p.dout_dim_stride;
-  const T* zrow = p.z ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride +
-                            cc * p.z_dim_stride
-                      : nullptr;
-  const float bias = (cvalid && p.delta_bias) ? p.delta_bias[c] : 0.f;
-  const float Dv = (cvalid && p.D) ? p.D[c] : 0.f;
-
-  float dD_acc = 0.f, dbias_acc = 0.f;
-  const int ntiles = (L + Tile::kLen - 1) / Tile::kLen;
-
-  for (int tile = ntiles - 1; tile >= 0; --tile) {
-    const int t0 = tile * Tile::kLen;
-    const int tl = t0 + lane * kItems;
-
-    // state at the start of this tile for every channel of the group
-    for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
-      const int cl = idx / (2 * NP), n = idx - cl * 2 * NP;
-      reinterpret_cast<float*>(hs)[idx] =
-          (c0 + cl < p.dim && n < N)
-              ? p.checkpoints[(((int64_t)b * p.dim + c0 + cl) * nchunks + tile) * N + n]
-              : 0.f;
-    }
-
-    float dl[kItems], du[kItems], dy[kItems], y[kItems], ddu[kItems], ddl[kItems];
-    float dsum = 0.f;
-    if (cvalid) {
-      float u[kItems];
-      load_items<T, kItems, kVec>(urow, tl, L, u);
-      load_items<T, kItems, kVec>(drow, tl, L, dl);
-      load_items<T, kItems, kVec>(gorow, tl, L, dy);
-      if (zrow) {
-        float zv[kItems];
-        load_items<T, kItems, kVec>(zrow, tl, L, zv);
+}
+template <typename T, bool kVec>
+__device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, const float* v) {
+  constexpr int VE = Io<T>::kVecElems;
+  if constexpr (kVec) {
+    if (t < len) stg16_stream(row + t, Io<T>::pack(v));
+  } else {
 #pragma unroll
-        for (int i = 0; i < kItems; ++i) dy[i] *= silu_f(zv[i]);
-      }
+    for (int i = 0; i < VE; ++i)
+      if (t + i < len) row[t + i] = Io<T>::from_f(v[i]);
+  }
+}
+
+// Sum 4 per-timestep scalars over the NG slice lanes of a channel (lane bits [0, log2 NG)) and store
+// them to row[0..3].  The last two lane bits are folded with a transposing butterfly.
+template <int NG>
+__device__ __forceinline__ void slice_reduce_store(float (&v)[4], int g, float* row) {
 #pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        float x = dl[i] + bias;
-        if (p.delta_softplus) x = softplus_f(x);
-        if (tl + i >= L) x = 0.f;
-        dl[i] = x;
-        du[i] = x * u[i];
-        y[i] = Dv * u[i];
-        dsum += x;
-        ddu[i] = 0.f;
-        ddl[i] = 0.f;
+  for (int o = NG / 2; o >= 4; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+  }
+  if constexpr (NG == 1) {
+    *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (NG == 2) {
+    const bool hi = g & 1;
+    const float s0 = hi ? v[0] : v[2], s1 = hi ? v[1] : v[3];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    const float r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const float k0 = (hi ? v[2] : v[0]) + r0, k1 = (hi ? v[3] : v[1]) + r1;
+    *reinterpret_cast<float2*>(row + (hi ? 2 : 0)) = make_float2(k0, k1);
+  } else {
+    const bool b1 = g & 2, b0 = g & 1;
+    const float s0 = b1 ? v[0] : v[2], s1 = b1 ? v[1] : v[3];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+    const float r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float k0 = (b1 ? v[2] : v[0]) + r0, k1 = (b1 ? v[3] : v[1]) + r1;
+    const float s = b0 ? k0 : k1;
+    const float r = __shfl_xor_sync(0xffffffffu, s, 1);
+    const float tot = (b0 ? k1 : k0) + r;
+    if (g < 4) row[g & 3] = tot;  // NG > 4: every group of 4 lanes holds the totals, the first writes
+  }
+}
+
+// Halving butterfly over the channel lanes (lane bits [log2 NG, 5)): v[j*4 + i] (timestep j, state i of
+// the slice) summed over the warp's 32/NG channels; the surviving values go to tile[(j)*NP + i].
+template <int NG, int CNT, int BIT>
+__device__ __forceinline__ void chan_reduce_step(float (&v)[16], int lane, int& prefix) {
+  if constexpr (BIT >= NG) {
+    if constexpr (CNT > 1) {
+      constexpr int H = CNT / 2;
+      const bool up = lane & BIT;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float send = up ? v[i] : v[i + H];
+        const float keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);
       }
+      prefix = prefix * 2 + (up ? 1 : 0);
+      chan_reduce_step<NG, H, BIT / 2>(v, lane, prefix);
     } else {
-#pragma unroll
-      for (int i = 0; i < kItems; ++i) dl[i] = du[i] = dy[i] = y[i] = ddu[i] = ddl[i] = 0.f;
-    }
-
-    for (int n0 = 0; n0 < N; n0 += kScanNChunk) {
-      const int ncnt = min(kScanNChunk, N - n0);
-      __syncthreads();
-      stage_pairs<T, kItems, kVec, kThreads>(Bb, p.B_state_stride, n0, ncnt, t0, L, Bs);
-      stage_pairs<T, kItems, kVec, kThreads>(Cb, p.C_state_stride, n0, ncnt, t0, L, Cs);
-      __syncthreads();
-      const int npairs = (ncnt + 1) >> 1;
-
-#pragma unroll 1
-      for (int pp = 0; pp < npairs; ++pp) {
-        const int pg = (n0 >> 1) + pp;
-        const float2 A2 = A2s[warp * NP + pg];
-        const float2 An = fmul2(A2, dup2(kLn2));
-        const float2 h_in = hs[warp * NP + pg];
-        const float2 g_in = gs[warp * NP + pg];
-        const float* Bl = Bs + pp * Tile::kRow + lane * Tile::kSeg;
-        const float* Cl = Cs + pp * Tile::kRow + lane * Tile::kSeg;
-
-        float2 a[kItems], h[kItems], cd[kItems];
-        {
-          float2 bv[kItems];
-          lane_pairs<kItems>(Bl, bv);
-          float2 hl = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < kItems; ++i) {
-            a[i] = ex2f2(fmul2(dup2(dl[i]), A2));
-            h[i] = fmul2(dup2(du[i]), bv[i]);
-            hl = ffma2(a[i], hl, h[i]);
-          }
-          const float2 P0 = ex2f2(fmul2(dup2(dsum), A2));
-          float2 Pf = P0;
-          warp_scan_affine_up2(Pf, hl, lane);
-          float2 Pe = shfl_up2(Pf, 1);
-          float2 he = shfl_up2(hl, 1);
-          if (lane == 0) {
-            Pe = make_float2(1.f, 1.f);
-            he = make_float2(0.f, 0.f);
-          }
-          const float2 hstart = ffma2(Pe, h_in, he);
-          lane_pairs<kItems>(Cl, cd);
-          float2 hp = hstart;
-#pragma unroll
-          for (int i = 0; i < kItems; ++i) {
-            h[i] = ffma2(a[i], hp, h[i]);
-            hp = h[i];
-            y[i] = fmaf(h[i].y, cd[i].y, fmaf(h[i].x, cd[i].x, y[i]));
-            cd[i] = fmul2(cd[i], dup2(dy[i]));  // C_t * dy_t
-          }
-          // reverse-time lane-local sweep
-          float2 gl = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = kItems - 1; i >= 0; --i) gl = fmul2(a[i], fadd2(gl, cd[i]));
-          float2 Pr = P0;
-          warp_scan_affine_down2(Pr, gl, lane);
-          float2 Pn = shfl_down2(Pr, 1);
-          float2 gn = shfl_down2(gl, 1);
-          if (lane == 31) {
-            Pn = make_float2(1.f, 1.f);
-            gn = make_float2(0.f, 0.f);
-          }
-          float2 g = ffma2(Pn, g_in, gn);  // g entering this lane's last timestep from the future
-          if (lane == 0) gs[warp * NP + pg] = ffma2(Pr, g_in, gl);  // carry for the previous tile
-
-          lane_pairs<kItems>(Bl, bv);
-          float2 dA_acc = make_float2(0.f, 0.f);
-          float* rb = red + warp * kRed + lane * kItems;
-          float dBx[kItems], dBy[kItems], dCx[kItems], dCy[kItems];
-#pragma unroll
-          for (int i = kItems - 1; i >= 0; --i) {
-            const float2 dh = fadd2(cd[i], g);
-            g = fmul2(a[i], dh);
-            const float2 dCc = fmul2(dup2(dy[i]), h[i]);
-            const float2 dBc = fmul2(dh, dup2(du[i]));
-            dBx[i] = dBc.x; dBy[i] = dBc.y; dCx[i] = dCc.x; dCy[i] = dCc.y;
-            ddu[i] = fmaf(dh.y, bv[i].y, fmaf(dh.x, bv[i].x, ddu[i]));
-            const float2 hprev = (i > 0) ? h[i - 1] : hstart;
-            const float2 w = fmul2(g, hprev);
-            ddl[i] = fmaf(w.y, An.y, fmaf(w.x, An.x, ddl[i]));
-            dA_acc = ffma2(w, dup2(dl[i]), dA_acc);
-          }
-          if (lane_da) {
-            float2* dap = dAs + (warp * NP + pg) * 32 + lane;
-            *dap = fadd2(*dap, dA_acc);
-          } else {
-            const float sx = warp_sum(dA_acc.x), sy = warp_sum(dA_acc.y);
-            if (lane == 0) {
-              float2* dap = dAs + warp * NP + pg;
-              *dap = fadd2(*dap, make_float2(sx, sy));
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < kItems; j += 4) {
-            *reinterpret_cast<float4*>(rb + j) = make_float4(dBx[j], dBx[j + 1], dBx[j + 2], dBx[j + 3]);
-            *reinterpret_cast<float4*>(rb + Tile::kLen + j) =
-                make_float4(dBy[j], dBy[j + 1], dBy[j + 2], dBy[j + 3]);
-            *reinterpret_cast<float4*>(rb + 2 * Tile::kLen + j) =
-                make_float4(dCx[j], dCx[j + 1], dCx[j + 2], dCx[j + 3]);
-            *reinterpret_cast<float4*>(rb + 3 * Tile::kLen + j) =
-                make_float4(dCy[j], dCy[j + 1], dCy[j + 2], dCy[j + 3]);
-          }
-        }
-        __syncthreads();
-        // sum over the CTA's channels, then one RED per (state, timestep)
-        {
-          // thread -> (slot s in [0, 4): {dB row0, dB row1, dC row0, dC row1}, 4 timesteps)
-          const int s4 = threadIdx.x * 4;          // kThreads * 4 == kRed
-          const int slot = s4 / Tile::kLen, tp = s4 - slot * Tile::kLen;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) {
-            const float4 v = *reinterpret_cast<const float4*>(red + w * kRed + s4);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-          }
-          const int n = 2 * pg + (slot & 1);
-          if (n < N) {
-            float* dst = ((slot >> 1) == 0 ? p.dB : p.dC) + ((int64_t)b * N + n) * L + t0 + tp;
-            if (kVec && t0 + tp + 3 < L) {
-              // one 16-byte reduction instead of four (L % 4 == 0 on the vector path)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x),
-                           "f"(acc.y), "f"(acc.z), "f"(acc.w)
-                           : "memory");
-            } else {
-              if (t0 + tp < L) atomicAdd(dst, acc.x);
-              if (t0 + tp + 1 < L) atomicAdd(dst + 1, acc.y);
-              if (t0 + tp + 2 < L) atomicAdd(dst + 2, acc.z);
-              if (t0 + tp + 3 < L) atomicAdd(dst + 3, acc.w);
-            }
-          }
-        }
-        __syncthreads();  // red is single-buffered (keeps two CTAs per SM)
-      }
-    }
-
-    // per-timestep outputs of this tile
-    if (cvalid) {
-      float tmp[kItems], u[kItems];
-      load_items<T, kItems, kVec>(drow, tl, L, tmp);
-      load_items<T, kItems, kVec>(urow, tl, L, u);
-      float o_du[kItems], o_dd[kItems];
-#pragma unroll
-      for (int i = 0; i < kItems; ++i) {
-        const float x = tmp[i] + bias;
-        const float sg = (p.delta_softplus && x <= 20.f) ? sigmoid_f(x) : 1.f;
-        const bool in = tl + i < L;
-        o_du[i] = fmaf(ddu[i], dl[i], dy[i] * Dv);
-        const float dd = in ? fmaf(ddu[i], u[i], ddl[i]) * sg : 0.f;
-        o_dd[i] = dd;
-        dbias_acc += dd;
-        dD_acc = fmaf(dy[i], u[i], dD_acc);
-      }
-      T* du_row = reinterpret_cast<T*>(p.du) + (int64_t)b * p.du_batch_stride + (int64_t)c * p.du_dim_stride;
-      T* dd_row = reinterpret_cast<T*>(p.ddelta) + (int64_t)b * p.ddelta_batch_stride +
-                  (int64_t)c * p.ddelta_dim_stride;
-      store_items<T, kItems, kVec>(du_row, tl, L, o_du);
-      store_items<T, kItems, kVec>(dd_row, tl, L, o_dd);
-      if (zrow) {
-        float zv[kItems], go[kItems];
-        load_items<T, kItems, kVec>(zrow, tl, L, zv);
-        load_items<T, kItems, kVec>(gorow, tl, L, go);
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) {
-          const float sig = sigmoid_f(zv[i]);
-          go[i] = go[i] * y[i] * sig * fmaf(zv[i], 1.f - sig, 1.f);
-        }
-        T* dz_row = reinterpret_cast<T*>(p.dz) + (int64_t)b * p.dz_batch_stride + (int64_t)c * p.dz_dim_stride;
-        store_items<T, kItems, kVec>(dz_row, tl, L, go);
-      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], BIT);
+      chan_reduce_step<NG, 1, BIT / 2>(v, lane, prefix);
     }
   }
-
-  __syncthreads();
-  if (cvalid) {
-    dD_acc = warp_sum(dD_acc);
-    dbias_acc = warp_sum(dbias_acc);
-    if (lane == 0) {
-      if (p.dD) atomicAdd(p.dD + c, dD_acc);
-      if (p.ddelta_bias) atomicAdd(p.ddelta_bias + c, dbias_acc);
-    }
-    for (int pg = 0; pg < NP; ++pg) {
-      float sx, sy;
-      if (lane_da) {
-        const float2 v = dAs[(warp * NP + pg) * 32 + lane];
-        sx = warp_sum(v.x);
-        sy = warp_sum(v.y);
-      } else {
-        const float2 v = dAs[warp * NP + pg];
-        sx = v.x;
-        sy = v.y;
+}
+template <int NG, int NP>
+__device__ __forceinline__ void chan_reduce_store(float (&v)[16], int lane, int g, float* tile) {
+  constexpr int CL = 32 / NG;                      // channel lanes
+  constexpr int S = CL >= 16 ? 4 : (CL == 8 ? 3 : (CL == 4 ? 2 : 1));  // halving stages
+  constexpr int R = 16 >> S;                       // values left per lane
+  int prefix = 0;
+  chan_reduce_step<NG, 16, 16>(v, lane, prefix);
+  const bool writer = CL <= 16 || (lane & NG) == 0;  // CL = 32: the last stage was a plain xor
+  if (writer) {
+    if constexpr (R >= 4) {
+#pragma unroll
+      for (int r = 0; r < R; r += 4) {
+        const int idx = prefix * R + r;
+        *reinterpret_cast<float4*>(tile + (idx >> 2) * NP + g * 4) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
       }
-      if (lane == 0) {
-        atomicAdd(p.dA + (int64_t)c * N + 2 * pg, sx);
-        if (2 * pg + 1 < N) atomicAdd(p.dA + (int64_t)c * N + 2 * pg + 1, sy);
-      }
+    } else if constexpr (R == 2) {
+      const int idx = prefix * 2;
+      *reinterpret_cast<float2*>(tile + (idx >> 2) * NP + g * 4 + (idx & 3)) = make_float2(v[0], v[1]);
+    } else {
+      tile[(prefix >> 2) * NP + g * 4 + (prefix & 3)] = v[0];
     }
   }
 }
 
-template <typename T, bool kVec>
+}  // namespace
+
+template <typename T, int NG, bool kVec>
+struct ScanBwdCfg {
+  static constexpr int VE = Io<T>::kVecElems;
+  static constexpr int kChan = kBwdThreads / NG;
+  static constexpr int NP = 4 * NG;
+  static constexpr int kSwz = NG >= 4 ? 3 : NG - 1;
+  static constexpr int RS = kTT + 4;
+  static constexpr int kVecPerRow = kTT / VE;
+  static constexpr int kItems = kChan * kVecPerRow;
+  static constexpr int kIt = (kItems + kBwdThreads - 1) / kBwdThreads;
+  static constexpr int kBCItems = NG * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
+  // dt, dtu (-> sGB), gy, y, ddtA rows; B, C tiles; per-warp dB, dC tiles; group-start states
+  static constexpr size_t kSmemFloats = 5 * (size_t)kChan * RS + 2 * (size_t)kTT * NP +
+                                        2 * 2 * (size_t)kTT * NP + 7 * 4 * (size_t)kBwdThreads;
+};
+
+template <typename T, int NG, bool kVec>
+__global__ void __launch_bounds__(kBwdThreads, NG == 4 ? 7 : 1)
+scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
+  using Cfg = ScanBwdCfg<T, NG, kVec>;
+  constexpr int VE = Cfg::VE, kChan = Cfg::kChan, NP = Cfg::NP, RS = Cfg::RS;
+  constexpr int kIt = Cfg::kIt, kVecPerRow = Cfg::kVecPerRow, kThreads = kBwdThreads;
+
+  extern __shared__ __align__(16) float smem[];
+  float* dts = smem;                      // [kChan][RS] dt
+  float* dtus = dts + kChan * RS;         // dt*u, overwritten by sGB
+  float* gys = dtus + kChan * RS;         // dout * silu(z)
+  float* ys = gys + kChan * RS;           // <C, h>
+  float* das = ys + kChan * RS;           // <w, A*log2e>
+  float* Bs = das + kChan * RS;           // [kTT][NP] swizzled
+  float* Cs = Bs + kTT * NP;
+  float* dBw = Cs + kTT * NP;             // [2 warps][kTT][NP]
+  float* dCw = dBw + 2 * kTT * NP;
+  float* hbs = dCw + 2 * kTT * NP;        // [groups 1..7][kThreads][4] state at the start of the group
+
+  const int N = p.dstate, L = p.seqlen;
+  const int b = blockIdx.y, c0 = blockIdx.x * kChan;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chl = tid / NG, g = tid % NG;
+  const int c = c0 + chl;
+  const bool cvalid = c < p.dim;
+  const int64_t bc = (int64_t)b * p.dim + c;
+
+  float2 A2[2], Gc[2], dAacc[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = g * 4 + i;
+    reinterpret_cast<float*>(A2)[i] = (cvalid && n < N) ? p.A[(int64_t)c * N + n] * kLog2e : 0.f;
+    reinterpret_cast<float*>(Gc)[i] = 0.f;
+    reinterpret_cast<float*>(dAacc)[i] = 0.f;
+  }
+
+  const T* ub = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride;
+  const T* db = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride;
+  const T* gob = reinterpret_cast<const T*>(p.dout) + (int64_t)b * p.dout_batch_stride;
+  const T* zb = p.z ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride : nullptr;
+  const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
+  const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
+
+  float dD_acc[kIt], dbias_acc[kIt];
+#pragma unroll
+  for (int k = 0; k < kIt; ++k) dD_acc[k] = dbias_acc[k] = 0.f;
+
+  const int ntiles = (L + kTT - 1) / kTT;
+  for (int tile = ntiles - 1; tile >= 0; --tile) {
+    const int t0 = tile * kTT;
+
+    // ---- P ----------------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      const int idx = tid + k * kThreads;
+      if (idx < Cfg::kItems) {
+        const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
+        const int cc = c0 + ich;
+        const bool ok = cc < p.dim;
+        float uv[VE], dv[VE], gv[VE];
+        {
+          uint4 ur = make_uint4(0u, 0u, 0u, 0u), dr = ur, gr = ur, zr = ur;
+          if (ok) {
+            ur = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
+            dr = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
+            gr = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
+            if (zb) zr = load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L);
+          }
+          Io<T>::unpack(ur, uv);
+          Io<T>::unpack(dr, dv);
+          Io<T>::unpack(gr, gv);
+          if (zb) {
+            float zv[VE];
+            Io<T>::unpack(zr, zv);
+#pragma unroll
+            for (int i = 0; i < VE; ++i) gv[i] *= silu_f(zv[i]);
+          }
+        }
+        const float bias = (ok && p.delta_bias) ? p.delta_bias[cc] : 0.f;
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+          float x = dv[i] + bias;
+          if (p.delta_softplus) x = softplus_f(x);
+          if (!ok || t0 + it + i >= L) x = 0.f;  // identity step (gy is 0 there: dout loads as 0)
+          dv[i] = x;
+          uv[i] *= x;
+        }
+        float* r0 = dts + ich * RS + it;
+        float* r1 = dtus + ich * RS + it;
+        float* r2 = gys + ich * RS + it;
+#pragma unroll
+        for (int i = 0; i < VE; i += 4) {
+          *reinterpret_cast<float4*>(r0 + i) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
+          *reinterpret_cast<float4*>(r1 + i) = make_float4(uv[i], uv[i + 1], uv[i + 2], uv[i + 3]);
+          *reinterpret_cast<float4*>(r2 + i) = make_float4(gv[i], gv[i + 1], gv[i + 2], gv[i + 3]);
+        }
+      }
+    }
+    // B / C: item = (tensor, chunk of 4 dstate rows, 16-byte vector of timesteps) -> VE STS.128
+    for (int idx = tid; idx < 2 * Cfg::kBCItems; idx += kThreads) {
+      const int which = idx / Cfg::kBCItems, r = idx % Cfg::kBCItems;
+      const int chunk = r / kVecPerRow, tv = (r % kVecPerRow) * VE;
+      const T* src = which ? Cb : Bb;
+      const int64_t rs = which ? p.C_state_stride : p.B_state_stride;
+      float* dst = which ? Cs : Bs;
+      float rows[4][VE];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = chunk * 4 + i;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (n < N) raw = load_raw<T, kVec>(src + (int64_t)n * rs, t0 + tv, L);
+        Io<T>::unpack(raw, rows[i]);
+      }
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        const int t = tv + e;
+        *reinterpret_cast<float4*>(dst + t * NP + ((chunk ^ ((t >> 3) & Cfg::kSwz)) << 2)) =
+            make_float4(rows[0][e], rows[1][e], rows[2][e], rows[3][e]);
+      }
+    }
+    __syncthreads();
+
+    // ---- M ----------------------------------------------------------------------------------------
+    {
+      const float* dtr = dts + chl * RS;
+      float* dur = dtus + chl * RS;
+      const float* gyr = gys + chl * RS;
+      float* yr = ys + chl * RS;
+      float* dar = das + chl * RS;
+      float* hb = hbs + tid * 4;
+      float* dBt = dBw + warp * kTT * NP;
+      float* dCt = dCw + warp * kTT * NP;
+
+      float2 h[2];
+      {
+        float hv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (cvalid) {
+          const float* ck = p.checkpoints + (bc * nchunks + tile) * N + g * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (g * 4 + i < N) hv[i] = ck[i];
+        }
+        h[0] = make_float2(hv[0], hv[1]);
+        h[1] = make_float2(hv[2], hv[3]);
+      }
+      // pre-pass: state at the start of every group of 4 timesteps
+      const float4 h0 = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+#pragma unroll 1
+      for (int s = 0; s < 7; ++s) {
+        const float4 d4 = lds128(dtr + 4 * s);
+        const float4 x4 = lds128(dur + 4 * s);
+        const float dtv[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
+        const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 Bv = lds128(Bs + (4 * s + j) * NP + off);
+          const float2 dt2 = dup2(dtv[j]), du2 = dup2(duv[j]);
+          h[0] = ffma2(ex2f2(fmul2(dt2, A2[0])), h[0], fmul2(du2, lo2(Bv)));
+          h[1] = ffma2(ex2f2(fmul2(dt2, A2[1])), h[1], fmul2(du2, hi2(Bv)));
+        }
+        *reinterpret_cast<float4*>(hb + s * 4 * kThreads) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+      }
+
+#pragma unroll 1
+      for (int s = 7; s >= 0; --s) {
+        const float4 d4 = lds128(dtr + 4 * s);
+        const float4 x4 = lds128(dur + 4 * s);
+        const float4 g4 = lds128(gyr + 4 * s);
+        const float dtv[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
+        const float gyv[4] = {g4.x, g4.y, g4.z, g4.w};
+        const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
+        const float* Bt = Bs + 4 * s * NP + off;
+        const float* Ct = Cs + 4 * s * NP + off;
+
+        // re-run the 4 steps, keeping decays and states
+        float2 a[4][2], hs[4][2];
+        {
+          const float4 h4 = s == 0 ? h0 : lds128(hb + (s - 1) * 4 * kThreads);
+          float2 hc0 = lo2(h4), hc1 = hi2(h4);
+          float yp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 Bv = lds128(Bt + j * NP);
+            const float4 Cv = lds128(Ct + j * NP);
+            const float2 dt2 = dup2(dtv[j]), du2 = dup2(duv[j]);
+            a[j][0] = ex2f2(fmul2(dt2, A2[0]));
+            a[j][1] = ex2f2(fmul2(dt2, A2[1]));
+            hc0 = ffma2(a[j][0], hc0, fmul2(du2, lo2(Bv)));
+            hc1 = ffma2(a[j][1], hc1, fmul2(du2, hi2(Bv)));
+            hs[j][0] = hc0;
+            hs[j][1] = hc1;
+            const float2 acc = ffma2(hc1, hi2(Cv), fmul2(hc0, lo2(Cv)));
+            yp[j] = acc.x + acc.y;
+          }
+          slice_reduce_store<NG>(yp, g, yr + 4 * s);
+        }
+
+        // reverse recurrence
+        float dBv[16], dCv[16], sgb[4], dda[4];
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+          const float4 Bv = lds128(Bt + j * NP);
+          const float4 Cv = lds128(Ct + j * NP);
+          const float2 gy2 = dup2(gyv[j]), du2 = dup2(duv[j]), dt2 = dup2(dtv[j]);
+          const float2 G0 = ffma2(lo2(Cv), gy2, Gc[0]);
+          const float2 G1 = ffma2(hi2(Cv), gy2, Gc[1]);
+          const float2 dC0 = fmul2(gy2, hs[j][0]), dC1 = fmul2(gy2, hs[j][1]);
+          const float2 dB0 = fmul2(du2, G0), dB1 = fmul2(du2, G1);
+          dCv[4 * j] = dC0.x; dCv[4 * j + 1] = dC0.y; dCv[4 * j + 2] = dC1.x; dCv[4 * j + 3] = dC1.y;
+          dBv[4 * j] = dB0.x; dBv[4 * j + 1] = dB0.y; dBv[4 * j + 2] = dB1.x; dBv[4 * j + 3] = dB1.y;
+          const float2 sg = ffma2(G1, hi2(Bv), fmul2(G0, lo2(Bv)));
+          sgb[j] = sg.x + sg.y;
+          // a_t h_{t-1} = h_t - dt u B_t
+          const float2 ah0 = ffma2(make_float2(-du2.x, -du2.y), lo2(Bv), hs[j][0]);
+          const float2 ah1 = ffma2(make_float2(-du2.x, -du2.y), hi2(Bv), hs[j][1]);
+          const float2 w0 = fmul2(G0, ah0), w1 = fmul2(G1, ah1);
+          const float2 da = ffma2(w1, A2[1], fmul2(w0, A2[0]));
+          dda[j] = da.x + da.y;
+          dAacc[0] = ffma2(w0, dt2, dAacc[0]);
+          dAacc[1] = ffma2(w1, dt2, dAacc[1]);
+          Gc[0] = fmul2(a[j][0], G0);
+          Gc[1] = fmul2(a[j][1], G1);
+        }
+        slice_reduce_store<NG>(sgb, g, dur + 4 * s);
+        slice_reduce_store<NG>(dda, g, dar + 4 * s);
+        chan_reduce_store<NG, NP>(dBv, lane, g, dBt + 4 * s * NP);
+        chan_reduce_store<NG, NP>(dCv, lane, g, dCt + 4 * s * NP);
+      }
+    }
+    __syncthreads();
+
+    // ---- E ----------------------------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      const int idx = tid + k * kThreads;
+      const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
+      const int cc = c0 + ich;
+      if (idx < Cfg::kItems && cc < p.dim) {
+        float uv[VE], dv[VE], gv[VE], zv[VE];
+        Io<T>::unpack(load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L), uv);
+        Io<T>::unpack(load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L), dv);
+        Io<T>::unpack(load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L), gv);
+        if (zb) Io<T>::unpack(load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L), zv);
+        const float bias = p.delta_bias ? p.delta_bias[cc] : 0.f;
+        const float Dv = p.D ? p.D[cc] : 0.f;
+        float dtv[VE], sgv[VE], yv[VE], dav[VE];
+#pragma unroll
+        for (int i = 0; i < VE; i += 4) {
+          const float4 q0 = lds128(dts + ich * RS + it + i);
+          const float4 q1 = lds128(dtus + ich * RS + it + i);
+          const float4 q2 = lds128(ys + ich * RS + it + i);
+          const float4 q3 = lds128(das + ich * RS + it + i);
+          dtv[i] = q0.x; dtv[i + 1] = q0.y; dtv[i + 2] = q0.z; dtv[i + 3] = q0.w;
+          sgv[i] = q1.x; sgv[i + 1] = q1.y; sgv[i + 2] = q1.z; sgv[i + 3] = q1.w;
+          yv[i] = q2.x; yv[i + 1] = q2.y; yv[i + 2] = q2.z; yv[i + 3] = q2.w;
+          dav[i] = q3.x; dav[i + 1] = q3.y; dav[i + 2] = q3.z; dav[i + 3] = q3.w;
+        }
+        float o_du[VE], o_dd[VE], o_dz[VE];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+          float gy = gv[i];
+          if (zb) {
+            const float sig = sigmoid_f(zv[i]);
+            gy *= zv[i] * sig;
+            o_dz[i] = gv[i] * fmaf(Dv, uv[i], yv[i]) * sig * fmaf(zv[i], 1.f - sig, 1.f);
+          }
+          const float x = dv[i] + bias;
+          const float sp = (p.delta_softplus && x <= 20.f) ? sigmoid_f(x) : 1.f;
+          o_du[i] = fmaf(dtv[i], sgv[i], gy * Dv);
+          const float dd = (t0 + it + i < L) ? fmaf(uv[i], sgv[i], dav[i] * kLn2) * sp : 0.f;
+          o_dd[i] = dd;
+          dbias_acc[k] += dd;
+          dD_acc[k] = fmaf(gy, uv[i], dD_acc[k]);
+        }
+        store_raw<T, kVec>(reinterpret_cast<T*>(p.du) + (int64_t)b * p.du_batch_stride +
+                               (int64_t)cc * p.du_dim_stride, t0 + it, L, o_du);
+        store_raw<T, kVec>(reinterpret_cast<T*>(p.ddelta) + (int64_t)b * p.ddelta_batch_stride +
+                               (int64_t)cc * p.ddelta_dim_stride, t0 + it, L, o_dd);
+        if (zb)
+          store_raw<T, kVec>(reinterpret_cast<T*>(p.dz) + (int64_t)b * p.dz_batch_stride +
+                                 (int64_t)cc * p.dz_dim_stride, t0 + it, L, o_dz);
+      }
+    }
+    // dB / dC: sum the two warps' tiles, one 16-byte RED per (state row, 4 timesteps)
+    for (int idx = tid; idx < 2 * NP * (kTT / 4); idx += kThreads) {
+      const int which = idx / (NP * (kTT / 4)), r = idx % (NP * (kTT / 4));
+      const int n = r % NP, tq = (r / NP) * 4;
+      if (n < N && t0 + tq < L) {
+        const float* w0 = (which ? dCw : dBw) + tq * NP + n;
+        const float* w1 = w0 + kTT * NP;
+        float acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = w0[i * NP] + w1[i * NP];
+        float* dst = (which ? p.dC : p.dB) + ((int64_t)b * N + n) * L + t0 + tq;
+        if (kVec && t0 + tq + 3 < L) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]),
+                       "f"(acc[1]), "f"(acc[2]), "f"(acc[3])
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (t0 + tq + i < L) atomicAdd(dst + i, acc[i]);
+        }
+      }
+    }
+    __syncthreads();  // tiles are single-buffered
+  }
+
+  // ---- per-channel reductions over time ------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < kIt; ++k) {
+    float sD = dD_acc[k], sb = dbias_acc[k];
+#pragma unroll
+    for (int o = kVecPerRow / 2; o > 0; o >>= 1) {
+      sD += __shfl_xor_sync(0xffffffffu, sD, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    const int idx = tid + k * kThreads;
+    const int cc = c0 + idx / kVecPerRow;
+    if (idx < Cfg::kItems && cc < p.dim && (idx % kVecPerRow) == 0) {
+      if (p.dD) atomicAdd(p.dD + cc, sD);
+      if (p.ddelta_bias) atomicAdd(p.ddelta_bias + cc, sb);
+    }
+  }
+  if (cvalid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (g * 4 + i < N) atomicAdd(p.dA + (int64_t)c * N + g * 4 + i, reinterpret_cast<const float*>(dAacc)[i]);
+  }
+}
+
+template <typename T, int NG, bool kVec>
 static int launch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
-  constexpr int kWarps = 8;
-  using Tile = PairTile<8>;
+  using Cfg = ScanBwdCfg<T, NG, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
-  const int NP = (p.dstate + 1) / 2;
-  const size_t smem = sizeof(float) * (2 * Tile::kPairs * Tile::kRow + kWarps * 4 * Tile::kLen +
-                                       (size_t)kWarps * NP * (6 + (p.dstate <= kScanNChunk ? 64 : 2)));
-  auto kern = scan_bwd_kernel<T, kWarps, kVec>;
+  const size_t smem = sizeof(float) * Cfg::kSmemFloats;
+  auto kern = scan_bwd_kernel<T, NG, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
-  const dim3 grid((p.dim + kWarps - 1) / kWarps, p.batch);
-  kern<<<grid, kWarps * 32, smem, stream>>>(p, nchunks);
+  const dim3 grid((p.dim + Cfg::kChan - 1) / Cfg::kChan, p.batch);
+  kern<<<grid, kBwdThreads, smem, stream>>>(p, nchunks);
   return launch_status();
+}
+
+template <typename T, bool kVec>
+static int dispatch_scan_bwd_n(const mtts_scan_bwd_params& p, cudaStream_t stream) {
+  const int N = p.dstate;
+  if (N <= 4) return launch_scan_bwd<T, 1, kVec>(p, stream);
+  if (N <= 8) return launch_scan_bwd<T, 2, kVec>(p, stream);
+  if (N <= 16) return launch_scan_bwd<T, 4, kVec>(p, stream);
+  if (N <= 32) return launch_scan_bwd<T, 8, kVec>(p, stream);
+  return launch_scan_bwd<T, 16, kVec>(p, stream);
 }
 
 template <typename T>
 static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
+  if (p.dstate > 64) return dispatch_scan_bwd_wide(p, stream);
   const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&
@@ -335,7 +525,7 @@ static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream)
                    vec_ok<T>(p.du, p.du_batch_stride, p.du_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.ddelta, p.ddelta_batch_stride, p.ddelta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.dz, p.dz_batch_stride, p.dz_dim_stride, p.seqlen);
-  return vec ? launch_scan_bwd<T, true>(p, stream) : launch_scan_bwd<T, false>(p, stream);
+  return vec ? dispatch_scan_bwd_n<T, true>(p, stream) : dispatch_scan_bwd_n<T, false>(p, stream);
 }
 
 }  // namespace mtts

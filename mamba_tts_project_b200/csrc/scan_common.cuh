@@ -62,7 +62,7 @@ struct PairTile {
   static constexpr int kRow = 32 * kSeg;
   static constexpr int kLen = 32 * kItems;
   static constexpr int kPairs = kScanNChunk / 2;  // dstate row pairs resident at a time
-  static_assert(MTTS_SCAN_CHUNK % kItems == 0 && kLen % MTTS_SCAN_CHUNK == 0, "tile vs chunk");
+  static_assert(kLen % MTTS_SCAN_CHUNK == 0, "tile vs chunk");
 };
 
 // Stage dstate rows [n0, n0+ncnt) (ncnt <= kScanNChunk) x timesteps [t0, t0+kLen) interleaved by

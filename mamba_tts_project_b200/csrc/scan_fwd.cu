@@ -1,187 +1,383 @@
 // selective_scan forward for sm_100a.  Replaces selective_scan_cuda.fwd (mamba_ssm), which the
 // reference reaches through Mamba.forward at mamba_decoder.py:61.  Math: see mamba_tts_b200.h.
 //
-// Per (lane, pair of dstate rows): one MUFU.EX2 per timestep-state (the binding unit on B200:
-// 16/clk/SM); everything else is packed fp32x2 (FFMA2/FMUL2: the two rows of a pair share an issue
-// slot).  Sweep 1 builds the lane-local affine map, a 5-step shuffle scan stitches the 32 lanes,
-// sweep 2 replays the recurrence from the true incoming state and contracts with C.
+// Design ("time-sequential, state-sliced"):
+//   thread = one channel x G consecutive dstate rows; it walks the sequence IN ORDER with the G states
+//            in registers, so there is no scan across time at all: per state update exactly one
+//            MUFU.EX2 (the binding unit on B200, 16/clk/SM) and 2 packed FFMA2/FMUL2 issue slots;
+//   warp   = 32/NG channels x NG state slices of the same channel in adjacent lanes; the only
+//            cross-lane traffic is the <C, h> partial sum over the NG slices (a transposing
+//            butterfly: 3 SHFL per 4 timesteps at NG = 4);
+//   CTA    = kChan channels of one batch element, sequence walked in tiles of TT timesteps:
+//            P  every thread turns its 16-byte vectors of u / delta (prefetched into registers one
+//               tile ahead) into fp32 dt = softplus(delta + bias) and dt*u rows in shared memory, and
+//               transposes the tile of B / C to fp32 [t][n] (16-byte chunk XOR-swizzled);
+//            M  the scan proper: LDS.128 of dt, dt*u (per 4 timesteps) and B, C (per timestep, warp
+//               broadcast), y partials reduced over the NG lanes and stored to a shared y tile;
+//            E  out = (y + D u) * silu(z), packed and streamed out with 16-byte stores.
+//   Parallelism comes from channels x state slices (B*Di*NG threads); several small CTAs per SM overlap
+//   each other's P/E phases with M.
 #include "scan_common.cuh"
 
 namespace mtts {
 
-template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
-  using Tile = PairTile<kItems>;
-  constexpr int kThreads = kWarps * 32;
-  constexpr int G = kWarps * kCPW;
-  constexpr int kLanesPerChunk = MTTS_SCAN_CHUNK / kItems;
-  constexpr int kChunksPerTile = Tile::kLen / MTTS_SCAN_CHUNK;
+namespace {
 
-  extern __shared__ __align__(16) float smem[];
-  const int N = p.dstate, L = p.seqlen;
-  const int NP = (N + 1) >> 1;  // dstate row pairs
-  float* Bs = smem;
-  float* Cs = Bs + Tile::kPairs * Tile::kRow;
-  float2* A2s = reinterpret_cast<float2*>(Cs + Tile::kPairs * Tile::kRow);  // A*log2(e), [G][NP]
-  float2* hs = A2s + G * NP;                                                // running state [G][NP]
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-  const int b = blockIdx.y, c0 = blockIdx.x * G;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
-    const int cl = idx / (2 * NP), n = idx - cl * 2 * NP, c = c0 + cl;
-    float a2 = 0.f, h = 0.f;
-    if (c < p.dim && n < N) {
-      a2 = p.A[(int64_t)c * N + n] * kLog2e;
-      const int64_t bc = (int64_t)b * p.dim + c;
-      if (p.initial_state) h = p.initial_state[bc * N + n];
-      if (p.checkpoints) p.checkpoints[bc * nchunks * N + n] = h;
-    }
-    reinterpret_cast<float*>(A2s)[idx] = a2;
-    reinterpret_cast<float*>(hs)[idx] = h;
+// 16 bytes of a row starting at element t: vector path or bounds-checked scalar gather (zeros >= len)
+template <typename T, bool kVec>
+__device__ __forceinline__ uint4 load_raw(const T* __restrict__ row, int t, int len) {
+  constexpr int VE = Io<T>::kVecElems;
+  if constexpr (kVec) {
+    if (t < len) return ldg16_stream(row + t);
+    return make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    float v[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) v[i] = (t + i < len) ? Io<T>::to_f(row[t + i]) : 0.f;
+    return Io<T>::pack(v);
   }
-  __syncthreads();
-
-  const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
-  const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
-  const int ntiles = (L + Tile::kLen - 1) / Tile::kLen;
-  const bool restage_per_pass = N > kScanNChunk;
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int t0 = tile * Tile::kLen;
-    const int tl = t0 + lane * kItems;
-    const bool partial = t0 + Tile::kLen > L;
-#pragma unroll 1
-    for (int pass = 0; pass < kCPW; ++pass) {
-      const int cl = pass * kWarps + warp;
-      const int c = c0 + cl;
-      const bool cvalid = c < p.dim;  // warp-uniform
-
-      float dl[kItems], du[kItems], y[kItems];
-      float dsum = 0.f;
-      if (cvalid) {
-        const T* urow = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride +
-                        (int64_t)c * p.u_dim_stride;
-        const T* drow = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride +
-                        (int64_t)c * p.delta_dim_stride;
-        load_items<T, kItems, kVec>(urow, tl, L, du);
-        load_items<T, kItems, kVec>(drow, tl, L, dl);
-        const float bias = p.delta_bias ? p.delta_bias[c] : 0.f;
-        const float Dv = p.D ? p.D[c] : 0.f;
+}
+template <typename T, bool kVec>
+__device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, const float* v) {
+  constexpr int VE = Io<T>::kVecElems;
+  if constexpr (kVec) {
+    if (t < len) stg16_stream(row + t, Io<T>::pack(v));
+  } else {
 #pragma unroll
-        for (int i = 0; i < kItems; ++i) {
-          float x = dl[i] + bias;
-          if (p.delta_softplus) x = softplus_f(x);
-          if (partial && tl + i >= L) x = 0.f;  // padding: decay 1, input 0 = identity step
-          const float uu = du[i];
-          dl[i] = x;
-          y[i] = Dv * uu;
-          du[i] = x * uu;
-          dsum += x;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) dl[i] = du[i] = y[i] = 0.f;
-      }
-
-      for (int n0 = 0; n0 < N; n0 += kScanNChunk) {
-        const int ncnt = min(kScanNChunk, N - n0);
-        if (restage_per_pass || pass == 0) {
-          __syncthreads();  // every warp is done reading the previous B/C tile
-          stage_pairs<T, kItems, kVec, kThreads>(Bb, p.B_state_stride, n0, ncnt, t0, L, Bs);
-          stage_pairs<T, kItems, kVec, kThreads>(Cb, p.C_state_stride, n0, ncnt, t0, L, Cs);
-          __syncthreads();
-        }
-        if (!cvalid) continue;
-        const int npairs = (ncnt + 1) >> 1;
-#pragma unroll 1
-        for (int pp = 0; pp < npairs; ++pp) {
-          const int pg = (n0 >> 1) + pp;  // global pair index
-          const float2 A2 = A2s[cl * NP + pg];
-          const float2 h_in = hs[cl * NP + pg];
-          const float* Bl = Bs + pp * Tile::kRow + lane * Tile::kSeg;
-          const float* Cl = Cs + pp * Tile::kRow + lane * Tile::kSeg;
-          float2 a[kItems], tmp[kItems];
-          lane_pairs<kItems>(Bl, tmp);
-          float2 hl = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < kItems; ++i) {
-            a[i] = ex2f2(fmul2(dup2(dl[i]), A2));
-            hl = ffma2(a[i], hl, fmul2(dup2(du[i]), tmp[i]));
-          }
-          float2 P = ex2f2(fmul2(dup2(dsum), A2));  // product of the lane's decays
-          warp_scan_affine_up2(P, hl, lane);
-          float2 Pe = shfl_up2(P, 1);
-          float2 he = shfl_up2(hl, 1);
-          if (lane == 0) {
-            Pe = make_float2(1.f, 1.f);
-            he = make_float2(0.f, 0.f);
-          }
-          float2 h = ffma2(Pe, h_in, he);  // state entering this lane's first timestep
-          {
-            float2 cv[kItems];
-            lane_pairs<kItems>(Bl, tmp);  // b is recomputed rather than kept: 32 registers saved
-            lane_pairs<kItems>(Cl, cv);
-#pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-              h = ffma2(a[i], h, fmul2(dup2(du[i]), tmp[i]));
-              y[i] = fmaf(h.y, cv[i].y, fmaf(h.x, cv[i].x, y[i]));
-            }
-          }
-          // h = state after this lane's last timestep
-          if (lane == 31) hs[cl * NP + pg] = h;
-          if (p.checkpoints && ((lane + 1) % kLanesPerChunk) == 0) {
-            const int k = tile * kChunksPerTile + (lane + 1) / kLanesPerChunk;
-            if (k < nchunks) {
-              float* ck = p.checkpoints + (((int64_t)b * p.dim + c) * nchunks + k) * N + 2 * pg;
-              ck[0] = h.x;
-              if (2 * pg + 1 < N) ck[1] = h.y;
-            }
-          }
-        }
-        __syncwarp();
-      }
-
-      if (cvalid) {
-        if (p.z) {
-          const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride +
-                          (int64_t)c * p.z_dim_stride;
-          float zv[kItems];
-          load_items<T, kItems, kVec>(zrow, tl, L, zv);
-#pragma unroll
-          for (int i = 0; i < kItems; ++i) y[i] *= silu_f(zv[i]);
-        }
-        T* orow = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_batch_stride +
-                  (int64_t)c * p.out_dim_stride;
-        store_items<T, kItems, kVec>(orow, tl, L, y);
-      }
-    }
-  }
-
-  if (p.last_state) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < G * NP * 2; idx += kThreads) {
-      const int cl = idx / (2 * NP), n = idx - cl * 2 * NP, c = c0 + cl;
-      if (c < p.dim && n < N)
-        p.last_state[((int64_t)b * p.dim + c) * N + n] = reinterpret_cast<const float*>(hs)[idx];
-    }
+    for (int i = 0; i < VE; ++i)
+      if (t + i < len) row[t + i] = Io<T>::from_f(v[i]);
   }
 }
 
-template <typename T, int kItems, int kWarps, int kCPW, bool kVec>
+}  // namespace
+
+template <typename T, int G, int NG, int kChan, int TT, bool kVec>
+struct ScanFwdCfg {
+  static constexpr int VE = Io<T>::kVecElems;
+  static constexpr int kThreads = kChan * NG;
+  static constexpr int NP = G * NG;            // padded dstate
+  static constexpr int kChunks = NP / 4;       // 16-byte chunks per B/C row
+  static constexpr int kSwz = kChunks >= 4 ? 3 : kChunks - 1;
+  static constexpr int RS = TT + 4;            // dt / dtu / y row stride (floats)
+  static constexpr int kVecPerRow = TT / VE;
+  static constexpr int kItems = kChan * kVecPerRow;                   // u/delta/z vectors per tile
+  static constexpr int kIt = (kItems + kThreads - 1) / kThreads;      // ... per thread
+  static constexpr int kBCItems = NP * kVecPerRow;                    // B (or C) vectors per tile
+  static constexpr int kBC = (kBCItems + kThreads - 1) / kThreads;
+  static constexpr size_t kSmemFloats = 3 * (size_t)kChan * RS + 2 * (size_t)TT * NP;
+  static_assert(G % 4 == 0 && (NG & (NG - 1)) == 0 && NG <= 32 && TT % VE == 0 && TT % 4 == 0, "cfg");
+  static_assert(kThreads % 32 == 0, "whole warps");
+};
+
+template <typename T, int G, int NG, int kChan, int TT, bool kVec>
+__global__ void __launch_bounds__(kChan * NG, G <= 4 ? 512 / (kChan * NG) : 1)
+scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
+  using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
+  constexpr int VE = Cfg::VE, kThreads = Cfg::kThreads, NP = Cfg::NP, RS = Cfg::RS;
+  constexpr int kIt = Cfg::kIt, kBC = Cfg::kBC, kVecPerRow = Cfg::kVecPerRow;
+  constexpr int Q = G / 4;
+
+  extern __shared__ __align__(16) float smem[];
+  float* dts = smem;                  // [kChan][RS]  dt
+  float* dtus = dts + kChan * RS;     // [kChan][RS]  dt * u
+  float* ys = dtus + kChan * RS;      // [kChan][RS]  <C, h>
+  float* Bs = ys + kChan * RS;        // [TT][NP]     swizzled
+  float* Cs = Bs + TT * NP;
+
+  const int N = p.dstate, L = p.seqlen;
+  const int b = blockIdx.y, c0 = blockIdx.x * kChan;
+  const int tid = threadIdx.x;
+  const int chl = tid / NG, g = tid % NG;
+  const int c = c0 + chl;
+  const bool cvalid = c < p.dim;
+  const int64_t bc = (int64_t)b * p.dim + c;
+
+  // ---- per-thread constants: A*log2(e) and the running state of the G rows of this slice ----------
+  float2 A2[G / 2], h[G / 2];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const int n = g * G + i;
+    float a = 0.f, hv = 0.f;
+    if (cvalid && n < N) {
+      a = p.A[(int64_t)c * N + n] * kLog2e;
+      if (p.initial_state) hv = p.initial_state[bc * N + n];
+    }
+    reinterpret_cast<float*>(A2)[i] = a;
+    reinterpret_cast<float*>(h)[i] = hv;
+  }
+
+  // ---- P/E item bookkeeping: item = (channel row, 16-byte vector) -----------------------------------
+  const T* ub = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride;
+  const T* db = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride;
+  const T* zb = p.z ? reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride : nullptr;
+  T* ob = reinterpret_cast<T*>(p.out) + (int64_t)b * p.out_batch_stride;
+  const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
+  const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
+
+  int it_ch[kIt], it_t[kIt];
+  float it_bias[kIt], it_D[kIt];
+  bool it_ok[kIt];
+#pragma unroll
+  for (int k = 0; k < kIt; ++k) {
+    const int idx = tid + k * kThreads;
+    it_ch[k] = idx / kVecPerRow;
+    it_t[k] = (idx % kVecPerRow) * VE;
+    it_ok[k] = idx < Cfg::kItems && c0 + it_ch[k] < p.dim;
+    it_bias[k] = (it_ok[k] && p.delta_bias) ? p.delta_bias[c0 + it_ch[k]] : 0.f;
+    it_D[k] = (it_ok[k] && p.D) ? p.D[c0 + it_ch[k]] : 0.f;
+  }
+  int bc_n[kBC], bc_t[kBC];
+  bool bc_ok[kBC];
+#pragma unroll
+  for (int k = 0; k < kBC; ++k) {
+    const int idx = tid + k * kThreads;
+    bc_n[k] = idx / kVecPerRow;
+    bc_t[k] = (idx % kVecPerRow) * VE;
+    bc_ok[k] = idx < Cfg::kBCItems;
+  }
+
+  uint4 u_nx[kIt], d_nx[kIt], z_cur[kIt], u_cur[kIt], B_nx[kBC], C_nx[kBC];
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  auto prefetch = [&](int t0) {
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      u_nx[k] = d_nx[k] = zero4;
+      if (it_ok[k]) {
+        const int cc = c0 + it_ch[k];
+        u_nx[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it_t[k], L);
+        d_nx[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it_t[k], L);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kBC; ++k) {
+      B_nx[k] = C_nx[k] = zero4;
+      if (bc_ok[k] && bc_n[k] < N) {
+        B_nx[k] = load_raw<T, kVec>(Bb + (int64_t)bc_n[k] * p.B_state_stride, t0 + bc_t[k], L);
+        C_nx[k] = load_raw<T, kVec>(Cb + (int64_t)bc_n[k] * p.C_state_stride, t0 + bc_t[k], L);
+      }
+    }
+  };
+
+  prefetch(0);
+  const int ntiles = (L + TT - 1) / TT;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int t0 = tile * TT;
+
+    // ---- P: registers -> shared fp32 tiles --------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      if (tid + k * kThreads < Cfg::kItems) {
+        float uv[VE], dv[VE];
+        Io<T>::unpack(u_nx[k], uv);
+        Io<T>::unpack(d_nx[k], dv);
+        u_cur[k] = u_nx[k];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+          float x = dv[i] + it_bias[k];
+          if (p.delta_softplus) x = softplus_f(x);
+          if (!it_ok[k] || t0 + it_t[k] + i >= L) x = 0.f;  // identity step: decay 1, input 0
+          dv[i] = x;
+          uv[i] *= x;
+        }
+        float* d0 = dts + it_ch[k] * RS + it_t[k];
+        float* d1 = dtus + it_ch[k] * RS + it_t[k];
+#pragma unroll
+        for (int i = 0; i < VE; i += 4) {
+          *reinterpret_cast<float4*>(d0 + i) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
+          *reinterpret_cast<float4*>(d1 + i) = make_float4(uv[i], uv[i + 1], uv[i + 2], uv[i + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kBC; ++k) {
+      if (bc_ok[k]) {
+        float bv[VE], cv[VE];
+        Io<T>::unpack(B_nx[k], bv);
+        Io<T>::unpack(C_nx[k], cv);
+        const int n = bc_n[k];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+          const int t = bc_t[k] + i;
+          const int pos = t * NP + (((n >> 2) ^ ((t >> 3) & Cfg::kSwz)) << 2) + (n & 3);
+          Bs[pos] = bv[i];
+          Cs[pos] = cv[i];
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- prefetch the next tile (and this tile's z) while M runs -----------------------------------
+    if (zb) {
+#pragma unroll
+      for (int k = 0; k < kIt; ++k) {
+        z_cur[k] = zero4;
+        if (it_ok[k])
+          z_cur[k] = load_raw<T, kVec>(zb + (int64_t)(c0 + it_ch[k]) * p.z_dim_stride, t0 + it_t[k], L);
+      }
+    }
+    if (tile + 1 < ntiles) prefetch(t0 + TT);
+
+    // ---- M: the recurrence -------------------------------------------------------------------------
+    {
+      const float* dtr = dts + chl * RS;
+      const float* dur = dtus + chl * RS;
+      float* yr = ys + chl * RS;
+      // software pipeline: the decays exp2(dt*A) of timestep t + kPD are issued before the FMA work of
+      // timestep t, so MUFU latency never sits on the recurrence's critical path
+      constexpr int kPD = G >= 16 ? 1 : (G >= 8 ? 2 : 4);
+      float2 er[kPD][G / 2];
+      float4 dcur = lds128(dtr);
+      {
+        const float dtv[4] = {dcur.x, dcur.y, dcur.z, dcur.w};
+#pragma unroll
+        for (int j = 0; j < kPD; ++j)
+#pragma unroll
+          for (int q = 0; q < G / 2; ++q) er[j][q] = ex2f2(fmul2(dup2(dtv[j]), A2[q]));
+      }
+#pragma unroll 1
+      for (int t4 = 0; t4 < TT; t4 += 4) {
+        // checkpoint: state at the start of every MTTS_SCAN_CHUNK timesteps (what the backward restarts from)
+        if (p.checkpoints && ((t0 + t4) % MTTS_SCAN_CHUNK) == 0 && t0 + t4 < L && cvalid) {
+          float* ck = p.checkpoints + (bc * nchunks + (t0 + t4) / MTTS_SCAN_CHUNK) * N + g * G;
+          if ((N & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < G; i += 4)
+              if (g * G + i < N)
+                *reinterpret_cast<float4*>(ck + i) = make_float4(h[i / 2].x, h[i / 2].y, h[i / 2 + 1].x, h[i / 2 + 1].y);
+          } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i)
+              if (g * G + i < N) ck[i] = reinterpret_cast<const float*>(h)[i];
+          }
+        }
+        const float4 dnext = lds128(dtr + t4 + 4);  // the row pad makes the last read harmless
+        const float4 x4 = lds128(dur + t4);
+        const float dtv[8] = {dcur.x, dcur.y, dcur.z, dcur.w, dnext.x, dnext.y, dnext.z, dnext.w};
+        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
+        dcur = dnext;
+        const int swz = (t4 >> 3) & Cfg::kSwz;
+        float yp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* Bt = Bs + (t4 + j) * NP;
+          const float* Ct = Cs + (t4 + j) * NP;
+          const float2 du2 = dup2(duv[j]);
+          float2 ec[G / 2];
+#pragma unroll
+          for (int q = 0; q < G / 2; ++q) {
+            ec[q] = er[j % kPD][q];
+            er[j % kPD][q] = ex2f2(fmul2(dup2(dtv[j + kPD]), A2[q]));
+          }
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const int off = ((g * Q + q) ^ swz) << 2;
+            const float4 Bv = lds128(Bt + off);
+            const float4 Cv = lds128(Ct + off);
+            h[2 * q] = ffma2(ec[2 * q], h[2 * q], fmul2(du2, make_float2(Bv.x, Bv.y)));
+            h[2 * q + 1] = ffma2(ec[2 * q + 1], h[2 * q + 1], fmul2(du2, make_float2(Bv.z, Bv.w)));
+            acc = ffma2(h[2 * q], make_float2(Cv.x, Cv.y), acc);
+            acc = ffma2(h[2 * q + 1], make_float2(Cv.z, Cv.w), acc);
+          }
+          yp[j] = acc.x + acc.y;
+        }
+        // sum the partials over the NG lanes of this channel
+#pragma unroll
+        for (int o = NG / 2; o >= 4; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yp[j] += __shfl_xor_sync(0xffffffffu, yp[j], o);
+        }
+        if constexpr (NG == 1) {
+          *reinterpret_cast<float4*>(yr + t4) = make_float4(yp[0], yp[1], yp[2], yp[3]);
+        } else if constexpr (NG == 2) {
+          // lane bit0 = 0 ends with t4+0,1 ; bit0 = 1 with t4+2,3
+          const bool hi = g & 1;
+          const float s0 = hi ? yp[0] : yp[2], s1 = hi ? yp[1] : yp[3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+          const float r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+          const float k0 = (hi ? yp[2] : yp[0]) + r0, k1 = (hi ? yp[3] : yp[1]) + r1;
+          *reinterpret_cast<float2*>(yr + t4 + (hi ? 2 : 0)) = make_float2(k0, k1);
+        } else {
+          // transposing butterfly over lane bits 1 and 0: lane (g & 3) ends with timestep t4 + (g & 3)
+          const bool b1 = g & 2, b0 = g & 1;
+          const float s0 = b1 ? yp[0] : yp[2], s1 = b1 ? yp[1] : yp[3];
+          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+          const float r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+          const float k0 = (b1 ? yp[2] : yp[0]) + r0, k1 = (b1 ? yp[3] : yp[1]) + r1;
+          const float s = b0 ? k0 : k1;
+          const float r = __shfl_xor_sync(0xffffffffu, s, 1);
+          const float tot = (b0 ? k1 : k0) + r;
+          // for NG > 4 every group of 4 lanes holds the same totals; the first group writes
+          if (g < 4) yr[t4 + (g & 3)] = tot;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- E: gate and stream out --------------------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      if (it_ok[k]) {
+        float uv[VE], yv[VE];
+        Io<T>::unpack(u_cur[k], uv);
+        const float* y0 = ys + it_ch[k] * RS + it_t[k];
+#pragma unroll
+        for (int i = 0; i < VE; i += 4) {
+          const float4 v = lds128(y0 + i);
+          yv[i] = v.x; yv[i + 1] = v.y; yv[i + 2] = v.z; yv[i + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < VE; ++i) yv[i] = fmaf(it_D[k], uv[i], yv[i]);
+        if (zb) {
+          float zv[VE];
+          Io<T>::unpack(z_cur[k], zv);
+#pragma unroll
+          for (int i = 0; i < VE; ++i) yv[i] *= silu_f(zv[i]);
+        }
+        store_raw<T, kVec>(ob + (int64_t)(c0 + it_ch[k]) * p.out_dim_stride, t0 + it_t[k], L, yv);
+      }
+    }
+    // no barrier needed here: the next P writes dts/dtus/Bs/Cs (last read in M, before the barrier
+    // above) and the next M writes ys only after the next P's barrier.
+  }
+
+  if (p.last_state && cvalid) {
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+      if (g * G + i < N) p.last_state[bc * N + g * G + i] = reinterpret_cast<const float*>(h)[i];
+  }
+}
+
+template <typename T, int G, int NG, int kChan, int TT, bool kVec>
 static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
-  using Tile = PairTile<kItems>;
-  constexpr int G = kWarps * kCPW;
+  using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
-  const int NP = (p.dstate + 1) / 2;
-  const size_t smem = sizeof(float) * (2 * Tile::kPairs * Tile::kRow + 4 * (size_t)G * NP);
-  auto kern = scan_fwd_kernel<T, kItems, kWarps, kCPW, kVec>;
+  const size_t smem = sizeof(float) * Cfg::kSmemFloats;
+  auto kern = scan_fwd_kernel<T, G, NG, kChan, TT, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
-  const dim3 grid((p.dim + G - 1) / G, p.batch);
-  kern<<<grid, kWarps * 32, smem, stream>>>(p, nchunks);
+  const dim3 grid((p.dim + kChan - 1) / kChan, p.batch);
+  kern<<<grid, Cfg::kThreads, smem, stream>>>(p, nchunks);
   return launch_status();
+}
+
+// G states per thread x NG slices cover the (padded) dstate; TT scales with the bytes per element so
+// that the register-resident prefetch stays at two vectors per thread and stream.
+template <typename T, bool kVec>
+static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t stream) {
+  constexpr int TT = Io<T>::kVecElems * 8;  // 64 (bf16) / 32 (fp32)
+  const int N = p.dstate;
+  if (N <= 4) return launch_scan_fwd<T, 4, 1, 64, TT / 4, kVec>(p, stream);
+  if (N <= 8) return launch_scan_fwd<T, 4, 2, 32, TT / 2, kVec>(p, stream);
+  if (N <= 16) return launch_scan_fwd<T, 4, 4, 16, TT, kVec>(p, stream);
+  if (N <= 32) return launch_scan_fwd<T, 8, 4, 16, TT, kVec>(p, stream);
+  if (N <= 64) return launch_scan_fwd<T, 16, 4, 32, TT, kVec>(p, stream);
+  if (N <= 128) return launch_scan_fwd<T, 16, 8, 16, TT, kVec>(p, stream);
+  return launch_scan_fwd<T, 16, 16, 8, TT, kVec>(p, stream);
 }
 
 template <typename T>
@@ -192,13 +388,7 @@ static int dispatch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream)
                    vec_ok<T>(p.C, p.C_batch_stride, p.C_state_stride, p.seqlen) &&
                    vec_ok<T>(p.z, p.z_batch_stride, p.z_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen);
-  const bool two = p.dstate <= kScanNChunk && p.dim >= 16;
-  if (vec) {
-    return two ? launch_scan_fwd<T, 16, 8, 2, true>(p, stream)
-               : launch_scan_fwd<T, 16, 8, 1, true>(p, stream);
-  }
-  return two ? launch_scan_fwd<T, 16, 8, 2, false>(p, stream)
-             : launch_scan_fwd<T, 16, 8, 1, false>(p, stream);
+  return vec ? dispatch_scan_fwd_n<T, true>(p, stream) : dispatch_scan_fwd_n<T, false>(p, stream);
 }
 
 }  // namespace mtts
