@@ -93,8 +93,8 @@ __device__ __forceinline__ void slice_reduce_store(float (&v)[4], int g, float* 
   }
 }
 
-// Halving butterfly over the channel lanes (lane bits [log2 NG, 5)): v[j*4 + i] (timestep j, state i of
-// the slice) summed over the warp's 32/NG channels; the surviving values go to tile[(j)*NP + i].
+// Halving butterfly over the channel lanes (lane bits [log2 NG, 5)): v[i*4 + j] (state i of the slice,
+// timestep j) summed over the warp's 32/NG channels; the surviving values go to tile[(j)*NP + i].
 template <int NG, int CNT, int BIT>
 __device__ __forceinline__ void chan_reduce_step(float (&v)[16], int lane, int& prefix) {
   if constexpr (BIT >= NG) {
@@ -124,45 +124,43 @@ __device__ __forceinline__ void chan_reduce_store(float (&v)[16], int lane, int 
   chan_reduce_step<NG, 16, 16>(v, lane, prefix);
   const bool writer = CL <= 16 || (lane & NG) == 0;  // CL = 32: the last stage was a plain xor
   if (writer) {
-    if constexpr (R >= 4) {
+    // surviving values: idx = prefix * R + r, state i = idx >> 2, timestep j = idx & 3
 #pragma unroll
-      for (int r = 0; r < R; r += 4) {
-        const int idx = prefix * R + r;
-        *reinterpret_cast<float4*>(tile + (idx >> 2) * NP + g * 4) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-      }
-    } else if constexpr (R == 2) {
-      const int idx = prefix * 2;
-      *reinterpret_cast<float2*>(tile + (idx >> 2) * NP + g * 4 + (idx & 3)) = make_float2(v[0], v[1]);
-    } else {
-      tile[(prefix >> 2) * NP + g * 4 + (prefix & 3)] = v[0];
+    for (int r = 0; r < R; ++r) {
+      const int idx = prefix * R + r;
+      tile[(idx & 3) * NP + g * 4 + (idx >> 2)] = v[r];
     }
   }
 }
 
 }  // namespace
 
-template <typename T, int NG, bool kVec>
+// CC = channels per thread (register tiling of the B / C operands: every LDS of a B / C chunk feeds CC
+// recurrences, and the dB / dC contributions of the CC channels are summed in-thread before the
+// butterfly), kWarps = warps per CTA.
+template <typename T, int NG, int CC, int kWarps, bool kVec>
 struct ScanBwdCfg {
   static constexpr int VE = Io<T>::kVecElems;
-  static constexpr int kChan = kBwdThreads / NG;
+  static constexpr int kThreads = 32 * kWarps;
+  static constexpr int kChan = kThreads / NG * CC;
   static constexpr int NP = 4 * NG;
   static constexpr int kSwz = NG >= 4 ? 3 : NG - 1;
   static constexpr int RS = kTT + 4;
   static constexpr int kVecPerRow = kTT / VE;
   static constexpr int kItems = kChan * kVecPerRow;
-  static constexpr int kIt = (kItems + kBwdThreads - 1) / kBwdThreads;
+  static constexpr int kIt = (kItems + kThreads - 1) / kThreads;
   static constexpr int kBCItems = NG * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
   // dt, dtu (-> sGB), gy, y, ddtA rows; B, C tiles; per-warp dB, dC tiles; group-start states
   static constexpr size_t kSmemFloats = 5 * (size_t)kChan * RS + 2 * (size_t)kTT * NP +
-                                        2 * 2 * (size_t)kTT * NP + 7 * 4 * (size_t)kBwdThreads;
+                                        2 * kWarps * (size_t)kTT * NP + 7 * 4 * CC * (size_t)kThreads;
 };
 
-template <typename T, int NG, bool kVec>
-__global__ void __launch_bounds__(kBwdThreads, NG == 4 ? 7 : 1)
+template <typename T, int NG, int CC, int kWarps, bool kVec>
+__global__ void __launch_bounds__(32 * kWarps, (NG == 4 && CC == 1) ? 7 : 1)
 scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
-  using Cfg = ScanBwdCfg<T, NG, kVec>;
+  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
   constexpr int VE = Cfg::VE, kChan = Cfg::kChan, NP = Cfg::NP, RS = Cfg::RS;
-  constexpr int kIt = Cfg::kIt, kVecPerRow = Cfg::kVecPerRow, kThreads = kBwdThreads;
+  constexpr int kIt = Cfg::kIt, kVecPerRow = Cfg::kVecPerRow, kThreads = Cfg::kThreads;
 
   extern __shared__ __align__(16) float smem[];
   float* dts = smem;                      // [kChan][RS] dt
@@ -172,25 +170,26 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   float* das = ys + kChan * RS;           // <w, A*log2e>
   float* Bs = das + kChan * RS;           // [kTT][NP] swizzled
   float* Cs = Bs + kTT * NP;
-  float* dBw = Cs + kTT * NP;             // [2 warps][kTT][NP]
-  float* dCw = dBw + 2 * kTT * NP;
-  float* hbs = dCw + 2 * kTT * NP;        // [groups 1..7][kThreads][4] state at the start of the group
+  float* dBw = Cs + kTT * NP;             // [kWarps][kTT][NP]
+  float* dCw = dBw + kWarps * kTT * NP;
+  float* hbs = dCw + kWarps * kTT * NP;   // [groups 1..7][kThreads][CC][4] state at the start of the group
 
   const int N = p.dstate, L = p.seqlen;
   const int b = blockIdx.y, c0 = blockIdx.x * kChan;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chl = tid / NG, g = tid % NG;
+  const int chl = tid / NG * CC, g = tid % NG;  // first of this thread's CC channels
   const int c = c0 + chl;
-  const bool cvalid = c < p.dim;
-  const int64_t bc = (int64_t)b * p.dim + c;
 
-  float2 A2[2], Gc[2], dAacc[2];
+  float2 A2[CC][2], Gc[CC][2], dAacc[CC][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int n = g * 4 + i;
-    reinterpret_cast<float*>(A2)[i] = (cvalid && n < N) ? p.A[(int64_t)c * N + n] * kLog2e : 0.f;
-    reinterpret_cast<float*>(Gc)[i] = 0.f;
-    reinterpret_cast<float*>(dAacc)[i] = 0.f;
+  for (int k = 0; k < CC; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = g * 4 + i;
+      reinterpret_cast<float*>(A2[k])[i] = (c + k < p.dim && n < N) ? p.A[(int64_t)(c + k) * N + n] * kLog2e : 0.f;
+      reinterpret_cast<float*>(Gc[k])[i] = 0.f;
+      reinterpret_cast<float*>(dAacc[k])[i] = 0.f;
+    }
   }
 
   const T* ub = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride;
@@ -204,7 +203,47 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
 #pragma unroll
   for (int k = 0; k < kIt; ++k) dD_acc[k] = dbias_acc[k] = 0.f;
 
+  // Raw inputs of a tile (u, delta, dout, z vectors of this thread's items) and its checkpoints are fetched
+  // one tile ahead, during the previous tile's E phase, so they are never live across M.
+  uint4 ur[kIt], dr[kIt], gr[kIt], zr[kIt];
+  float4 ck4[CC];
+  auto fetch_tile = [&](int tile) {
+    const int t0 = tile * kTT;
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      const int idx = tid + k * kThreads;
+      const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
+      const int cc = c0 + ich;
+      ur[k] = dr[k] = gr[k] = zr[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < Cfg::kItems && cc < p.dim) {
+        ur[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
+        dr[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
+        gr[k] = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
+        if (zb) zr[k] = load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CC; ++k) {
+      float hv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c + k < p.dim) {
+        const float* ck = p.checkpoints + (((int64_t)b * p.dim + c + k) * nchunks + tile) * N + g * 4;
+        if ((N & 3) == 0) {
+          if (g * 4 < N) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(ck));
+            hv[0] = v.x; hv[1] = v.y; hv[2] = v.z; hv[3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (g * 4 + i < N) hv[i] = ck[i];
+        }
+      }
+      ck4[k] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
+  };
+
   const int ntiles = (L + kTT - 1) / kTT;
+  fetch_tile(ntiles - 1);
   for (int tile = ntiles - 1; tile >= 0; --tile) {
     const int t0 = tile * kTT;
 
@@ -218,19 +257,12 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
         const bool ok = cc < p.dim;
         float uv[VE], dv[VE], gv[VE];
         {
-          uint4 ur = make_uint4(0u, 0u, 0u, 0u), dr = ur, gr = ur, zr = ur;
-          if (ok) {
-            ur = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
-            dr = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
-            gr = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
-            if (zb) zr = load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L);
-          }
-          Io<T>::unpack(ur, uv);
-          Io<T>::unpack(dr, dv);
-          Io<T>::unpack(gr, gv);
+          Io<T>::unpack(ur[k], uv);
+          Io<T>::unpack(dr[k], dv);
+          Io<T>::unpack(gr[k], gv);
           if (zb) {
             float zv[VE];
-            Io<T>::unpack(zr, zv);
+            Io<T>::unpack(zr[k], zv);
 #pragma unroll
             for (int i = 0; i < VE; ++i) gv[i] *= silu_f(zv[i]);
           }
@@ -286,104 +318,137 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       const float* gyr = gys + chl * RS;
       float* yr = ys + chl * RS;
       float* dar = das + chl * RS;
-      float* hb = hbs + tid * 4;
+      float* hb = hbs + tid * (4 * CC);
       float* dBt = dBw + warp * kTT * NP;
       float* dCt = dCw + warp * kTT * NP;
 
-      float2 h[2];
-      {
-        float hv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (cvalid) {
-          const float* ck = p.checkpoints + (bc * nchunks + tile) * N + g * 4;
+      float2 h[CC][2];
+      float4 h0[CC];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (g * 4 + i < N) hv[i] = ck[i];
-        }
-        h[0] = make_float2(hv[0], hv[1]);
-        h[1] = make_float2(hv[2], hv[3]);
+      for (int k = 0; k < CC; ++k) {
+        h[k][0] = make_float2(ck4[k].x, ck4[k].y);
+        h[k][1] = make_float2(ck4[k].z, ck4[k].w);
+        h0[k] = ck4[k];
       }
       // pre-pass: state at the start of every group of 4 timesteps
-      const float4 h0 = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
 #pragma unroll 1
       for (int s = 0; s < 7; ++s) {
-        const float4 d4 = lds128(dtr + 4 * s);
-        const float4 x4 = lds128(dur + 4 * s);
-        const float dtv[4] = {d4.x, d4.y, d4.z, d4.w};
-        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
+        float dtv[CC][4], duv[CC][4];
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          const float4 d4 = lds128(dtr + k * RS + 4 * s);
+          const float4 x4 = lds128(dur + k * RS + 4 * s);
+          dtv[k][0] = d4.x; dtv[k][1] = d4.y; dtv[k][2] = d4.z; dtv[k][3] = d4.w;
+          duv[k][0] = x4.x; duv[k][1] = x4.y; duv[k][2] = x4.z; duv[k][3] = x4.w;
+        }
         const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 Bv = lds128(Bs + (4 * s + j) * NP + off);
-          const float2 dt2 = dup2(dtv[j]), du2 = dup2(duv[j]);
-          h[0] = ffma2(ex2f2(fmul2(dt2, A2[0])), h[0], fmul2(du2, lo2(Bv)));
-          h[1] = ffma2(ex2f2(fmul2(dt2, A2[1])), h[1], fmul2(du2, hi2(Bv)));
+#pragma unroll
+          for (int k = 0; k < CC; ++k) {
+            const float2 dt2 = dup2(dtv[k][j]), du2 = dup2(duv[k][j]);
+            h[k][0] = ffma2(ex2f2(fmul2(dt2, A2[k][0])), h[k][0], fmul2(du2, lo2(Bv)));
+            h[k][1] = ffma2(ex2f2(fmul2(dt2, A2[k][1])), h[k][1], fmul2(du2, hi2(Bv)));
+          }
         }
-        *reinterpret_cast<float4*>(hb + s * 4 * kThreads) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+#pragma unroll
+        for (int k = 0; k < CC; ++k)
+          *reinterpret_cast<float4*>(hb + s * 4 * CC * kThreads + 4 * k) =
+              make_float4(h[k][0].x, h[k][0].y, h[k][1].x, h[k][1].y);
       }
 
 #pragma unroll 1
       for (int s = 7; s >= 0; --s) {
-        const float4 d4 = lds128(dtr + 4 * s);
-        const float4 x4 = lds128(dur + 4 * s);
-        const float4 g4 = lds128(gyr + 4 * s);
-        const float dtv[4] = {d4.x, d4.y, d4.z, d4.w};
-        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
-        const float gyv[4] = {g4.x, g4.y, g4.z, g4.w};
+        float dtv[CC][4], duv[CC][4], gyv[CC][4];
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          const float4 d4 = lds128(dtr + k * RS + 4 * s);
+          const float4 x4 = lds128(dur + k * RS + 4 * s);
+          const float4 g4 = lds128(gyr + k * RS + 4 * s);
+          dtv[k][0] = d4.x; dtv[k][1] = d4.y; dtv[k][2] = d4.z; dtv[k][3] = d4.w;
+          duv[k][0] = x4.x; duv[k][1] = x4.y; duv[k][2] = x4.z; duv[k][3] = x4.w;
+          gyv[k][0] = g4.x; gyv[k][1] = g4.y; gyv[k][2] = g4.z; gyv[k][3] = g4.w;
+        }
         const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
         const float* Bt = Bs + 4 * s * NP + off;
         const float* Ct = Cs + 4 * s * NP + off;
 
         // re-run the 4 steps, keeping decays and states
-        float2 a[4][2], hs[4][2];
+        float2 a[CC][4][2], hs[CC][4][2];
         {
-          const float4 h4 = s == 0 ? h0 : lds128(hb + (s - 1) * 4 * kThreads);
-          float2 hc0 = lo2(h4), hc1 = hi2(h4);
-          float yp[4];
+          float2 hc[CC][2];
+          float yp[CC][4];
+#pragma unroll
+          for (int k = 0; k < CC; ++k) {
+            const float4 h4 = s == 0 ? h0[k] : lds128(hb + (s - 1) * 4 * CC * kThreads + 4 * k);
+            hc[k][0] = lo2(h4);
+            hc[k][1] = hi2(h4);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 Bv = lds128(Bt + j * NP);
             const float4 Cv = lds128(Ct + j * NP);
-            const float2 dt2 = dup2(dtv[j]), du2 = dup2(duv[j]);
-            a[j][0] = ex2f2(fmul2(dt2, A2[0]));
-            a[j][1] = ex2f2(fmul2(dt2, A2[1]));
-            hc0 = ffma2(a[j][0], hc0, fmul2(du2, lo2(Bv)));
-            hc1 = ffma2(a[j][1], hc1, fmul2(du2, hi2(Bv)));
-            hs[j][0] = hc0;
-            hs[j][1] = hc1;
-            const float2 acc = ffma2(hc1, hi2(Cv), fmul2(hc0, lo2(Cv)));
-            yp[j] = acc.x + acc.y;
+#pragma unroll
+            for (int k = 0; k < CC; ++k) {
+              const float2 dt2 = dup2(dtv[k][j]), du2 = dup2(duv[k][j]);
+              a[k][j][0] = ex2f2(fmul2(dt2, A2[k][0]));
+              a[k][j][1] = ex2f2(fmul2(dt2, A2[k][1]));
+              hc[k][0] = ffma2(a[k][j][0], hc[k][0], fmul2(du2, lo2(Bv)));
+              hc[k][1] = ffma2(a[k][j][1], hc[k][1], fmul2(du2, hi2(Bv)));
+              hs[k][j][0] = hc[k][0];
+              hs[k][j][1] = hc[k][1];
+              const float2 acc = ffma2(hc[k][1], hi2(Cv), fmul2(hc[k][0], lo2(Cv)));
+              yp[k][j] = acc.x + acc.y;
+            }
           }
-          slice_reduce_store<NG>(yp, g, yr + 4 * s);
+#pragma unroll
+          for (int k = 0; k < CC; ++k) slice_reduce_store<NG>(yp[k], g, yr + k * RS + 4 * s);
         }
 
         // reverse recurrence
-        float dBv[16], dCv[16], sgb[4], dda[4];
+        float dBv[16], dCv[16], sgb[CC][4], dda[CC][4];
 #pragma unroll
         for (int j = 3; j >= 0; --j) {
           const float4 Bv = lds128(Bt + j * NP);
           const float4 Cv = lds128(Ct + j * NP);
-          const float2 gy2 = dup2(gyv[j]), du2 = dup2(duv[j]), dt2 = dup2(dtv[j]);
-          const float2 G0 = ffma2(lo2(Cv), gy2, Gc[0]);
-          const float2 G1 = ffma2(hi2(Cv), gy2, Gc[1]);
-          const float2 dC0 = fmul2(gy2, hs[j][0]), dC1 = fmul2(gy2, hs[j][1]);
-          const float2 dB0 = fmul2(du2, G0), dB1 = fmul2(du2, G1);
-          dCv[4 * j] = dC0.x; dCv[4 * j + 1] = dC0.y; dCv[4 * j + 2] = dC1.x; dCv[4 * j + 3] = dC1.y;
-          dBv[4 * j] = dB0.x; dBv[4 * j + 1] = dB0.y; dBv[4 * j + 2] = dB1.x; dBv[4 * j + 3] = dB1.y;
-          const float2 sg = ffma2(G1, hi2(Bv), fmul2(G0, lo2(Bv)));
-          sgb[j] = sg.x + sg.y;
-          // a_t h_{t-1} = h_t - dt u B_t
-          const float2 ah0 = ffma2(make_float2(-du2.x, -du2.y), lo2(Bv), hs[j][0]);
-          const float2 ah1 = ffma2(make_float2(-du2.x, -du2.y), hi2(Bv), hs[j][1]);
-          const float2 w0 = fmul2(G0, ah0), w1 = fmul2(G1, ah1);
-          const float2 da = ffma2(w1, A2[1], fmul2(w0, A2[0]));
-          dda[j] = da.x + da.y;
-          dAacc[0] = ffma2(w0, dt2, dAacc[0]);
-          dAacc[1] = ffma2(w1, dt2, dAacc[1]);
-          Gc[0] = fmul2(a[j][0], G0);
-          Gc[1] = fmul2(a[j][1], G1);
+          float2 dB0, dB1, dC0, dC1;
+#pragma unroll
+          for (int k = 0; k < CC; ++k) {
+            const float2 gy2 = dup2(gyv[k][j]), du2 = dup2(duv[k][j]), dt2 = dup2(dtv[k][j]);
+            const float2 G0 = ffma2(lo2(Cv), gy2, Gc[k][0]);
+            const float2 G1 = ffma2(hi2(Cv), gy2, Gc[k][1]);
+            if (k == 0) {
+              dC0 = fmul2(gy2, hs[k][j][0]); dC1 = fmul2(gy2, hs[k][j][1]);
+              dB0 = fmul2(du2, G0); dB1 = fmul2(du2, G1);
+            } else {
+              dC0 = ffma2(gy2, hs[k][j][0], dC0); dC1 = ffma2(gy2, hs[k][j][1], dC1);
+              dB0 = ffma2(du2, G0, dB0); dB1 = ffma2(du2, G1, dB1);
+            }
+            const float2 sg = ffma2(G1, hi2(Bv), fmul2(G0, lo2(Bv)));
+            sgb[k][j] = sg.x + sg.y;
+            // a_t h_{t-1} = h_t - dt u B_t
+            const float2 ndu = make_float2(-du2.x, -du2.y);
+            const float2 ah0 = ffma2(ndu, lo2(Bv), hs[k][j][0]);
+            const float2 ah1 = ffma2(ndu, hi2(Bv), hs[k][j][1]);
+            const float2 w0 = fmul2(G0, ah0), w1 = fmul2(G1, ah1);
+            const float2 da = ffma2(w1, A2[k][1], fmul2(w0, A2[k][0]));
+            dda[k][j] = da.x + da.y;
+            dAacc[k][0] = ffma2(w0, dt2, dAacc[k][0]);
+            dAacc[k][1] = ffma2(w1, dt2, dAacc[k][1]);
+            Gc[k][0] = fmul2(a[k][j][0], G0);
+            Gc[k][1] = fmul2(a[k][j][1], G1);
+          }
+          // state-major (idx = i*4 + j): the first butterfly stages split on the state bits, so they can
+          // start as soon as this timestep is done instead of after the whole group
+          dCv[j] = dC0.x; dCv[4 + j] = dC0.y; dCv[8 + j] = dC1.x; dCv[12 + j] = dC1.y;
+          dBv[j] = dB0.x; dBv[4 + j] = dB0.y; dBv[8 + j] = dB1.x; dBv[12 + j] = dB1.y;
         }
-        slice_reduce_store<NG>(sgb, g, dur + 4 * s);
-        slice_reduce_store<NG>(dda, g, dar + 4 * s);
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          slice_reduce_store<NG>(sgb[k], g, dur + k * RS + 4 * s);
+          slice_reduce_store<NG>(dda[k], g, dar + k * RS + 4 * s);
+        }
         chan_reduce_store<NG, NP>(dBv, lane, g, dBt + 4 * s * NP);
         chan_reduce_store<NG, NP>(dCv, lane, g, dCt + 4 * s * NP);
       }
@@ -391,6 +456,48 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     __syncthreads();
 
     // ---- E ----------------------------------------------------------------------------------------
+    // this tile's raw inputs are read again (L2 hits) and the next tile's are requested now; both arrive
+    // while the dB / dC tiles are flushed
+    uint4 eu[kIt], ed[kIt], eg[kIt], ez[kIt];
+#pragma unroll
+    for (int k = 0; k < kIt; ++k) {
+      const int idx = tid + k * kThreads;
+      const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
+      const int cc = c0 + ich;
+      eu[k] = ed[k] = eg[k] = ez[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < Cfg::kItems && cc < p.dim) {
+        eu[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
+        ed[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
+        eg[k] = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
+        if (zb) ez[k] = load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L);
+      }
+    }
+    if (tile > 0) fetch_tile(tile - 1);
+    // dB / dC: sum the warps' tiles, one 16-byte RED per (state row, 4 timesteps)
+    for (int idx = tid; idx < 2 * NP * (kTT / 4); idx += kThreads) {
+      const int which = idx / (NP * (kTT / 4)), r = idx % (NP * (kTT / 4));
+      const int n = r % NP, tq = (r / NP) * 4;
+      if (n < N && t0 + tq < L) {
+        const float* w0 = (which ? dCw : dBw) + tq * NP + n;
+        float acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i] = w0[i * NP];
+#pragma unroll
+          for (int w = 1; w < kWarps; ++w) acc[i] += w0[w * kTT * NP + i * NP];
+        }
+        float* dst = (which ? p.dC : p.dB) + ((int64_t)b * N + n) * L + t0 + tq;
+        if (kVec && t0 + tq + 3 < L) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]),
+                       "f"(acc[1]), "f"(acc[2]), "f"(acc[3])
+                       : "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (t0 + tq + i < L) atomicAdd(dst + i, acc[i]);
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       const int idx = tid + k * kThreads;
@@ -398,10 +505,10 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       const int cc = c0 + ich;
       if (idx < Cfg::kItems && cc < p.dim) {
         float uv[VE], dv[VE], gv[VE], zv[VE];
-        Io<T>::unpack(load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L), uv);
-        Io<T>::unpack(load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L), dv);
-        Io<T>::unpack(load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L), gv);
-        if (zb) Io<T>::unpack(load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L), zv);
+        Io<T>::unpack(eu[k], uv);
+        Io<T>::unpack(ed[k], dv);
+        Io<T>::unpack(eg[k], gv);
+        if (zb) Io<T>::unpack(ez[k], zv);
         const float bias = p.delta_bias ? p.delta_bias[cc] : 0.f;
         const float Dv = p.D ? p.D[cc] : 0.f;
         float dtv[VE], sgv[VE], yv[VE], dav[VE];
@@ -442,28 +549,6 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
                                  (int64_t)cc * p.dz_dim_stride, t0 + it, L, o_dz);
       }
     }
-    // dB / dC: sum the two warps' tiles, one 16-byte RED per (state row, 4 timesteps)
-    for (int idx = tid; idx < 2 * NP * (kTT / 4); idx += kThreads) {
-      const int which = idx / (NP * (kTT / 4)), r = idx % (NP * (kTT / 4));
-      const int n = r % NP, tq = (r / NP) * 4;
-      if (n < N && t0 + tq < L) {
-        const float* w0 = (which ? dCw : dBw) + tq * NP + n;
-        const float* w1 = w0 + kTT * NP;
-        float acc[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = w0[i * NP] + w1[i * NP];
-        float* dst = (which ? p.dC : p.dB) + ((int64_t)b * N + n) * L + t0 + tq;
-        if (kVec && t0 + tq + 3 < L) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]),
-                       "f"(acc[1]), "f"(acc[2]), "f"(acc[3])
-                       : "memory");
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (t0 + tq + i < L) atomicAdd(dst + i, acc[i]);
-        }
-      }
-    }
     __syncthreads();  // tiles are single-buffered
   }
 
@@ -483,39 +568,43 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       if (p.ddelta_bias) atomicAdd(p.ddelta_bias + cc, sb);
     }
   }
-  if (cvalid) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (g * 4 + i < N) atomicAdd(p.dA + (int64_t)c * N + g * 4 + i, reinterpret_cast<const float*>(dAacc)[i]);
+  for (int k = 0; k < CC; ++k) {
+    if (c + k < p.dim) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (g * 4 + i < N)
+          atomicAdd(p.dA + (int64_t)(c + k) * N + g * 4 + i, reinterpret_cast<const float*>(dAacc[k])[i]);
+    }
   }
 }
 
-template <typename T, int NG, bool kVec>
+template <typename T, int NG, int CC, int kWarps, bool kVec>
 static int launch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
-  using Cfg = ScanBwdCfg<T, NG, kVec>;
+  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
   const size_t smem = sizeof(float) * Cfg::kSmemFloats;
-  auto kern = scan_bwd_kernel<T, NG, kVec>;
+  auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + Cfg::kChan - 1) / Cfg::kChan, p.batch);
-  kern<<<grid, kBwdThreads, smem, stream>>>(p, nchunks);
+  kern<<<grid, Cfg::kThreads, smem, stream>>>(p, nchunks);
   return launch_status();
 }
 
 template <typename T, bool kVec>
 static int dispatch_scan_bwd_n(const mtts_scan_bwd_params& p, cudaStream_t stream) {
   const int N = p.dstate;
-  if (N <= 4) return launch_scan_bwd<T, 1, kVec>(p, stream);
-  if (N <= 8) return launch_scan_bwd<T, 2, kVec>(p, stream);
-  if (N <= 16) return launch_scan_bwd<T, 4, kVec>(p, stream);
-  if (N <= 32) return launch_scan_bwd<T, 8, kVec>(p, stream);
-  return launch_scan_bwd<T, 16, kVec>(p, stream);
+  if (N <= 4) return launch_scan_bwd<T, 1, 1, 2, kVec>(p, stream);
+  if (N <= 8) return launch_scan_bwd<T, 2, 1, 2, kVec>(p, stream);
+  return launch_scan_bwd<T, 4, 2, 1, kVec>(p, stream);
 }
 
 template <typename T>
 static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
-  if (p.dstate > 64) return dispatch_scan_bwd_wide(p, stream);
+  // wide states (this kernel's slice butterflies stop paying beyond 4 slices), or too few channels: the
+  // time-parallel kernel
+  if (p.dstate > 16 || scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_bwd_wide(p, stream);
   const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&

@@ -10,6 +10,8 @@
 //           and shared by every channel of the group -- upstream re-reads it from L2 per channel.
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mtts {
@@ -150,6 +152,19 @@ template <typename T>
 inline bool vec_ok(const void* p, int64_t s0, int64_t s1, int seqlen) {
   constexpr int VE = Io<T>::kVecElems;
   return p == nullptr || (aligned16(p) && s0 % VE == 0 && s1 % VE == 0 && seqlen % VE == 0);
+}
+
+// Which kernel family runs a scan.  The time-sequential kernels (scan_fwd.cu / scan_bwd.cu: one thread per
+// channel and 4-state slice) need batch x dim channels to fill the machine; long sequences over few
+// channels go to the time-parallel kernels (scan_*_wide.cu: lanes = timesteps).  MTTS_SCAN_IMPL=seq|wide
+// overrides the choice (tests exercise both families on the same inputs).
+inline bool scan_use_wide(int batch, int dim, int seqlen) {
+  if (const char* e = getenv("MTTS_SCAN_IMPL")) {
+    if (e[0] == 's') return false;
+    if (e[0] == 'w') return true;
+  }
+  const int64_t channels = (int64_t)batch * dim;
+  return channels < 8192 && channels * seqlen >= (int64_t(1) << 24);
 }
 
 }  // namespace mtts

@@ -21,6 +21,8 @@
 
 namespace mtts {
 
+int dispatch_scan_fwd_wide(const mtts_scan_fwd_params& p, cudaStream_t stream);  // scan_fwd_wide.cu
+
 namespace {
 
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -382,6 +384,7 @@ static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t strea
 
 template <typename T>
 static int dispatch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
+  if (scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_fwd_wide(p, stream);
   const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&

@@ -105,7 +105,11 @@ SCAN_CASES = [
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("case", SCAN_CASES, ids=[f"b{c[0]}d{c[1]}t{c[2]}n{c[3]}" + "".join(
     k.replace("with_", "_") + str(int(v)) for k, v in c[4].items()) for c in SCAN_CASES])
-def test_selective_scan_fwd_bwd_vs_oracle(case, dtype):
+@pytest.mark.parametrize("impl", ["seq", "wide"])
+def test_selective_scan_fwd_bwd_vs_oracle(case, dtype, impl, monkeypatch):
+    # both kernel families (time-sequential / time-parallel, csrc/scan_common.cuh::scan_use_wide) on the
+    # same inputs; without the override the library picks by problem size
+    monkeypatch.setenv("MTTS_SCAN_IMPL", impl)
     batch, dim, T, N, kw = case
     inp = make_scan_inputs(batch, dim, T, N, seed=T + N, dtype=dtype, **kw)
     ref = run_scan_oracle(inp)

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=131072)
     ap.add_argument("--dim", type=int, default=2048)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="", help="N,T: a single point of the sweep")
     args = ap.parse_args()
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     e = 2 if dt == torch.bfloat16 else 4
@@ -49,8 +50,11 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     dev = "cuda"
     rows = []
+    only = tuple(int(v) for v in args.only.split(",")) if args.only else None
     for N in (16, 64):
         for T in (4096, 16384, 65536):
+            if only and (N, T) != only:
+                continue
             B, Di = args.tokens // T, args.dim
             u = torch.randn(B, Di, T, device=dev, dtype=dt).requires_grad_()
             delta = (0.5 * torch.rand(B, Di, T, device=dev)).to(dt).requires_grad_()
