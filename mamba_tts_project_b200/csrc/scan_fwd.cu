@@ -73,7 +73,7 @@ struct ScanFwdCfg {
   static_assert(kThreads % 32 == 0, "whole warps");
 };
 
-template <typename T, int G, int NG, int kChan, int TT, bool kVec>
+template <typename T, int G, int NG, int kChan, int TT, bool kVec, int kPDsel = -1>
 __global__ void __launch_bounds__(kChan * NG, G <= 4 ? 512 / (kChan * NG) : 1)
 scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
@@ -228,10 +228,13 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
       const float* dtr = dts + chl * RS;
       const float* dur = dtus + chl * RS;
       float* yr = ys + chl * RS;
-      // software pipeline: the decays exp2(dt*A) of timestep t + kPD are issued before the FMA work of
-      // timestep t, so MUFU latency never sits on the recurrence's critical path
-      constexpr int kPD = G >= 16 ? 1 : (G >= 8 ? 2 : 4);
-      float2 er[kPD][G / 2];
+      // optional software pipeline (kPD > 0): the decays exp2(dt*A) of timestep t + kPD are issued before
+      // the FMA work of timestep t.  Measured on B200 at G = 4 it loses to plain 2x unrolling (kPD = 0:
+      // 1.85 ms vs 1.99 ms at the C4 shape) -- the kernel is bound by shared-memory wavefronts, not by
+      // MUFU latency -- so the G = 4 configuration runs with kPD = 0.
+      constexpr int kPD = kPDsel >= 0 ? kPDsel : (G >= 16 ? 1 : (G >= 8 ? 2 : 4));
+      constexpr int kPDn = kPD > 0 ? kPD : 1;
+      float2 er[kPDn][G / 2];
       float4 dcur = lds128(dtr);
       {
         const float dtv[4] = {dcur.x, dcur.y, dcur.z, dcur.w};
@@ -240,7 +243,7 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
 #pragma unroll
           for (int q = 0; q < G / 2; ++q) er[j][q] = ex2f2(fmul2(dup2(dtv[j]), A2[q]));
       }
-#pragma unroll 1
+#pragma unroll(kPD == 0 ? 2 : 1)
       for (int t4 = 0; t4 < TT; t4 += 4) {
         // checkpoint: state at the start of every MTTS_SCAN_CHUNK timesteps (what the backward restarts from)
         if (p.checkpoints && ((t0 + t4) % MTTS_SCAN_CHUNK) == 0 && t0 + t4 < L && cvalid) {
@@ -271,8 +274,12 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
           float2 ec[G / 2];
 #pragma unroll
           for (int q = 0; q < G / 2; ++q) {
-            ec[q] = er[j % kPD][q];
-            er[j % kPD][q] = ex2f2(fmul2(dup2(dtv[j + kPD]), A2[q]));
+            if constexpr (kPD == 0) {
+              ec[q] = ex2f2(fmul2(dup2(dtv[j]), A2[q]));
+            } else {
+              ec[q] = er[j % kPDn][q];
+              er[j % kPDn][q] = ex2f2(fmul2(dup2(dtv[j + kPD]), A2[q]));
+            }
           }
           float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -354,12 +361,12 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   }
 }
 
-template <typename T, int G, int NG, int kChan, int TT, bool kVec>
+template <typename T, int G, int NG, int kChan, int TT, bool kVec, int kPDsel = -1>
 static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
   using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
   const size_t smem = sizeof(float) * Cfg::kSmemFloats;
-  auto kern = scan_fwd_kernel<T, G, NG, kChan, TT, kVec>;
+  auto kern = scan_fwd_kernel<T, G, NG, kChan, TT, kVec, kPDsel>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + kChan - 1) / kChan, p.batch);
@@ -375,7 +382,7 @@ static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t strea
   const int N = p.dstate;
   if (N <= 4) return launch_scan_fwd<T, 4, 1, 64, TT / 4, kVec>(p, stream);
   if (N <= 8) return launch_scan_fwd<T, 4, 2, 32, TT / 2, kVec>(p, stream);
-  if (N <= 16) return launch_scan_fwd<T, 4, 4, 16, TT, kVec>(p, stream);
+  if (N <= 16) return launch_scan_fwd<T, 4, 4, 16, TT, kVec, 0>(p, stream);
   if (N <= 32) return launch_scan_fwd<T, 8, 4, 16, TT, kVec>(p, stream);
   if (N <= 64) return launch_scan_fwd<T, 16, 4, 32, TT, kVec>(p, stream);
   if (N <= 128) return launch_scan_fwd<T, 16, 8, 16, TT, kVec>(p, stream);
