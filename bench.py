@@ -359,8 +359,8 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": round(kern[dom], 4),
                 "launches_per_step": len(hook[dom]) // args.steps,
                 "share_of_step": round(kern[dom] * (len(hook[dom]) / args.steps) / ms, 4),
-                "co_bound": "SIMT issue / MUFU.EX2 (16 per clk per SM): one exp per (b, d, t, n) state "
-                            "update; see DESIGN.md",
+                "co_bound": "shared-memory / shuffle data pipe (LSU wavefronts) and warp-level latency; MUFU.EX2 "
+                            "(16 per clk per SM) caps the scan at 36% of HBM peak for bf16 N=16; see DESIGN.md",
                 "state_updates_per_s": round(B * Di * T * N / kern[dom] * 1e3, -6),
                 "others": {k: {"ms_per_launch": round(v, 4), "GBs": round(alg[k] / v / 1e6, 1),
                                "frac": round(alg[k] / v / 1e6 / peak, 4),

@@ -16,7 +16,14 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__inst_executed_pipe_lsu.sum', 'sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__average_warp_latency_per_inst_issued.ratio', 'smsp__warps_eligible.avg.per_cycle_active',
-        'smsp__cycles_elapsed.avg.per_second']
+        'smsp__cycles_elapsed.avg.per_second',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.per_cycle_active', 'smsp__inst_executed.sum']
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
