@@ -366,6 +366,30 @@ typedef struct {
 } mtts_gemm_bf16_params;
 int mtts_gemm_bf16(const mtts_gemm_bf16_params* p, mtts_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * FFN / projection glue (mamba_decoder.py:39-43,86-88: Linear -> GELU -> Linear, and the bias gradients
+ * of every biased Linear on the path).  Row-major (rows, cols) tensors of the io dtype with leading
+ * dimension ld (elements); cols, ld multiples of the 16-byte vector (8 bf16 / 4 fp32).
+ *   bias_gelu_fwd: out = gelu(x + bias)                       exact erf GELU; bias (cols) fp32 or NULL
+ *   bias_gelu_bwd: out = dout * gelu'(x + bias);  colsum[c] += sum_r out[r, c]   (colsum fp32, ACCUMULATED)
+ *   colsum:        colsum[c] += sum_r x[r, c]                  (dout, out, bias ignored)
+ * Replace aten::gelu / gelu_backward / sum(0) [upstream: nn.GELU, nn.Linear's bias gradient].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t rows, cols;
+  int32_t io_dtype;
+  int32_t reserved;
+  int64_t ld;
+  const void* x;
+  const float* bias;
+  const void* dout;
+  void* out;
+  float* colsum;
+} mtts_bias_gelu_params;
+int mtts_bias_gelu_fwd(const mtts_bias_gelu_params* p, mtts_stream_t stream);
+int mtts_bias_gelu_bwd(const mtts_bias_gelu_params* p, mtts_stream_t stream);
+int mtts_colsum(const mtts_bias_gelu_params* p, mtts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,11 +109,14 @@ SkinnyLinearParams = _struct("SkinnyLinearParams", """
 GemmBf16Params = _struct("GemmBf16Params", """
     i:m i:n i:k i:gelu p:a l:lda p:w l:ldw p:bias p:out l:ldo p:pre_out""")
 
+BiasGeluParams = _struct("BiasGeluParams", """
+    i:rows i:cols i:io_dtype i:reserved l:ld p:x p:bias p:dout p:out p:colsum""")
+
 # declaration order of the header == argument of mtts_sizeof_params
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
-                 GemmBf16Params]
+                 GemmBf16Params, BiasGeluParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -133,6 +136,9 @@ ENTRY_POINTS = {
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,
     "mtts_gemm_bf16": GemmBf16Params,
+    "mtts_bias_gelu_fwd": BiasGeluParams,
+    "mtts_bias_gelu_bwd": BiasGeluParams,
+    "mtts_colsum": BiasGeluParams,
 }
 
 _lib = None

@@ -36,6 +36,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 9: return (int)sizeof(mtts_add_layernorm_bwd_params);
     case 10: return (int)sizeof(mtts_skinny_linear_params);
     case 11: return (int)sizeof(mtts_gemm_bf16_params);
+    case 12: return (int)sizeof(mtts_bias_gelu_params);
     default: return -1;
   }
 }

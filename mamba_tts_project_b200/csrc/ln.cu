@@ -99,9 +99,17 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
 //            accumulated into `colsum` (batch, 3, dim)); S3 is the gradient of delta's bias; the host finishes dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b,
 //            dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b  on (batch, dim)-sized tensors.
 template <typename T, int kG>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, kG <= 4 ? 5 : 2)
 add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_per_warp) {
-  __shared__ float red[kLnWarps][3][kG * 128];
+  // Column statistics live in shared memory (one private row set per warp, each lane owns its columns, so
+  // plain load/add/store): keeping them in registers cost 48 registers per thread and with them half the
+  // resident warps -- the kernel is bound by bytes in flight, not by LSU slots.
+  __shared__ __align__(16) float red[kLnWarps][3][kG * 128];
+  // ln_weight * gamma_b: shared for dim <= 512 (frees 16 registers per thread), per-lane registers above
+  // (the 48 KB static limit is taken by `red` there)
+  constexpr bool kWsm = kG <= 4;
+  __shared__ __align__(16) float wsm[kWsm ? kG * 128 : 4];
+  float wreg[kWsm ? 1 : kG][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dm = p.dim;
   // a CTA never straddles two batch elements: grid.x tiles rows_per_batch, grid.y = batch
@@ -110,25 +118,32 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
   const int r_end = min(p.rows_per_batch, r_begin + rows_per_warp);
   const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
 
-  float w[kG][4], s1[kG][4], s2[kG][4], s3[kG][4];
 #pragma unroll
   for (int g = 0; g < kG; ++g) {
     const int e = (g * 32 + lane) * 4;
-    if (e < Dm) {
-      load4<float>(p.ln_weight + e, w[g]);
-      if (gam) {
-        float gm[4];
-        load4<float>(gam + e, gm);
+    if (warp == 0 || !kWsm) {
+      float wv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (e < Dm) {
+        load4<float>(p.ln_weight + e, wv);
+        if (gam) {
+          float gm[4];
+          load4<float>(gam + e, gm);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[g][j] *= gm[j];
+          for (int j = 0; j < 4; ++j) wv[j] *= gm[j];
+        }
       }
-    } else {
+      if constexpr (kWsm) {
+        *reinterpret_cast<float4*>(&wsm[e]) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[g][j] = 0.f;
+        for (int j = 0; j < 4; ++j) wreg[g][j] = wv[j];
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) s1[g][j] = s2[g][j] = s3[g][j] = 0.f;
+    for (int k = 0; k < 3; ++k)
+      *reinterpret_cast<float4*>(&red[warp][k][e]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  __syncthreads();
 
   for (int r = r_begin; r < r_end; ++r) {
     const int64_t row = (int64_t)bidx * p.rows_per_batch + r;
@@ -155,15 +170,29 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
         float xv[4], dv[4];
         load4<float>(xo + e, xv);
         load4<T>(go + e, dv);
+        float4 c1 = *reinterpret_cast<const float4*>(&red[warp][0][e]);
+        float4 c2 = *reinterpret_cast<const float4*>(&red[warp][1][e]);
+        float* c1v = reinterpret_cast<float*>(&c1);
+        float* c2v = reinterpret_cast<float*>(&c2);
+        float wv[4];
+        if constexpr (kWsm) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&wsm[e]);
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wv[j] = wreg[g][j];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           xh[g][j] = (xv[j] - mean) * rstd;
-          s1[g][j] = fmaf(dv[j], xh[g][j], s1[g][j]);
-          s2[g][j] += dv[j];
-          gg[g][j] = dv[j] * w[g][j];
+          c1v[j] = fmaf(dv[j], xh[g][j], c1v[j]);
+          c2v[j] += dv[j];
+          gg[g][j] = dv[j] * wv[j];
           a += gg[g][j];
           bsum = fmaf(gg[g][j], xh[g][j], bsum);
         }
+        *reinterpret_cast<float4*>(&red[warp][0][e]) = c1;
+        *reinterpret_cast<float4*>(&red[warp][1][e]) = c2;
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) xh[g][j] = gg[g][j] = 0.f;
@@ -178,24 +207,16 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
         float dx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) dx[j] = rstd * (gg[g][j] - a - xh[g][j] * bsum) + up[g][j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) s3[g][j] += dx[j];
+        float4 c3 = *reinterpret_cast<const float4*>(&red[warp][2][e]);
+        c3.x += dx[0]; c3.y += dx[1]; c3.z += dx[2]; c3.w += dx[3];
+        *reinterpret_cast<float4*>(&red[warp][2][e]) = c3;
         store4<float>(p.dx + row * Dm + e, dx);
         if (p.ddelta) store4<T>(reinterpret_cast<T*>(p.ddelta) + row * Dm + e, dx);
       }
     }
   }
 
-  // column sums: warps -> CTA (smem) -> one RED per column per CTA
-#pragma unroll
-  for (int g = 0; g < kG; ++g) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      red[warp][0][(g * 32 + lane) * 4 + j] = s1[g][j];
-      red[warp][1][(g * 32 + lane) * 4 + j] = s2[g][j];
-      red[warp][2][(g * 32 + lane) * 4 + j] = s3[g][j];
-    }
-  }
+  // column sums: warps -> CTA -> one RED per column per CTA
   __syncthreads();
   for (int idx = threadIdx.x; idx < 3 * Dm; idx += kLnWarps * 32) {
     const int which = idx / Dm, e = idx - which * Dm;

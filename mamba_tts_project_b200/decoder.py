@@ -71,7 +71,7 @@ class CrossAttention(nn.Module):
         residual-add + LayerNorm launch together with its gradient)."""
         B, T, E = query.shape
         H, dh = self.num_heads, self.head_dim
-        q = F.linear(query, self.in_proj_weight[:E], self.in_proj_bias[:E])
+        q = ops.linear(query, self.in_proj_weight[:E], self.in_proj_bias[:E])
         k, v = self.project_kv(memory)
         q = q.view(B, T, H, dh).transpose(1, 2)
         k = k.view(B, -1, H, dh).transpose(1, 2)
@@ -118,7 +118,9 @@ class MambaTTSDecoderLayer(nn.Module):
         x, h = ops.add_layernorm(x, attn_out, self.norm_ff.weight, self.norm_ff.bias,
                                  self.norm_ff.eps, gamma=gamma, beta=beta, out_dtype=cdt,
                                  delta_bias=self.cross_attn.out_proj.bias)
-        f = F.linear(self.ff[1](self.ff[0](h)), self.ff[2].weight)   # ff[2].bias rides with delta
+        # ff[0].bias is added inside the GELU kernel (and its gradient is that kernel's column sum);
+        # ff[2].bias rides with delta into the next LayerNorm
+        f = F.linear(ops.bias_gelu(F.linear(h, self.ff[0].weight), self.ff[0].bias), self.ff[2].weight)
         return x, f, self.ff[2].bias, new_state
 
     def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):

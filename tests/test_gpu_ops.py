@@ -414,3 +414,47 @@ def test_gemm_bf16_tcgen05_vs_torch(shape, gelu):
     check("pre", pre, pre_ref, BF16_TOL)
     out3 = gemm_bf16(a.cuda().view(1, m, k), w.cuda(), None, gelu=False)
     check("no bias, 3-D input", out3[0], torch.nn.functional.linear(a.float(), w.float()), BF16_TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# FFN glue: bias + exact GELU forward / backward (+ bias gradient), column sums
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(3, 7, 64), (2, 300, 520), (1, 1, 8), (4, 1000, 2048)])
+def test_bias_gelu_and_colsum_vs_torch(shape, dtype):
+    from mamba_tts_project_b200 import bias_gelu, colsum
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape).to(dtype)
+    bias = torch.randn(shape[-1])
+    dout = torch.randn(*shape).to(dtype)
+    # reference: fp32 math on the same (rounded) inputs (mamba_decoder.py:39-43: Linear -> GELU)
+    xr = x.float().requires_grad_()
+    br = bias.clone().requires_grad_()
+    ref = torch.nn.functional.gelu(xr + br)
+    gx, gb = torch.autograd.grad(ref, [xr, br], dout.float())
+    xg = cuda(x).requires_grad_()
+    bg = cuda(bias).requires_grad_()
+    out = bias_gelu(xg, bg)
+    dx, db = torch.autograd.grad(out, [xg, bg], cuda(dout))
+    t = tol(dtype)
+    check("out", out, ref.detach(), t)
+    check("dx", dx, gx, t)
+    check("dbias", db, gb, t)
+    check("colsum", colsum(cuda(dout)), dout.float().reshape(-1, shape[-1]).sum(0), t)
+
+
+def test_linear_fn_matches_f_linear():
+    from mamba_tts_project_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(2, 50, 64, requires_grad=True)
+    w = torch.randn(3 * 64, 64, requires_grad=True)
+    b = torch.randn(3 * 64, requires_grad=True)
+    g = torch.randn(2, 50, 64)
+    ref = torch.nn.functional.linear(x, w[:64], b[:64])
+    rg = torch.autograd.grad(ref, [x, w, b], g)
+    xc, wc, bc = (cuda(t.detach()).requires_grad_() for t in (x, w, b))
+    out = ops.linear(xc, wc[:64], bc[:64])
+    gg = torch.autograd.grad(out, [xc, wc, bc], cuda(g))
+    check("out", out, ref.detach(), FP32_TOL)
+    for n, a, r in zip(("dx", "dw", "db"), gg, rg):
+        check(n, a, r, FP32_TOL)

@@ -18,5 +18,10 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     bench.train_step(model, inp)
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45,
-                                                           max_name_column_width=60, max_shapes_column_width=70))
+rows = [(e.key, e.self_device_time_total / 1e3, e.count, str(e.input_shapes)[:90])
+        for e in prof.key_averages(group_by_input_shape=True)
+        if e.self_device_time_total > 0 and (e.key.startswith("aten::") or e.key.startswith("_") or "Backward" in e.key)]
+tot = sum(r[1] for r in rows)
+print(f"ops with device time: {tot:.2f} ms")
+for k, t, n, sh in sorted(rows, key=lambda r: -r[1])[:110]:
+    print(f"{t:8.3f} ms x{n:<4d} {k:<40s} {sh}")
