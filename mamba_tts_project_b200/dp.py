@@ -7,8 +7,11 @@ NVLink; decode is shard-local with no collective".  One process per GPU, identic
 * ``shard_batch``     rank r takes samples [r*B/g, (r+1)*B/g) of every batch-leading tensor;
 * ``GradAllReducer``  buckets the parameters in reverse registration order (the order backward
   produces gradients), and as soon as the last gradient of a bucket has been accumulated it packs the
-  bucket and launches an asynchronous all-reduce -- communication overlaps the rest of backward.
-  ``finish()`` waits, averages and scatters the result back into ``.grad``.
+  bucket (ONE multi-tensor copy) and launches an asynchronous all-reduce (NCCL ``AVG``) --
+  communication overlaps the rest of backward.  ``finish()`` waits and re-points every ``.grad`` at its
+  slice of the reduced bucket: no scatter copies.  (The first version issued one copy per parameter each
+  way plus a ``div_``: ~720 extra launches per step made the 8-GPU step CPU-launch-bound, 50.7 ms vs
+  43.1 ms on one GPU.)
 
 Works with any ``torch.distributed`` backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
 """
@@ -63,6 +66,15 @@ class GradAllReducer:
                 self._bucket_of[p] = bi
         self._flat = [torch.empty(sum(p.numel() for p in b), dtype=b[0].dtype, device=b[0].device)
                       for b in self.buckets]
+        self._views = []           # per bucket: views of the flat buffer shaped like the parameters
+        for b, flat in zip(self.buckets, self._flat):
+            off, vs = 0, []
+            for p in b:
+                vs.append(flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            self._views.append(vs)
+        backend = dist.get_backend(group) if dist.is_initialized() else ""
+        self._avg_op = average and self.world > 1 and backend == "nccl"
         self._pending = [0] * len(self.buckets)
         self._work = [None] * len(self.buckets)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
@@ -83,18 +95,18 @@ class GradAllReducer:
 
     def _launch(self, bi):
         flat = self._flat[bi]
-        off = 0
-        for p in self.buckets[bi]:
-            n = p.numel()
-            g = p.grad
-            if g is None:
-                flat[off:off + n].zero_()
-            else:
-                flat[off:off + n].copy_(g.reshape(-1))
-            off += n
+        dst, src = [], []
+        for p, v in zip(self.buckets[bi], self._views[bi]):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():   # already a bucket view: nothing to pack
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
         if self.world > 1:
-            self._work[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group,
-                                             async_op=True)
+            op = dist.ReduceOp.AVG if self._avg_op else dist.ReduceOp.SUM
+            self._work[bi] = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
 
     def _on_grad(self, p):
         if self._paused:
@@ -105,21 +117,19 @@ class GradAllReducer:
             self._launch(bi)
 
     def finish(self):
-        """Wait for every bucket, write the (averaged) gradients back, re-arm for the next step."""
+        """Wait for every bucket, point every ``.grad`` at its (averaged) slice of the reduced bucket
+        and re-arm for the next step.  The ``.grad`` tensors alias the bucket until the next step's
+        gradients are packed (consume them -- optimizer step, clipping -- before the next backward)."""
         for bi, b in enumerate(self.buckets):
             if self._pending[bi] > 0:      # some parameter received no gradient this step
                 self._launch(bi)
             if self._work[bi] is not None:
                 self._work[bi].wait()
-            flat = self._flat[bi]
-            if self.average and self.world > 1:
-                flat.div_(self.world)
-            off = 0
-            for p in b:
-                n = p.numel()
+            if self.average and self.world > 1 and not self._avg_op:
+                self._flat[bi].div_(self.world)
+            for p, v in zip(b, self._views[bi]):
                 if p.grad is not None:
-                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+                    p.grad = v
         self.reset()
 
     def remove(self):
