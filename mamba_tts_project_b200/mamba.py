@@ -176,6 +176,15 @@ class Mamba(nn.Module):
         Bsz, T, _ = h.shape
         R, N, W = self.dt_rank, self.d_state, self.d_conv
         cdt = compute_dtype(h)
+        if state is None and self.in_proj.bias is None and self.out_proj.bias is None \
+                and self.conv1d.bias is not None and T > 0 and Bsz > 0 \
+                and cdt in (torch.float32, torch.bfloat16):
+            # the training hot path: the whole block body as one autograd node
+            out, new_conv, last = ops.mamba_block_fn(
+                h, self.in_proj.weight, self.conv1d.weight.squeeze(1), self.conv1d.bias,
+                self.x_proj.weight, self.dt_proj.weight, self.dt_proj.bias, self.A_log, self.D,
+                self.out_proj.weight, cdt)
+            return out, (new_conv, last)
         # channel-major projection: (2Di, D) @ (B, D, T) -> (B, 2Di, T), no transposing copy
         xz = _ChannelMajorLinear.apply(self.in_proj.weight, h.transpose(1, 2), cdt)
         if self.in_proj.bias is not None:

@@ -318,6 +318,142 @@ def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_wei
                     None if out_proj_bias is None else out_proj_bias.to(y.dtype))
 
 
+class _MambaBlockFn(torch.autograd.Function):
+    """The whole Mamba block body as ONE autograd node (upstream's ``MambaInnerFn``):
+    in_proj -> conv+SiLU -> x_proj -> dt_proj -> scan -> out_proj on a (B, T, D) input.
+
+    Why not the composition of the individual Functions: their backward hands autograd dx and dz as two
+    tensors (it then ``cat``s them for ``xz.chunk``), du and the x_proj input gradient as two tensors (it
+    then ``add_``s them), and every weight gets its own cast.  Here conv and scan backward write dx | dz
+    into the two halves of one (B, 2 Di, T) buffer, du is the accumulator of the x_proj GEMM, and nothing
+    is copied.  All activations stay channel-major (B, C, T)."""
+
+    @staticmethod
+    def forward(ctx, h, in_w, conv_w, conv_b, xproj_w, dtproj_w, dt_bias, A_log, D, out_w, dtype):
+        _lib.require_cuda(h, in_w, conv_w, xproj_w, dtproj_w, A_log, out_w)
+        Bsz, T, Dm = h.shape
+        Di, W = conv_w.shape
+        R = dtproj_w.shape[1]
+        N = A_log.shape[1]
+        dev = h.device
+        hc = h if h.dtype == dtype else h.to(dtype)
+        Wi, Wx, Wdt, Wo = (w.detach().to(dtype) for w in (in_w, xproj_w, dtproj_w, out_w))
+        cw32, cb32 = _f32c(conv_w), _f32c(conv_b)
+        A = -torch.exp(A_log.detach().float())
+        D32, db32 = _f32c(D), _f32c(dt_bias)
+        io = _lib.io_dtype(hc)
+        with torch.autocast("cuda", enabled=False):
+            xz = torch.bmm(Wi.unsqueeze(0).expand(Bsz, -1, -1), hc.transpose(1, 2))     # (B, 2Di, T)
+            x, z = xz[:, :Di], xz[:, Di:]
+            xc = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
+            _lib.call("mtts_causal_conv1d_fwd", _lib.Conv1dFwdParams(
+                batch=Bsz, dim=Di, seqlen=T, width=W, io_dtype=io, silu=1, x=ptr(x),
+                x_batch_stride=x.stride(0), x_dim_stride=x.stride(1), weight=ptr(cw32), bias=ptr(cb32),
+                initial_states=None, init_batch_stride=0, init_dim_stride=0, out=ptr(xc),
+                out_batch_stride=xc.stride(0), out_dim_stride=xc.stride(1)))
+            x_dbl = torch.bmm(Wx.unsqueeze(0).expand(Bsz, -1, -1), xc)                   # (B, R+2N, T)
+            delta = torch.bmm(Wdt.unsqueeze(0).expand(Bsz, -1, -1), x_dbl[:, :R])        # (B, Di, T)
+            Bm, Cm = x_dbl[:, R:R + N], x_dbl[:, R + N:]
+            y = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
+            last = torch.empty((Bsz, Di, N), dtype=torch.float32, device=dev)
+            chk = torch.empty((Bsz, Di, max(scan_num_chunks(T), 1), N), dtype=torch.float32, device=dev)
+            _lib.call("mtts_selective_scan_fwd", _lib.ScanFwdParams(
+                batch=Bsz, dim=Di, seqlen=T, dstate=N, io_dtype=io, delta_softplus=1,
+                u=ptr(xc), u_batch_stride=xc.stride(0), u_dim_stride=xc.stride(1),
+                delta=ptr(delta), delta_batch_stride=delta.stride(0), delta_dim_stride=delta.stride(1),
+                A=ptr(A), B=ptr(Bm), B_batch_stride=Bm.stride(0), B_state_stride=Bm.stride(1),
+                C=ptr(Cm), C_batch_stride=Cm.stride(0), C_state_stride=Cm.stride(1),
+                D=ptr(D32), delta_bias=ptr(db32), z=ptr(z), z_batch_stride=z.stride(0),
+                z_dim_stride=z.stride(1), initial_state=None, out=ptr(y),
+                out_batch_stride=y.stride(0), out_dim_stride=y.stride(1), last_state=ptr(last),
+                checkpoints=ptr(chk)))
+            out = torch.bmm(y.transpose(1, 2), Wo.t().unsqueeze(0).expand(Bsz, -1, -1))  # (B, T, D)
+            new_conv = F.pad(x[..., -W:], (max(0, W - T), 0)) if T < W else x[..., -W:].clone()
+        ctx.save_for_backward(hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo)
+        ctx.meta = (h.dtype, tuple(t.dtype for t in (in_w, conv_w, conv_b, xproj_w, dtproj_w, dt_bias,
+                                                      A_log, D, out_w)))
+        ctx.mark_non_differentiable(new_conv, last)
+        return out, new_conv, last
+
+    @staticmethod
+    def backward(ctx, dout, _dconv, _dlast):
+        hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo = ctx.saved_tensors
+        t_h, (t_in, t_cw, t_cb, t_xw, t_dtw, t_dtb, t_A, t_D, t_ow) = ctx.meta
+        Bsz, T, Dm = hc.shape
+        Di, W = cw32.shape
+        R = Wdt.shape[1]
+        N = A.shape[1]
+        dev, dtype = hc.device, hc.dtype
+        io = _lib.io_dtype(hc)
+        dout = dout.to(dtype)
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        f32 = torch.float32
+        with torch.autocast("cuda", enabled=False):
+            doutT = dout.transpose(1, 2)                                                  # (B, D, T)
+            dy = torch.bmm(Wo.t().unsqueeze(0).expand(Bsz, -1, -1), doutT)                 # (B, Di, T)
+            dWo = torch.bmm(doutT, y.transpose(1, 2)).sum(0)                               # (D, Di)
+            dxz = torch.empty_like(xz)
+            dxh, dzh = dxz[:, :Di], dxz[:, Di:]
+            x, z = xz[:, :Di], xz[:, Di:]
+            Bm, Cm = x_dbl[:, R:R + N], x_dbl[:, R + N:]
+            du = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
+            ddelta = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
+            dA = torch.zeros((Di, N), dtype=f32, device=dev)
+            dBC = torch.zeros((2, Bsz, N, T), dtype=f32, device=dev)
+            dD = torch.zeros(Di, dtype=f32, device=dev)
+            ddb = torch.zeros(Di, dtype=f32, device=dev)
+            _lib.call("mtts_selective_scan_bwd", _lib.ScanBwdParams(
+                batch=Bsz, dim=Di, seqlen=T, dstate=N, io_dtype=io, delta_softplus=1,
+                u=ptr(xc), u_batch_stride=xc.stride(0), u_dim_stride=xc.stride(1),
+                delta=ptr(delta), delta_batch_stride=delta.stride(0), delta_dim_stride=delta.stride(1),
+                A=ptr(A), B=ptr(Bm), B_batch_stride=Bm.stride(0), B_state_stride=Bm.stride(1),
+                C=ptr(Cm), C_batch_stride=Cm.stride(0), C_state_stride=Cm.stride(1),
+                D=ptr(D32), delta_bias=ptr(db32), z=ptr(z), z_batch_stride=z.stride(0),
+                z_dim_stride=z.stride(1), dout=ptr(dy), dout_batch_stride=dy.stride(0),
+                dout_dim_stride=dy.stride(1), checkpoints=ptr(chk),
+                du=ptr(du), du_batch_stride=du.stride(0), du_dim_stride=du.stride(1),
+                ddelta=ptr(ddelta), ddelta_batch_stride=ddelta.stride(0),
+                ddelta_dim_stride=ddelta.stride(1),
+                dz=ptr(dzh), dz_batch_stride=dzh.stride(0), dz_dim_stride=dzh.stride(1),
+                dA=ptr(dA), dB=ptr(dBC[0]), dC=ptr(dBC[1]), dD=ptr(dD), ddelta_bias=ptr(ddb)))
+            # d x_dbl = [W_dt^T ddelta | dB | dC]  (B, R + 2N, T), small
+            dx_dbl = torch.empty((Bsz, R + 2 * N, T), dtype=dtype, device=dev)
+            dx_dbl[:, :R].copy_(torch.bmm(Wdt.t().unsqueeze(0).expand(Bsz, -1, -1), ddelta))
+            dx_dbl[:, R:R + N].copy_(dBC[0])
+            dx_dbl[:, R + N:].copy_(dBC[1])
+            dWdt = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)                  # (Di, R)
+            # d xc = du + W_x^T d x_dbl : du is the GEMM's accumulator
+            dxc = torch.baddbmm(du, Wx.t().unsqueeze(0).expand(Bsz, -1, -1), dx_dbl)
+            dWx = torch.bmm(dx_dbl, xc.transpose(1, 2)).sum(0)                             # (R+2N, Di)
+            dcw = torch.zeros_like(cw32)
+            dcb = torch.zeros(Di, dtype=f32, device=dev)
+            _lib.call("mtts_causal_conv1d_bwd", _lib.Conv1dBwdParams(
+                batch=Bsz, dim=Di, seqlen=T, width=W, io_dtype=io, silu=1, x=ptr(x),
+                x_batch_stride=x.stride(0), x_dim_stride=x.stride(1), weight=ptr(cw32), bias=ptr(cb32),
+                initial_states=None, init_batch_stride=0, init_dim_stride=0,
+                dout=ptr(dxc), dout_batch_stride=dxc.stride(0), dout_dim_stride=dxc.stride(1),
+                dx=ptr(dxh), dx_batch_stride=dxh.stride(0), dx_dim_stride=dxh.stride(1),
+                dweight=ptr(dcw), dbias=ptr(dcb)))
+            dh = torch.bmm(dxz.transpose(1, 2), Wi.unsqueeze(0).expand(Bsz, -1, -1))       # (B, T, D)
+            dWi = torch.bmm(dxz, hc).sum(0)                                                # (2Di, D)
+            dA_log = dA * A                                                                # A = -exp(A_log)
+        return (dh.to(t_h), dWi.to(t_in), dcw.to(t_cw), None if t_cb is None else dcb.to(t_cb),
+                dWx.to(t_xw), dWdt.to(t_dtw), ddb.to(t_dtb), dA_log.to(t_A), dD.to(t_D), dWo.to(t_ow),
+                None)
+
+
+def mamba_block_fn(h, in_proj_weight, conv_weight, conv_bias, x_proj_weight, dt_proj_weight, dt_bias,
+                   A_log, D, out_proj_weight, dtype=None):
+    """h (batch, T, d_model) -> (out (batch, T, d_model), conv_state (batch, d_inner, width),
+    ssm_state (batch, d_inner, dstate) fp32): the bias-free Mamba block from the zero state, as one
+    autograd node.  conv_weight (d_inner, width)."""
+    if dtype is None:
+        dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else h.dtype
+    return _MambaBlockFn.apply(h, in_proj_weight, conv_weight, conv_bias, x_proj_weight, dt_proj_weight,
+                               dt_bias, A_log, D, out_proj_weight, dtype)
+
+
 # ------------------------------------------------------------------------------------------------
 # decode-step kernels (inference only)
 # ------------------------------------------------------------------------------------------------
