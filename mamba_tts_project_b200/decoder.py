@@ -62,7 +62,8 @@ class CrossAttention(nn.Module):
         w, b = self.in_proj_weight, self.in_proj_bias
         if dtype is not None:
             w, b, memory = w.to(dtype), b.to(dtype), memory.to(dtype)
-        kv = F.linear(memory, w[E:], b[E:])     # one GEMM for both projections
+        kv = ops.linear(memory, w[E:], b[E:]) if dtype is None else F.linear(memory, w[E:], b[E:])
+        # (one GEMM for both projections; the bias gradient is a streaming column sum)
         return kv[..., :E], kv[..., E:]
 
     def forward(self, query, memory, key_padding_mask=None, add_out_bias=True):

@@ -424,7 +424,7 @@ class _MambaBlockFn(torch.autograd.Function):
             dx_dbl[:, R + N:].copy_(dBC[1])
             dWdt = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)                  # (Di, R)
             # d xc = du + W_x^T d x_dbl : du is the GEMM's accumulator
-            dxc = torch.baddbmm(du, Wx.t().unsqueeze(0).expand(Bsz, -1, -1), dx_dbl)
+            dxc = du.baddbmm_(Wx.t().unsqueeze(0).expand(Bsz, -1, -1), dx_dbl)
             dWx = torch.bmm(dx_dbl, xc.transpose(1, 2)).sum(0)                             # (R+2N, Di)
             dcw = torch.zeros_like(cw32)
             dcb = torch.zeros(Di, dtype=f32, device=dev)
