@@ -154,6 +154,37 @@ inline bool vec_ok(const void* p, int64_t s0, int64_t s1, int seqlen) {
   return p == nullptr || (aligned16(p) && s0 % VE == 0 && s1 % VE == 0 && seqlen % VE == 0);
 }
 
+// Sum 4 per-timestep scalars over the NG slice lanes of a channel (lane bits [0, log2 NG)) and store
+// them to row[0..3].  The last two lane bits are folded with a transposing butterfly.
+template <int NG>
+__device__ __forceinline__ void slice_reduce_store(float (&v)[4], int g, float* row) {
+#pragma unroll
+  for (int o = NG / 2; o >= 4; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+  }
+  if constexpr (NG == 1) {
+    *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (NG == 2) {
+    const bool hi = g & 1;
+    const float s0 = hi ? v[0] : v[2], s1 = hi ? v[1] : v[3];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    const float r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const float k0 = (hi ? v[2] : v[0]) + r0, k1 = (hi ? v[3] : v[1]) + r1;
+    *reinterpret_cast<float2*>(row + (hi ? 2 : 0)) = make_float2(k0, k1);
+  } else {
+    const bool b1 = g & 2, b0 = g & 1;
+    const float s0 = b1 ? v[0] : v[2], s1 = b1 ? v[1] : v[3];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+    const float r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float k0 = (b1 ? v[2] : v[0]) + r0, k1 = (b1 ? v[3] : v[1]) + r1;
+    const float s = b0 ? k0 : k1;
+    const float r = __shfl_xor_sync(0xffffffffu, s, 1);
+    const float tot = (b0 ? k1 : k0) + r;
+    if (g < 4) row[g & 3] = tot;  // NG > 4: every group of 4 lanes holds the totals, the first writes
+  }
+}
+
 // Which kernel family runs a scan.  The time-sequential kernels (scan_fwd.cu / scan_bwd.cu: one thread per
 // channel and 4-state slice) need batch x dim channels to fill the machine; long sequences over few
 // channels go to the time-parallel kernels (scan_*_wide.cu: lanes = timesteps).  MTTS_SCAN_IMPL=seq|wide

@@ -55,10 +55,12 @@ __device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, c
 
 }  // namespace
 
-template <typename T, int G, int NG, int kChan, int TT, bool kVec>
+// CC = channels per thread: every LDS of a B / C chunk then feeds CC recurrences (register tiling of
+// the shared operands -- the kernel is bound by shared-memory wavefronts).
+template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
 struct ScanFwdCfg {
   static constexpr int VE = Io<T>::kVecElems;
-  static constexpr int kThreads = kChan * NG;
+  static constexpr int kThreads = kChan / CC * NG;
   static constexpr int NP = G * NG;            // padded dstate
   static constexpr int kChunks = NP / 4;       // 16-byte chunks per B/C row
   static constexpr int kSwz = kChunks >= 4 ? 3 : kChunks - 1;
@@ -70,13 +72,13 @@ struct ScanFwdCfg {
   static constexpr int kBC = (kBCItems + kThreads - 1) / kThreads;
   static constexpr size_t kSmemFloats = 3 * (size_t)kChan * RS + 2 * (size_t)TT * NP;
   static_assert(G % 4 == 0 && (NG & (NG - 1)) == 0 && NG <= 32 && TT % VE == 0 && TT % 4 == 0, "cfg");
-  static_assert(kThreads % 32 == 0, "whole warps");
+  static_assert(kChan % CC == 0 && kThreads % 32 == 0, "whole warps");
 };
 
-template <typename T, int G, int NG, int kChan, int TT, bool kVec, int kPDsel = -1>
-__global__ void __launch_bounds__(kChan * NG, G <= 4 ? 512 / (kChan * NG) : 1)
+template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
+__global__ void __launch_bounds__(kChan / CC * NG, (G <= 4 && CC == 1) ? 512 / (kChan * NG) : 1)
 scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
-  using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
+  using Cfg = ScanFwdCfg<T, G, NG, CC, kChan, TT, kVec>;
   constexpr int VE = Cfg::VE, kThreads = Cfg::kThreads, NP = Cfg::NP, RS = Cfg::RS;
   constexpr int kIt = Cfg::kIt, kBC = Cfg::kBC, kVecPerRow = Cfg::kVecPerRow;
   constexpr int Q = G / 4;
@@ -91,23 +93,24 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   const int N = p.dstate, L = p.seqlen;
   const int b = blockIdx.y, c0 = blockIdx.x * kChan;
   const int tid = threadIdx.x;
-  const int chl = tid / NG, g = tid % NG;
+  const int chl = tid / NG * CC, g = tid % NG;   // first of this thread's CC channels
   const int c = c0 + chl;
-  const bool cvalid = c < p.dim;
-  const int64_t bc = (int64_t)b * p.dim + c;
 
   // ---- per-thread constants: A*log2(e) and the running state of the G rows of this slice ----------
-  float2 A2[G / 2], h[G / 2];
+  float2 A2[CC][G / 2], h[CC][G / 2];
 #pragma unroll
-  for (int i = 0; i < G; ++i) {
-    const int n = g * G + i;
-    float a = 0.f, hv = 0.f;
-    if (cvalid && n < N) {
-      a = p.A[(int64_t)c * N + n] * kLog2e;
-      if (p.initial_state) hv = p.initial_state[bc * N + n];
+  for (int k = 0; k < CC; ++k) {
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int n = g * G + i;
+      float a = 0.f, hv = 0.f;
+      if (c + k < p.dim && n < N) {
+        a = p.A[(int64_t)(c + k) * N + n] * kLog2e;
+        if (p.initial_state) hv = p.initial_state[((int64_t)b * p.dim + c + k) * N + n];
+      }
+      reinterpret_cast<float*>(A2[k])[i] = a;
+      reinterpret_cast<float*>(h[k])[i] = hv;
     }
-    reinterpret_cast<float*>(A2)[i] = a;
-    reinterpret_cast<float*>(h)[i] = hv;
   }
 
   // ---- P/E item bookkeeping: item = (channel row, 16-byte vector) -----------------------------------
@@ -224,105 +227,73 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
     if (tile + 1 < ntiles) prefetch(t0 + TT);
 
     // ---- M: the recurrence -------------------------------------------------------------------------
+    // (issuing the exps a group ahead was measured and lost to plain unrolling: the kernel is bound by
+    //  shared-memory wavefronts, not by MUFU latency)
     {
       const float* dtr = dts + chl * RS;
       const float* dur = dtus + chl * RS;
       float* yr = ys + chl * RS;
-      // optional software pipeline (kPD > 0): the decays exp2(dt*A) of timestep t + kPD are issued before
-      // the FMA work of timestep t.  Measured on B200 at G = 4 it loses to plain 2x unrolling (kPD = 0:
-      // 1.85 ms vs 1.99 ms at the C4 shape) -- the kernel is bound by shared-memory wavefronts, not by
-      // MUFU latency -- so the G = 4 configuration runs with kPD = 0.
-      constexpr int kPD = kPDsel >= 0 ? kPDsel : (G >= 16 ? 1 : (G >= 8 ? 2 : 4));
-      constexpr int kPDn = kPD > 0 ? kPD : 1;
-      float2 er[kPDn][G / 2];
-      float4 dcur = lds128(dtr);
-      {
-        const float dtv[4] = {dcur.x, dcur.y, dcur.z, dcur.w};
-#pragma unroll
-        for (int j = 0; j < kPD; ++j)
-#pragma unroll
-          for (int q = 0; q < G / 2; ++q) er[j][q] = ex2f2(fmul2(dup2(dtv[j]), A2[q]));
-      }
-#pragma unroll(kPD == 0 ? 2 : 1)
+#pragma unroll(G * CC <= 8 ? 2 : 1)
       for (int t4 = 0; t4 < TT; t4 += 4) {
         // checkpoint: state at the start of every MTTS_SCAN_CHUNK timesteps (what the backward restarts from)
-        if (p.checkpoints && ((t0 + t4) % MTTS_SCAN_CHUNK) == 0 && t0 + t4 < L && cvalid) {
-          float* ck = p.checkpoints + (bc * nchunks + (t0 + t4) / MTTS_SCAN_CHUNK) * N + g * G;
-          if ((N & 3) == 0) {
+        if (p.checkpoints && ((t0 + t4) % MTTS_SCAN_CHUNK) == 0 && t0 + t4 < L) {
 #pragma unroll
-            for (int i = 0; i < G; i += 4)
-              if (g * G + i < N)
-                *reinterpret_cast<float4*>(ck + i) = make_float4(h[i / 2].x, h[i / 2].y, h[i / 2 + 1].x, h[i / 2 + 1].y);
-          } else {
+          for (int k = 0; k < CC; ++k) {
+            if (c + k < p.dim) {
+              float* ck = p.checkpoints +
+                          ((((int64_t)b * p.dim + c + k) * nchunks) + (t0 + t4) / MTTS_SCAN_CHUNK) * N + g * G;
+              if ((N & 3) == 0) {
 #pragma unroll
-            for (int i = 0; i < G; ++i)
-              if (g * G + i < N) ck[i] = reinterpret_cast<const float*>(h)[i];
+                for (int i = 0; i < G; i += 4)
+                  if (g * G + i < N)
+                    *reinterpret_cast<float4*>(ck + i) =
+                        make_float4(h[k][i / 2].x, h[k][i / 2].y, h[k][i / 2 + 1].x, h[k][i / 2 + 1].y);
+              } else {
+#pragma unroll
+                for (int i = 0; i < G; ++i)
+                  if (g * G + i < N) ck[i] = reinterpret_cast<const float*>(h[k])[i];
+              }
+            }
           }
         }
-        const float4 dnext = lds128(dtr + t4 + 4);  // the row pad makes the last read harmless
-        const float4 x4 = lds128(dur + t4);
-        const float dtv[8] = {dcur.x, dcur.y, dcur.z, dcur.w, dnext.x, dnext.y, dnext.z, dnext.w};
-        const float duv[4] = {x4.x, x4.y, x4.z, x4.w};
-        dcur = dnext;
+        float dtv[CC][4], duv[CC][4], yp[CC][4];
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          const float4 d4 = lds128(dtr + k * RS + t4);
+          const float4 x4 = lds128(dur + k * RS + t4);
+          dtv[k][0] = d4.x; dtv[k][1] = d4.y; dtv[k][2] = d4.z; dtv[k][3] = d4.w;
+          duv[k][0] = x4.x; duv[k][1] = x4.y; duv[k][2] = x4.z; duv[k][3] = x4.w;
+        }
         const int swz = (t4 >> 3) & Cfg::kSwz;
-        float yp[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float* Bt = Bs + (t4 + j) * NP;
           const float* Ct = Cs + (t4 + j) * NP;
-          const float2 du2 = dup2(duv[j]);
-          float2 ec[G / 2];
+          float2 acc[CC];
 #pragma unroll
-          for (int q = 0; q < G / 2; ++q) {
-            if constexpr (kPD == 0) {
-              ec[q] = ex2f2(fmul2(dup2(dtv[j]), A2[q]));
-            } else {
-              ec[q] = er[j % kPDn][q];
-              er[j % kPDn][q] = ex2f2(fmul2(dup2(dtv[j + kPD]), A2[q]));
-            }
-          }
-          float2 acc = make_float2(0.f, 0.f);
+          for (int k = 0; k < CC; ++k) acc[k] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
             const int off = ((g * Q + q) ^ swz) << 2;
             const float4 Bv = lds128(Bt + off);
             const float4 Cv = lds128(Ct + off);
-            h[2 * q] = ffma2(ec[2 * q], h[2 * q], fmul2(du2, make_float2(Bv.x, Bv.y)));
-            h[2 * q + 1] = ffma2(ec[2 * q + 1], h[2 * q + 1], fmul2(du2, make_float2(Bv.z, Bv.w)));
-            acc = ffma2(h[2 * q], make_float2(Cv.x, Cv.y), acc);
-            acc = ffma2(h[2 * q + 1], make_float2(Cv.z, Cv.w), acc);
+#pragma unroll
+            for (int k = 0; k < CC; ++k) {
+              const float2 dt2 = dup2(dtv[k][j]), du2 = dup2(duv[k][j]);
+              const float2 e0 = ex2f2(fmul2(dt2, A2[k][2 * q]));
+              const float2 e1 = ex2f2(fmul2(dt2, A2[k][2 * q + 1]));
+              h[k][2 * q] = ffma2(e0, h[k][2 * q], fmul2(du2, make_float2(Bv.x, Bv.y)));
+              h[k][2 * q + 1] = ffma2(e1, h[k][2 * q + 1], fmul2(du2, make_float2(Bv.z, Bv.w)));
+              acc[k] = ffma2(h[k][2 * q], make_float2(Cv.x, Cv.y), acc[k]);
+              acc[k] = ffma2(h[k][2 * q + 1], make_float2(Cv.z, Cv.w), acc[k]);
+            }
           }
-          yp[j] = acc.x + acc.y;
-        }
-        // sum the partials over the NG lanes of this channel
 #pragma unroll
-        for (int o = NG / 2; o >= 4; o >>= 1) {
+          for (int k = 0; k < CC; ++k) yp[k][j] = acc[k].x + acc[k].y;
+        }
+        // sum the partials over the NG lanes of each channel
 #pragma unroll
-          for (int j = 0; j < 4; ++j) yp[j] += __shfl_xor_sync(0xffffffffu, yp[j], o);
-        }
-        if constexpr (NG == 1) {
-          *reinterpret_cast<float4*>(yr + t4) = make_float4(yp[0], yp[1], yp[2], yp[3]);
-        } else if constexpr (NG == 2) {
-          // lane bit0 = 0 ends with t4+0,1 ; bit0 = 1 with t4+2,3
-          const bool hi = g & 1;
-          const float s0 = hi ? yp[0] : yp[2], s1 = hi ? yp[1] : yp[3];
-          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1);
-          const float r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-          const float k0 = (hi ? yp[2] : yp[0]) + r0, k1 = (hi ? yp[3] : yp[1]) + r1;
-          *reinterpret_cast<float2*>(yr + t4 + (hi ? 2 : 0)) = make_float2(k0, k1);
-        } else {
-          // transposing butterfly over lane bits 1 and 0: lane (g & 3) ends with timestep t4 + (g & 3)
-          const bool b1 = g & 2, b0 = g & 1;
-          const float s0 = b1 ? yp[0] : yp[2], s1 = b1 ? yp[1] : yp[3];
-          const float r0 = __shfl_xor_sync(0xffffffffu, s0, 2);
-          const float r1 = __shfl_xor_sync(0xffffffffu, s1, 2);
-          const float k0 = (b1 ? yp[2] : yp[0]) + r0, k1 = (b1 ? yp[3] : yp[1]) + r1;
-          const float s = b0 ? k0 : k1;
-          const float r = __shfl_xor_sync(0xffffffffu, s, 1);
-          const float tot = (b0 ? k1 : k0) + r;
-          // for NG > 4 every group of 4 lanes holds the same totals; the first group writes
-          if (g < 4) yr[t4 + (g & 3)] = tot;
-        }
+        for (int k = 0; k < CC; ++k) slice_reduce_store<NG>(yp[k], g, yr + k * RS + t4);
       }
     }
     __syncthreads();
@@ -354,19 +325,25 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
     // above) and the next M writes ys only after the next P's barrier.
   }
 
-  if (p.last_state && cvalid) {
+  if (p.last_state) {
 #pragma unroll
-    for (int i = 0; i < G; ++i)
-      if (g * G + i < N) p.last_state[bc * N + g * G + i] = reinterpret_cast<const float*>(h)[i];
+    for (int k = 0; k < CC; ++k) {
+      if (c + k < p.dim) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+          if (g * G + i < N)
+            p.last_state[((int64_t)b * p.dim + c + k) * N + g * G + i] = reinterpret_cast<const float*>(h[k])[i];
+      }
+    }
   }
 }
 
-template <typename T, int G, int NG, int kChan, int TT, bool kVec, int kPDsel = -1>
+template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
 static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
-  using Cfg = ScanFwdCfg<T, G, NG, kChan, TT, kVec>;
+  using Cfg = ScanFwdCfg<T, G, NG, CC, kChan, TT, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
   const size_t smem = sizeof(float) * Cfg::kSmemFloats;
-  auto kern = scan_fwd_kernel<T, G, NG, kChan, TT, kVec, kPDsel>;
+  auto kern = scan_fwd_kernel<T, G, NG, CC, kChan, TT, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + kChan - 1) / kChan, p.batch);
@@ -380,13 +357,15 @@ template <typename T, bool kVec>
 static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t stream) {
   constexpr int TT = Io<T>::kVecElems * 8;  // 64 (bf16) / 32 (fp32)
   const int N = p.dstate;
-  if (N <= 4) return launch_scan_fwd<T, 4, 1, 64, TT / 4, kVec>(p, stream);
-  if (N <= 8) return launch_scan_fwd<T, 4, 2, 32, TT / 2, kVec>(p, stream);
-  if (N <= 16) return launch_scan_fwd<T, 4, 4, 16, TT, kVec, 0>(p, stream);
-  if (N <= 32) return launch_scan_fwd<T, 8, 4, 16, TT, kVec>(p, stream);
-  if (N <= 64) return launch_scan_fwd<T, 16, 4, 32, TT, kVec>(p, stream);
-  if (N <= 128) return launch_scan_fwd<T, 16, 8, 16, TT, kVec>(p, stream);
-  return launch_scan_fwd<T, 16, 16, 8, TT, kVec>(p, stream);
+  if (N <= 4) return launch_scan_fwd<T, 4, 1, 1, 64, TT / 4, kVec>(p, stream);
+  if (N <= 8) return launch_scan_fwd<T, 4, 2, 1, 32, TT / 2, kVec>(p, stream);
+  // CC = 2 (<T, 4, 4, 2, 16, TT / 2>) was measured at the C4 shape: 1.97 ms vs 1.87 ms for CC = 1 -- the
+  // halved LDS traffic is paid for with half the resident warps, as in the backward.
+  if (N <= 16) return launch_scan_fwd<T, 4, 4, 1, 16, TT, kVec>(p, stream);
+  if (N <= 32) return launch_scan_fwd<T, 8, 4, 1, 16, TT, kVec>(p, stream);
+  if (N <= 64) return launch_scan_fwd<T, 16, 4, 1, 32, TT, kVec>(p, stream);
+  if (N <= 128) return launch_scan_fwd<T, 16, 8, 1, 16, TT, kVec>(p, stream);
+  return launch_scan_fwd<T, 16, 16, 1, 8, TT, kVec>(p, stream);
 }
 
 template <typename T>
