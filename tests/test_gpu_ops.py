@@ -503,3 +503,80 @@ def test_linear_fn_matches_f_linear():
     check("out", out, ref.detach(), FP32_TOL)
     for n, a, r in zip(("dx", "dw", "db"), gg, rg):
         check(n, a, r, FP32_TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# Out-of-bounds writes: every output of the scan entry points sits between canary regions (the pool has no
+# compute-sanitizer; an off-by-one chunk index once wrote a checkpoint into the next channel's slot).
+# ------------------------------------------------------------------------------------------------
+_CANARY = 12345.678
+
+
+def _guarded(shape, dtype, pad=4096):
+    n = 1
+    for s in shape:
+        n *= s
+    buf = torch.full((n + 2 * pad,), _CANARY, dtype=dtype, device="cuda")
+    return buf, buf[pad:pad + n].view(*shape)
+
+
+def _canaries_intact(buf, n, pad=4096):
+    ref = torch.tensor(_CANARY, dtype=buf.dtype, device=buf.device)
+    return bool((buf[:pad] == ref).all() and (buf[pad + n:] == ref).all())
+
+
+@pytest.mark.parametrize("impl", ["seq", "wide"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 24, 300, 16), (1, 16, 1, 16), (1, 20, 257, 16), (1, 8, 200, 5),
+                                   (2, 16, 64, 16), (1, 40, 96, 64)],
+                         ids=lambda s: "b%dd%dt%dn%d" % s)
+def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatch):
+    from mamba_tts_project_b200 import _lib
+    monkeypatch.setenv("MTTS_SCAN_IMPL", impl)
+    Bz, Dm, T, N = shape
+    torch.manual_seed(T)
+    dev, f32 = "cuda", torch.float32
+    u = torch.randn(Bz, Dm, T, device=dev).to(dtype)
+    delta = (0.5 * torch.rand(Bz, Dm, T, device=dev)).to(dtype)
+    A = -0.5 * torch.rand(Dm, N, device=dev) - 1e-3
+    Bm = torch.randn(Bz, N, T, device=dev).to(dtype)
+    Cm = torch.randn(Bz, N, T, device=dev).to(dtype)
+    D = torch.randn(Dm, device=dev)
+    z = torch.randn(Bz, Dm, T, device=dev).to(dtype)
+    bias = 0.5 * torch.rand(Dm, device=dev)
+    dout = torch.randn(Bz, Dm, T, device=dev).to(dtype)
+    nch = (T + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
+    g = {}
+    for name, shp, dt in (("out", (Bz, Dm, T), dtype), ("last", (Bz, Dm, N), f32), ("chk", (Bz, Dm, nch, N), f32),
+                          ("du", (Bz, Dm, T), dtype), ("ddelta", (Bz, Dm, T), dtype), ("dz", (Bz, Dm, T), dtype),
+                          ("dA", (Dm, N), f32), ("dB", (Bz, N, T), f32), ("dC", (Bz, N, T), f32),
+                          ("dD", (Dm,), f32), ("ddb", (Dm,), f32)):
+        g[name] = _guarded(shp, dt)
+    for k in ("dA", "dB", "dC", "dD", "ddb"):
+        g[k][1].zero_()
+    P = _lib.ptr
+    io = _lib.io_dtype(u)
+    common = dict(batch=Bz, dim=Dm, seqlen=T, dstate=N, io_dtype=io, delta_softplus=1,
+                  u=P(u), u_batch_stride=u.stride(0), u_dim_stride=u.stride(1),
+                  delta=P(delta), delta_batch_stride=delta.stride(0), delta_dim_stride=delta.stride(1),
+                  A=P(A), B=P(Bm), B_batch_stride=Bm.stride(0), B_state_stride=Bm.stride(1),
+                  C=P(Cm), C_batch_stride=Cm.stride(0), C_state_stride=Cm.stride(1),
+                  D=P(D), delta_bias=P(bias), z=P(z), z_batch_stride=z.stride(0), z_dim_stride=z.stride(1))
+    out, last, chk = g["out"][1], g["last"][1], g["chk"][1]
+    _lib.call("mtts_selective_scan_fwd", _lib.ScanFwdParams(
+        **common, initial_state=None, out=P(out), out_batch_stride=out.stride(0),
+        out_dim_stride=out.stride(1), last_state=P(last), checkpoints=P(chk)))
+    du, dd, dz = g["du"][1], g["ddelta"][1], g["dz"][1]
+    _lib.call("mtts_selective_scan_bwd", _lib.ScanBwdParams(
+        **common, dout=P(dout), dout_batch_stride=dout.stride(0), dout_dim_stride=dout.stride(1),
+        checkpoints=P(chk), du=P(du), du_batch_stride=du.stride(0), du_dim_stride=du.stride(1),
+        ddelta=P(dd), ddelta_batch_stride=dd.stride(0), ddelta_dim_stride=dd.stride(1),
+        dz=P(dz), dz_batch_stride=dz.stride(0), dz_dim_stride=dz.stride(1),
+        dA=P(g["dA"][1]), dB=P(g["dB"][1]), dC=P(g["dC"][1]), dD=P(g["dD"][1]), ddelta_bias=P(g["ddb"][1])))
+    torch.cuda.synchronize()
+    for name, (buf, view) in g.items():
+        assert _canaries_intact(buf, view.numel()), f"{name}: write outside the tensor"
+        assert torch.isfinite(view.float()).all(), f"{name}: non-finite values"
+        if name not in ("dA", "dB", "dC", "dD", "ddb"):
+            assert not (view == torch.tensor(_CANARY, dtype=view.dtype, device=dev)).any(), \
+                f"{name}: elements left unwritten"
