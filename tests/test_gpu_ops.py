@@ -580,3 +580,29 @@ def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatc
         if name not in ("dA", "dB", "dC", "dD", "ddb"):
             assert not (view == torch.tensor(_CANARY, dtype=view.dtype, device=dev)).any(), \
                 f"{name}: elements left unwritten"
+
+
+def test_selective_scan_per_timestep_outputs_are_deterministic():
+    """out, du, ddelta, dz involve no atomics: two runs must agree bit for bit (a shared-memory race -- the
+    kernels reuse tile rows across phases -- would show up here; racecheck is not available on the pool)."""
+    from mamba_tts_project_b200 import selective_scan_fn
+    torch.manual_seed(7)
+    Bz, Dm, T, N = 4, 1024, 2048, 16
+    dev, bf = "cuda", torch.bfloat16
+    u = torch.randn(Bz, Dm, T, device=dev, dtype=bf).requires_grad_()
+    delta = (0.5 * torch.rand(Bz, Dm, T, device=dev)).to(bf).requires_grad_()
+    A = (-0.5 * torch.rand(Dm, N, device=dev) - 1e-3).requires_grad_()
+    Bm = torch.randn(Bz, N, T, device=dev, dtype=bf).requires_grad_()
+    Cm = torch.randn(Bz, N, T, device=dev, dtype=bf).requires_grad_()
+    D = torch.randn(Dm, device=dev).requires_grad_()
+    z = torch.randn(Bz, Dm, T, device=dev, dtype=bf).requires_grad_()
+    bias = (0.5 * torch.rand(Dm, device=dev)).requires_grad_()
+    dout = torch.randn(Bz, Dm, T, device=dev, dtype=bf)
+    runs = []
+    for _ in range(3):
+        out = selective_scan_fn(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias, delta_softplus=True)
+        du, dd, dz = torch.autograd.grad(out, [u, delta, z], dout)
+        runs.append((out.detach(), du, dd, dz))
+    for r in runs[1:]:
+        for name, a, b in zip(("out", "du", "ddelta", "dz"), runs[0], r):
+            assert torch.equal(a, b), f"{name} differs between runs"
