@@ -709,11 +709,16 @@ class _LinearFn(torch.autograd.Function):
         t_x, t_w, t_b = ctx.meta
         dy = dy.to(wc.dtype)
         dy2, x2 = _rows2d(dy), _rows2d(xc)
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        dx = dw = db = None
         with torch.autocast("cuda", enabled=False):
-            dx = (dy2 @ wc).view(xc.shape)
-            dw = dy2.t() @ x2
-        db = None if t_b is None else colsum(dy2).to(t_b)
-        return dx.to(t_x), dw.to(t_w), db, None
+            if need_x:   # e.g. text_hidden under the K/V projection needs none
+                dx = (dy2 @ wc).view(xc.shape).to(t_x)
+            if need_w:
+                dw = (dy2.t() @ x2).to(t_w)
+        if need_b and t_b is not None:
+            db = colsum(dy2).to(t_b)
+        return dx, dw, db, None
 
 
 def linear(x, weight, bias=None, dtype=None):
