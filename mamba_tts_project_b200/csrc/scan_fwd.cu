@@ -362,10 +362,12 @@ static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t strea
   // CC = 2 (<T, 4, 4, 2, 16, TT / 2>) was measured at the C4 shape: 1.97 ms vs 1.87 ms for CC = 1 -- the
   // halved LDS traffic is paid for with half the resident warps, as in the backward.
   if (N <= 16) return launch_scan_fwd<T, 4, 4, 1, 16, TT, kVec>(p, stream);
-  if (N <= 32) return launch_scan_fwd<T, 8, 4, 1, 16, TT, kVec>(p, stream);
-  if (N <= 64) return launch_scan_fwd<T, 16, 4, 1, 32, TT, kVec>(p, stream);
-  if (N <= 128) return launch_scan_fwd<T, 16, 8, 1, 16, TT, kVec>(p, stream);
-  return launch_scan_fwd<T, 16, 16, 1, 8, TT, kVec>(p, stream);
+  // wider states: still 4 rows per thread, more slices per channel (measured at N = 64, C4 shape: 4 x 16
+  // slices 7.9 ms, 8 x 8 10.5 ms, 16 x 4 9.1 ms -- registers, hence resident warps, decide)
+  if (N <= 32) return launch_scan_fwd<T, 4, 8, 1, 8, TT, kVec>(p, stream);
+  if (N <= 64) return launch_scan_fwd<T, 4, 16, 1, 8, TT, kVec>(p, stream);
+  if (N <= 128) return launch_scan_fwd<T, 4, 32, 1, 4, TT, kVec>(p, stream);
+  return launch_scan_fwd<T, 8, 32, 1, 4, TT, kVec>(p, stream);
 }
 
 template <typename T>

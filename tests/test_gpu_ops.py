@@ -95,7 +95,10 @@ SCAN_CASES = [
     (1, 16, 257, 16, {}),                     # chunk + 1, unaligned
     (2, 16, 512, 16, {}),
     (1, 16, 1100, 16, {"with_init": True}),
-    (1, 40, 520, 64, {}),                     # dstate > 16: staged in 4 row-chunks
+    (1, 40, 520, 64, {}),                     # dstate > 16: 16 slices per channel
+    (1, 12, 130, 32, {}),                     # 8 slices
+    (1, 12, 70, 128, {}),                     # 32 slices (a whole warp per channel)
+    (1, 8, 40, 200, {}),                      # 8 rows per thread, ragged dstate
     (1, 8, 200, 5, {"with_z": False}),        # odd dstate, no gate
     (2, 16, 128, 16, {"with_D": False, "with_bias": False}),
     (1, 4, 64, 16, {}),                       # fewer channels than one CTA group
