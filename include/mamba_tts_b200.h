@@ -150,6 +150,11 @@ typedef struct {
   int64_t out_batch_stride, out_dim_stride;
   float* last_state;  /* (batch, dim, dstate) contiguous or NULL */
   float* checkpoints; /* see above, or NULL */
+  /* optional: y = <C, h> + D u BEFORE the silu(z) gate, io dtype (batch, dim, seqlen).  Upstream saves the
+   * same tensor (`out`, next to `out_z`) for its backward; handing it to selective_scan_bwd spares the
+   * backward the <C, h> recompute it otherwise needs for dz. */
+  void* y_pre;
+  int64_t y_batch_stride, y_dim_stride;
 } mtts_scan_fwd_params;
 int mtts_selective_scan_fwd(const mtts_scan_fwd_params* p, mtts_stream_t stream);
 
@@ -187,6 +192,8 @@ typedef struct {
   float* dC;
   float* dD;          /* required iff D != NULL */
   float* ddelta_bias; /* required iff delta_bias != NULL */
+  const void* y_pre;  /* the forward's y_pre, or NULL (then y is recomputed) */
+  int64_t y_batch_stride, y_dim_stride;
 } mtts_scan_bwd_params;
 int mtts_selective_scan_bwd(const mtts_scan_bwd_params* p, mtts_stream_t stream);
 

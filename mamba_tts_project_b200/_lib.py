@@ -61,7 +61,8 @@ ScanFwdParams = _struct("ScanFwdParams", """
     p:z l:z_batch_stride l:z_dim_stride
     p:initial_state
     p:out l:out_batch_stride l:out_dim_stride
-    p:last_state p:checkpoints""")
+    p:last_state p:checkpoints
+    p:y_pre l:y_batch_stride l:y_dim_stride""")
 
 ScanBwdParams = _struct("ScanBwdParams", """
     i:batch i:dim i:seqlen i:dstate i:io_dtype i:delta_softplus
@@ -77,7 +78,8 @@ ScanBwdParams = _struct("ScanBwdParams", """
     p:du l:du_batch_stride l:du_dim_stride
     p:ddelta l:ddelta_batch_stride l:ddelta_dim_stride
     p:dz l:dz_batch_stride l:dz_dim_stride
-    p:dA p:dB p:dC p:dD p:ddelta_bias""")
+    p:dA p:dB p:dC p:dD p:ddelta_bias
+    p:y_pre l:y_batch_stride l:y_dim_stride""")
 
 StateUpdateParams = _struct("StateUpdateParams", """
     i:batch i:dim i:dstate i:io_dtype i:dt_softplus

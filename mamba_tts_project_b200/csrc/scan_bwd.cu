@@ -124,7 +124,8 @@ struct ScanBwdCfg {
                                         2 * kWarps * (size_t)kTT * NP + 7 * 4 * CC * (size_t)kThreads;
 };
 
-template <typename T, int NG, int CC, int kWarps, bool kVec>
+// kRecomputeY: dz needs y = <C, h> and the forward did not hand over its y_pre.
+template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY>
 __global__ void __launch_bounds__(32 * kWarps, (NG == 4 && CC == 1) ? 7 : 1)
 scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
@@ -345,6 +346,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
 
         // re-run the 4 steps, keeping decays and states
         float2 a[CC][4][2], hs[CC][4][2];
+        float4 Bkeep[4];  // B_t of the group: the reverse sweep needs it again
         {
           float2 hc[CC][2];
           float yp[CC][4];
@@ -357,7 +359,9 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 Bv = lds128(Bt + j * NP);
-            const float4 Cv = lds128(Ct + j * NP);
+            Bkeep[j] = Bv;
+            float4 Cv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (kRecomputeY) Cv = lds128(Ct + j * NP);
 #pragma unroll
             for (int k = 0; k < CC; ++k) {
               const float2 dt2 = dup2(dtv[k][j]), du2 = dup2(duv[k][j]);
@@ -367,19 +371,23 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
               hc[k][1] = ffma2(a[k][j][1], hc[k][1], fmul2(du2, hi2(Bv)));
               hs[k][j][0] = hc[k][0];
               hs[k][j][1] = hc[k][1];
-              const float2 acc = ffma2(hc[k][1], hi2(Cv), fmul2(hc[k][0], lo2(Cv)));
-              yp[k][j] = acc.x + acc.y;
+              if constexpr (kRecomputeY) {
+                const float2 acc = ffma2(hc[k][1], hi2(Cv), fmul2(hc[k][0], lo2(Cv)));
+                yp[k][j] = acc.x + acc.y;
+              }
             }
           }
+          if constexpr (kRecomputeY) {
 #pragma unroll
-          for (int k = 0; k < CC; ++k) slice_reduce_store<NG>(yp[k], g, yr + k * RS + 4 * s);
+            for (int k = 0; k < CC; ++k) slice_reduce_store<NG>(yp[k], g, yr + k * RS + 4 * s);
+          }
         }
 
         // reverse recurrence
         float dBv[16], dCv[16], sgb[CC][4], dda[CC][4];
 #pragma unroll
         for (int j = 3; j >= 0; --j) {
-          const float4 Bv = lds128(Bt + j * NP);
+          const float4 Bv = Bkeep[j];
           const float4 Cv = lds128(Ct + j * NP);
           float2 dB0, dB1, dC0, dC1;
 #pragma unroll
@@ -427,14 +435,16 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     // ---- E ----------------------------------------------------------------------------------------
     // this tile's raw inputs are read again (L2 hits) and the next tile's are requested now; both arrive
     // while the dB / dC tiles are flushed
-    uint4 eu[kIt], ed[kIt], eg[kIt], ez[kIt];
+    uint4 eu[kIt], ed[kIt], eg[kIt], ez[kIt], ey[kIt];
+    const T* yb = p.y_pre ? reinterpret_cast<const T*>(p.y_pre) + (int64_t)b * p.y_batch_stride : nullptr;
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       const int idx = tid + k * kThreads;
       const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
       const int cc = c0 + ich;
-      eu[k] = ed[k] = eg[k] = ez[k] = make_uint4(0u, 0u, 0u, 0u);
+      eu[k] = ed[k] = eg[k] = ez[k] = ey[k] = make_uint4(0u, 0u, 0u, 0u);
       if (idx < Cfg::kItems && cc < p.dim) {
+        if (!kRecomputeY && zb && yb) ey[k] = load_raw<T, kVec>(yb + (int64_t)cc * p.y_dim_stride, t0 + it, L);
         eu[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
         ed[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
         eg[k] = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
@@ -489,9 +499,12 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           const float4 q3 = lds128(das + ich * RS + it + i);
           dtv[i] = q0.x; dtv[i + 1] = q0.y; dtv[i + 2] = q0.z; dtv[i + 3] = q0.w;
           sgv[i] = q1.x; sgv[i + 1] = q1.y; sgv[i + 2] = q1.z; sgv[i + 3] = q1.w;
-          yv[i] = q2.x; yv[i + 1] = q2.y; yv[i + 2] = q2.z; yv[i + 3] = q2.w;
+          if constexpr (kRecomputeY) {
+            yv[i] = q2.x; yv[i + 1] = q2.y; yv[i + 2] = q2.z; yv[i + 3] = q2.w;
+          }
           dav[i] = q3.x; dav[i + 1] = q3.y; dav[i + 2] = q3.z; dav[i + 3] = q3.w;
         }
+        if constexpr (!kRecomputeY) Io<T>::unpack(ey[k], yv);  // the forward's y already holds D u
         float o_du[VE], o_dd[VE], o_dz[VE];
 #pragma unroll
         for (int i = 0; i < VE; ++i) {
@@ -499,7 +512,8 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           if (zb) {
             const float sig = sigmoid_f(zv[i]);
             gy *= zv[i] * sig;
-            o_dz[i] = gv[i] * fmaf(Dv, uv[i], yv[i]) * sig * fmaf(zv[i], 1.f - sig, 1.f);
+            const float yfull = kRecomputeY ? fmaf(Dv, uv[i], yv[i]) : yv[i];
+            o_dz[i] = gv[i] * yfull * sig * fmaf(zv[i], 1.f - sig, 1.f);
           }
           const float x = dv[i] + bias;
           const float sp = (p.delta_softplus && x <= 20.f) ? sigmoid_f(x) : 1.f;
@@ -548,17 +562,24 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   }
 }
 
-template <typename T, int NG, int CC, int kWarps, bool kVec>
-static int launch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
+template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY>
+static int launch_scan_bwd_y(const mtts_scan_bwd_params& p, cudaStream_t stream) {
   using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
   const size_t smem = sizeof(float) * Cfg::kSmemFloats;
-  auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec>;
+  auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec, kRecomputeY>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + Cfg::kChan - 1) / Cfg::kChan, p.batch);
   kern<<<grid, Cfg::kThreads, smem, stream>>>(p, nchunks);
   return launch_status();
+}
+
+template <typename T, int NG, int CC, int kWarps, bool kVec>
+static int launch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
+  // y is only needed for dz; with the forward's y_pre at hand the <C, h> recompute is skipped
+  if (p.z && !p.y_pre) return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, true>(p, stream);
+  return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, false>(p, stream);
 }
 
 template <typename T, bool kVec>
@@ -582,7 +603,8 @@ static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream)
                    vec_ok<T>(p.dout, p.dout_batch_stride, p.dout_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.du, p.du_batch_stride, p.du_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.ddelta, p.ddelta_batch_stride, p.ddelta_dim_stride, p.seqlen) &&
-                   vec_ok<T>(p.dz, p.dz_batch_stride, p.dz_dim_stride, p.seqlen);
+                   vec_ok<T>(p.dz, p.dz_batch_stride, p.dz_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.y_pre, p.y_batch_stride, p.y_dim_stride, p.seqlen);
   return vec ? dispatch_scan_bwd_n<T, true>(p, stream) : dispatch_scan_bwd_n<T, false>(p, stream);
 }
 

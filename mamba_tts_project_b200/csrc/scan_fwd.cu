@@ -312,6 +312,9 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
         }
 #pragma unroll
         for (int i = 0; i < VE; ++i) yv[i] = fmaf(it_D[k], uv[i], yv[i]);
+        if (p.y_pre)  // the backward's dz needs y before the gate
+          store_raw<T, kVec>(reinterpret_cast<T*>(p.y_pre) + (int64_t)b * p.y_batch_stride +
+                                 (int64_t)(c0 + it_ch[k]) * p.y_dim_stride, t0 + it_t[k], L, yv);
         if (zb) {
           float zv[VE];
           Io<T>::unpack(z_cur[k], zv);
@@ -378,7 +381,8 @@ static int dispatch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream)
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&
                    vec_ok<T>(p.C, p.C_batch_stride, p.C_state_stride, p.seqlen) &&
                    vec_ok<T>(p.z, p.z_batch_stride, p.z_dim_stride, p.seqlen) &&
-                   vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen);
+                   vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.y_pre, p.y_batch_stride, p.y_dim_stride, p.seqlen);
   return vec ? dispatch_scan_fwd_n<T, true>(p, stream) : dispatch_scan_fwd_n<T, false>(p, stream);
 }
 

@@ -144,6 +144,10 @@ scan_fwd_wide_kernel(const mtts_scan_fwd_params p, const int nchunks) {
       }
 
       if (cvalid) {
+        if (p.y_pre) {
+          T* yrow = reinterpret_cast<T*>(p.y_pre) + (int64_t)b * p.y_batch_stride + (int64_t)c * p.y_dim_stride;
+          store_items<T, kItems, kVec>(yrow, tl, L, y);
+        }
         if (p.z) {
           const T* zrow = reinterpret_cast<const T*>(p.z) + (int64_t)b * p.z_batch_stride +
                           (int64_t)c * p.z_dim_stride;
@@ -191,7 +195,8 @@ static int dispatch_scan_fwd_wide_t(const mtts_scan_fwd_params& p, cudaStream_t 
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&
                    vec_ok<T>(p.C, p.C_batch_stride, p.C_state_stride, p.seqlen) &&
                    vec_ok<T>(p.z, p.z_batch_stride, p.z_dim_stride, p.seqlen) &&
-                   vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen);
+                   vec_ok<T>(p.out, p.out_batch_stride, p.out_dim_stride, p.seqlen) &&
+                   vec_ok<T>(p.y_pre, p.y_batch_stride, p.y_dim_stride, p.seqlen);
   const bool two = p.dstate <= kScanNChunk && p.dim >= 16;
   if (vec) {
     return two ? launch_scan_fwd_wide<T, 16, 8, 2, true>(p, stream)

@@ -188,8 +188,10 @@ class _SelectiveScanFn(torch.autograd.Function):
             if return_last_state else None
         chk = torch.empty((batch, dim, max(scan_num_chunks(L), 1), N), dtype=torch.float32,
                           device=u.device) if needs_grad else None
+        # y before the gate, for the backward's dz (upstream saves the same tensor next to out_z)
+        ypre = torch.empty_like(out) if needs_grad and zz is not None else None
         ctx.delta_softplus = bool(delta_softplus)
-        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32, zz, db32, chk)
+        ctx.save_for_backward(u, delta, A32, Bm, Cm, D32, zz, db32, chk, ypre)
         if u.numel() == 0:  # empty input: the state passes through, nothing to launch
             if return_last_state:
                 last = h0.clone() if h0 is not None else last.zero_()
@@ -209,7 +211,9 @@ class _SelectiveScanFn(torch.autograd.Function):
             z_dim_stride=0 if zz is None else zz.stride(1),
             initial_state=ptr(h0),
             out=ptr(out), out_batch_stride=out.stride(0), out_dim_stride=out.stride(1),
-            last_state=ptr(last), checkpoints=ptr(chk))
+            last_state=ptr(last), checkpoints=ptr(chk),
+            y_pre=ptr(ypre), y_batch_stride=0 if ypre is None else ypre.stride(0),
+            y_dim_stride=0 if ypre is None else ypre.stride(1))
         _lib.call("mtts_selective_scan_fwd", p)
         if return_last_state:
             ctx.mark_non_differentiable(last)
@@ -218,7 +222,7 @@ class _SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *unused):
-        u, delta, A32, Bm, Cm, D32, zz, db32, chk = ctx.saved_tensors
+        u, delta, A32, Bm, Cm, D32, zz, db32, chk, ypre = ctx.saved_tensors
         batch, dim, L = u.shape
         N = A32.shape[1]
         dev = u.device
@@ -254,7 +258,9 @@ class _SelectiveScanFn(torch.autograd.Function):
             ddelta_dim_stride=ddelta.stride(1),
             dz=ptr(dz), dz_batch_stride=0 if dz is None else dz.stride(0),
             dz_dim_stride=0 if dz is None else dz.stride(1),
-            dA=ptr(dA), dB=ptr(dB), dC=ptr(dC), dD=ptr(dD), ddelta_bias=ptr(ddb))
+            dA=ptr(dA), dB=ptr(dB), dC=ptr(dC), dD=ptr(dD), ddelta_bias=ptr(ddb),
+            y_pre=ptr(ypre), y_batch_stride=0 if ypre is None else ypre.stride(0),
+            y_dim_stride=0 if ypre is None else ypre.stride(1))
         _lib.call("mtts_selective_scan_bwd", p)
         return (du, ddelta.to(t_delta), dA.to(t_A), dB.to(t_B), dC.to(t_C),
                 None if dD is None else dD.to(t_D), None if dz is None else dz.to(t_z),
@@ -357,6 +363,7 @@ class _MambaBlockFn(torch.autograd.Function):
             y = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
             last = torch.empty((Bsz, Di, N), dtype=torch.float32, device=dev)
             chk = torch.empty((Bsz, Di, max(scan_num_chunks(T), 1), N), dtype=torch.float32, device=dev)
+            ypre = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)   # y before the gate, for dz
             _lib.call("mtts_selective_scan_fwd", _lib.ScanFwdParams(
                 batch=Bsz, dim=Di, seqlen=T, dstate=N, io_dtype=io, delta_softplus=1,
                 u=ptr(xc), u_batch_stride=xc.stride(0), u_dim_stride=xc.stride(1),
@@ -366,10 +373,12 @@ class _MambaBlockFn(torch.autograd.Function):
                 D=ptr(D32), delta_bias=ptr(db32), z=ptr(z), z_batch_stride=z.stride(0),
                 z_dim_stride=z.stride(1), initial_state=None, out=ptr(y),
                 out_batch_stride=y.stride(0), out_dim_stride=y.stride(1), last_state=ptr(last),
-                checkpoints=ptr(chk)))
+                checkpoints=ptr(chk), y_pre=ptr(ypre), y_batch_stride=ypre.stride(0),
+                y_dim_stride=ypre.stride(1)))
             out = torch.bmm(y.transpose(1, 2), Wo.t().unsqueeze(0).expand(Bsz, -1, -1))  # (B, T, D)
             new_conv = F.pad(x[..., -W:], (max(0, W - T), 0)) if T < W else x[..., -W:].clone()
-        ctx.save_for_backward(hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo)
+        ctx.save_for_backward(hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo,
+                              ypre)
         ctx.meta = (h.dtype, tuple(t.dtype for t in (in_w, conv_w, conv_b, xproj_w, dtproj_w, dt_bias,
                                                       A_log, D, out_w)))
         ctx.mark_non_differentiable(new_conv, last)
@@ -377,7 +386,8 @@ class _MambaBlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dconv, _dlast):
-        hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo = ctx.saved_tensors
+        (hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo,
+         ypre) = ctx.saved_tensors
         t_h, (t_in, t_cw, t_cb, t_xw, t_dtw, t_dtb, t_A, t_D, t_ow) = ctx.meta
         Bsz, T, Dm = hc.shape
         Di, W = cw32.shape
@@ -416,7 +426,8 @@ class _MambaBlockFn(torch.autograd.Function):
                 ddelta=ptr(ddelta), ddelta_batch_stride=ddelta.stride(0),
                 ddelta_dim_stride=ddelta.stride(1),
                 dz=ptr(dzh), dz_batch_stride=dzh.stride(0), dz_dim_stride=dzh.stride(1),
-                dA=ptr(dA), dB=ptr(dBC[0]), dC=ptr(dBC[1]), dD=ptr(dD), ddelta_bias=ptr(ddb)))
+                dA=ptr(dA), dB=ptr(dBC[0]), dC=ptr(dBC[1]), dD=ptr(dD), ddelta_bias=ptr(ddb),
+                y_pre=ptr(ypre), y_batch_stride=ypre.stride(0), y_dim_stride=ypre.stride(1)))
             # d x_dbl = [W_dt^T ddelta | dB | dC]  (B, R + 2N, T), small
             dx_dbl = torch.empty((Bsz, R + 2 * N, T), dtype=dtype, device=dev)
             dx_dbl[:, :R].copy_(torch.bmm(Wdt.t().unsqueeze(0).expand(Bsz, -1, -1), ddelta))

@@ -551,6 +551,7 @@ def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatc
     nch = (T + _lib.SCAN_CHUNK - 1) // _lib.SCAN_CHUNK
     g = {}
     for name, shp, dt in (("out", (Bz, Dm, T), dtype), ("last", (Bz, Dm, N), f32), ("chk", (Bz, Dm, nch, N), f32),
+                          ("ypre", (Bz, Dm, T), dtype),
                           ("du", (Bz, Dm, T), dtype), ("ddelta", (Bz, Dm, T), dtype), ("dz", (Bz, Dm, T), dtype),
                           ("dA", (Dm, N), f32), ("dB", (Bz, N, T), f32), ("dC", (Bz, N, T), f32),
                           ("dD", (Dm,), f32), ("ddb", (Dm,), f32)):
@@ -568,14 +569,17 @@ def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatc
     out, last, chk = g["out"][1], g["last"][1], g["chk"][1]
     _lib.call("mtts_selective_scan_fwd", _lib.ScanFwdParams(
         **common, initial_state=None, out=P(out), out_batch_stride=out.stride(0),
-        out_dim_stride=out.stride(1), last_state=P(last), checkpoints=P(chk)))
+        out_dim_stride=out.stride(1), last_state=P(last), checkpoints=P(chk),
+        y_pre=P(g["ypre"][1]), y_batch_stride=out.stride(0), y_dim_stride=out.stride(1)))
     du, dd, dz = g["du"][1], g["ddelta"][1], g["dz"][1]
     _lib.call("mtts_selective_scan_bwd", _lib.ScanBwdParams(
         **common, dout=P(dout), dout_batch_stride=dout.stride(0), dout_dim_stride=dout.stride(1),
         checkpoints=P(chk), du=P(du), du_batch_stride=du.stride(0), du_dim_stride=du.stride(1),
         ddelta=P(dd), ddelta_batch_stride=dd.stride(0), ddelta_dim_stride=dd.stride(1),
         dz=P(dz), dz_batch_stride=dz.stride(0), dz_dim_stride=dz.stride(1),
-        dA=P(g["dA"][1]), dB=P(g["dB"][1]), dC=P(g["dC"][1]), dD=P(g["dD"][1]), ddelta_bias=P(g["ddb"][1])))
+        dA=P(g["dA"][1]), dB=P(g["dB"][1]), dC=P(g["dC"][1]), dD=P(g["dD"][1]), ddelta_bias=P(g["ddb"][1]),
+        y_pre=P(g["ypre"][1]) if T % 2 == 0 else None,   # both dz routes: forward's y / recomputed y
+        y_batch_stride=out.stride(0), y_dim_stride=out.stride(1)))
     torch.cuda.synchronize()
     for name, (buf, view) in g.items():
         assert _canaries_intact(buf, view.numel()), f"{name}: write outside the tensor"
