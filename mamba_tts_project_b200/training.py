@@ -4,6 +4,7 @@ what ``/root/reference/train.py`` does around ``decoder(...)``, restated for the
     embed_codec_tokens   <- train.py:115-131   ref_hidden from the decoder's own embeddings
     codec_ce_loss        <- train.py:31-42     cross entropy with ignore_index = pad_id
     TrainStep            <- train.py:152-159, 220-235  fwd + loss + bwd (+ DP all-reduce) + clip + Adam
+    GraphedForwardBackward   the same forward + loss + backward captured once in a CUDA graph and replayed
 
 ``TrainStep`` supports micro-batching (gradient accumulation) so that a global batch that does not fit
 one GPU (BASELINE config C5: 24 x d1024, B 64, T 4096) keeps identical numerics at every GPU count:
@@ -84,3 +85,63 @@ class TrainStep:
         torch.nn.utils.clip_grad_norm_(self.decoder.parameters(), self.max_norm)
         self.optim.step()
         return total / n_valid   # this rank's share of the global mean loss
+
+
+class GraphedForwardBackward:
+    """``decoder(...)`` + mean cross entropy + ``backward()`` of ``train.py:226-231`` for FIXED shapes, captured
+    once in a CUDA graph and replayed: one graph launch per step instead of ~1600 kernel launches, so the
+    host never sits between the GPU and its next kernel (eagerly, a step that ends in ``loss.item()`` cannot
+    queue ahead and pays the launch latency of every small kernel burst).
+
+        step = GraphedForwardBackward(decoder, tokens, text, z, targets)   # example tensors fix the shapes
+        loss = step(tokens, text, z, targets)      # host (pinned) or device tensors; returns a 0-d tensor
+
+    After a call every ``p.grad`` holds this step's gradient (in the graph's memory pool: consume it --
+    optimizer, clipping, all-reduce -- before the next call).  Data parallel: call
+    ``GradAllReducer.finish()`` after it (the all-reduce then runs after the backward, not under it)."""
+
+    def __init__(self, decoder, tokens, text_hidden, z_style, targets=None, amp_dtype=torch.bfloat16,
+                 pad_id=None, warmup=3):
+        self.decoder, self.amp_dtype, self.pad_id = decoder, amp_dtype, pad_id
+        dev = next(decoder.parameters()).device
+        targets = tokens if targets is None else targets
+        self._in = [torch.empty(t.shape, dtype=t.dtype, device=dev)
+                    for t in (tokens, text_hidden, z_style, targets)]
+        for dst, src in zip(self._in, (tokens, text_hidden, z_style, targets)):
+            dst.copy_(src, non_blocking=True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # warm-up: lazy initialisation, autotuning, workspaces
+            for _ in range(warmup):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        decoder.zero_grad(set_to_none=True)
+        from . import _lib
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        self.library_launches = _lib.launch_count - n0     # kernels of the C-ABI library inside one replay
+        # the graph writes its gradients into THESE tensors on every replay
+        self._params = [p for p in decoder.parameters() if p.grad is not None]
+        self._grads = [p.grad for p in self._params]
+
+    def _fwd_bwd(self):
+        tok, text, z, tgt = self._in
+        self.decoder.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            logits = self.decoder(tok, text, z)
+        V = logits.shape[-1]
+        kw = {} if self.pad_id is None else {"ignore_index": self.pad_id}
+        loss = F.cross_entropy(logits.reshape(-1, V).float(), tgt.reshape(-1), **kw)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, tokens, text_hidden, z_style, targets=None):
+        targets = tokens if targets is None else targets
+        for dst, src in zip(self._in, (tokens, text_hidden, z_style, targets)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for p, g in zip(self._params, self._grads):   # a caller (e.g. the DP reducer) may have re-pointed .grad
+            p.grad = g
+        return self.loss
