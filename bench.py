@@ -7,8 +7,15 @@
 Workload at every N: BASELINE.json configs[1] ("C2"): 12-layer d_model 512 MambaTTSDecoder, bf16
 (fp32 master weights, bf16 activations/GEMMs, fp32 scan state), teacher-forced forward + backward,
 B = 16 per GPU, T_audio 2048, T_text 256, cross-attn + FiLM.  N > 1 is batch-sharded data
-parallelism (weak scaling: 16 samples per GPU) with a bucketed NCCL gradient all-reduce overlapped
-with backward.  A "step" = forward + loss + backward (+ all-reduce) over one batch.
+parallelism (weak scaling: 16 samples per GPU) with a bucketed NCCL gradient all-reduce.
+A "step" = forward + loss + backward (+ all-reduce) over one batch.
+
+Two timed passes per run, both over the same K steps after W warm-up steps:
+  1. eager (one launch per kernel, all-reduce overlapped with backward): every call into the C-ABI library is
+     bracketed by CUDA events -> per-kernel durations for `roofline` (config.eager_ms_per_step);
+  2. the reported one: forward + loss + backward replayed from a CUDA graph
+     (mamba_tts_project_b200.GraphedForwardBackward), then the all-reduce -> `value`, `ms_per_step`, and,
+     with pinned host inputs copied in and loss.item() read back every step, `e2e`.
 
 One JSON line on stdout (rank 0).  Besides the contract keys it carries
   roofline      the dominant hand-written kernel (selective-scan backward) against the measured HBM peak
