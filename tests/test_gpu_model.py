@@ -86,6 +86,40 @@ def test_block_step_and_continue_vs_oracle(dtype):
     check("conv_state", st[0], cs_ref, t)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("d_model", [256, 512, 1024])
+def test_block_steps_at_serving_batch_vs_oracle(d_model, dtype):
+    """Mamba.step at batch 32 and d_inner 512 / 1024 / 2048: the cluster-of-S fused step kernel the decode
+    benchmark runs (decode.cu::decode_step_fast_kernel), against the oracle's full-sequence forward."""
+    from mamba_tts_project_b200 import Mamba
+    torch.manual_seed(d_model)
+    ref = MambaRef(d_model).eval()
+    with torch.no_grad():
+        ref.A_log.add_(0.2 * torch.randn_like(ref.A_log))
+        if dtype != torch.float32:
+            for p in ref.parameters():
+                if p.dim() > 1:
+                    p.copy_(p.to(dtype).float())
+    blk = Mamba(d_model).cuda()
+    blk.load_state_dict(ref.state_dict())
+    blk = blk.to(dtype) if dtype != torch.float32 else blk
+    B, T = 32, 12
+    h = torch.randn(B, T, d_model).to(dtype).float()
+    with torch.no_grad():
+        full_ref, (cs_ref, ss_ref) = ref(h)
+        hg = h.cuda().to(dtype)
+        st = blk.allocate_inference_cache(B, dtype=dtype)
+        outs = []
+        for t in range(T):
+            o, st = blk(hg[:, t:t + 1], st)
+            outs.append(o)
+        got = torch.cat(outs, 1)
+    t = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    check("steps", got, full_ref, t)
+    check("ssm_state", st[1], ss_ref, t)
+    check("conv_state", st[0], cs_ref, t)
+
+
 def _make_pair(cfg, seed, dtype=torch.float32):
     from mamba_tts_project_b200 import MambaTTSDecoder
     torch.manual_seed(seed)
