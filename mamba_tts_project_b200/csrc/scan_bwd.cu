@@ -17,9 +17,10 @@
 //           ddtA_t = <w_t, A>            dA += w_t dt_t
 //       y / sGB / ddtA are summed over the NG slice lanes with a transposing butterfly (3 SHFL per 4
 //       values at NG = 4); dB / dC over the warp's channel lanes with a halving butterfly (14 SHFL per
-//       16 values at 8 channel lanes) into a per-warp shared tile;
-//   E   du = gy D + dt sGB,  ddelta = (ddtA + u sGB) softplus'(.),  dz = dout y silu'(z), streamed out;
-//       the warps' dB / dC tiles are summed and added to global memory with 16-byte vector REDs.
+//       16 values at 8 channel lanes) whose survivors -- two consecutive timesteps of one state row per
+//       lane -- go straight to global memory with 8-byte vector REDs (no shared tile, no flush loop);
+//   E   du = gy D + dt sGB,  ddelta = (ddtA + u sGB) softplus'(.),  dz = dout y silu'(z), streamed out; the
+//       raw u / delta / dout / z vectors come back from thread-private shared slots filled in P.
 // Two MUFU.EX2 per state update (pre-pass + re-run), everything else packed fp32x2.
 #include "scan_common.cuh"
 
@@ -30,7 +31,6 @@ int dispatch_scan_bwd_wide(const mtts_scan_bwd_params& p, cudaStream_t stream); 
 namespace {
 
 constexpr int kTT = MTTS_SCAN_CHUNK;  // tile = checkpoint interval
-constexpr int kBwdThreads = 64;
 static_assert(kTT == 32, "tile bookkeeping below assumes 32-timestep tiles");
 
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -63,7 +63,7 @@ __device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, c
 }
 
 // Halving butterfly over the channel lanes (lane bits [log2 NG, 5)): v[i*4 + j] (state i of the slice,
-// timestep j) summed over the warp's 32/NG channels; the surviving values go to tile[(j)*NP + i].
+// timestep j) summed over the warp's 32/NG channels.
 template <int NG, int CNT, int BIT>
 __device__ __forceinline__ void chan_reduce_step(float (&v)[16], int lane, int& prefix) {
   if constexpr (BIT >= NG) {
@@ -84,20 +84,36 @@ __device__ __forceinline__ void chan_reduce_step(float (&v)[16], int lane, int& 
     }
   }
 }
-template <int NG, int NP>
-__device__ __forceinline__ void chan_reduce_store(float (&v)[16], int lane, int g, float* tile) {
-  constexpr int CL = 32 / NG;                      // channel lanes
-  constexpr int S = CL >= 16 ? 4 : (CL == 8 ? 3 : (CL == 4 ? 2 : 1));  // halving stages
-  constexpr int R = 16 >> S;                       // values left per lane
+// After the butterfly a writer lane holds R = 16 >> stages values v[0..R): idx = prefix * R + r with state
+// i = idx >> 2 of the slice and timestep j = idx & 3 of the group; prefix depends on the lane only.
+template <int NG>
+struct ChanReduce {
+  static constexpr int CL = 32 / NG;                                           // channel lanes
+  static constexpr int S = CL >= 16 ? 4 : (CL == 8 ? 3 : (CL == 4 ? 2 : 1));   // halving stages
+  static constexpr int R = 16 >> S;                                            // values left per lane
+  __device__ static __forceinline__ bool writer(int lane) { return CL <= 16 || (lane & NG) == 0; }
+  __device__ static __forceinline__ int prefix(int lane) {
+    int pf = 0;
+#pragma unroll
+    for (int bit = 16, cnt = 16; bit >= NG && cnt > 1; bit >>= 1, cnt >>= 1) pf = pf * 2 + ((lane & bit) ? 1 : 0);
+    return pf;
+  }
+};
+// Sum v over the channel lanes and add the survivors to row[0..R) (R consecutive timesteps of one state row
+// of dB / dC in global memory); nvalid = how many of them lie inside the sequence.
+template <int NG, bool kVec>
+__device__ __forceinline__ void chan_reduce_red(float (&v)[16], int lane, float* row, int nvalid) {
+  using CR = ChanReduce<NG>;
   int prefix = 0;
   chan_reduce_step<NG, 16, 16>(v, lane, prefix);
-  const bool writer = CL <= 16 || (lane & NG) == 0;  // CL = 32: the last stage was a plain xor
-  if (writer) {
-    // surviving values: idx = prefix * R + r, state i = idx >> 2, timestep j = idx & 3
+  if (CR::writer(lane) && row != nullptr) {
+    if (CR::R == 2 && kVec) {
+      if (nvalid > 0)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int idx = prefix * R + r;
-      tile[(idx & 3) * NP + g * 4 + (idx >> 2)] = v[r];
+      for (int r = 0; r < CR::R; ++r)
+        if (r < nvalid) atomicAdd(row + r, v[r]);
     }
   }
 }
@@ -119,9 +135,11 @@ struct ScanBwdCfg {
   static constexpr int kItems = kChan * kVecPerRow;
   static constexpr int kIt = (kItems + kThreads - 1) / kThreads;
   static constexpr int kBCItems = NG * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
-  // dt, dtu (-> sGB), gy, y, ddtA rows; B, C tiles; per-warp dB, dC tiles; group-start states
-  static constexpr size_t kSmemFloats = 5 * (size_t)kChan * RS + 2 * (size_t)kTT * NP +
-                                        2 * kWarps * (size_t)kTT * NP + 7 * 4 * CC * (size_t)kThreads;
+  // dt, dtu (-> sGB), gy, ddtA (, y) rows; B, C tiles; group-start states; raw u / delta / dout / z slots
+  static constexpr size_t smem_floats(bool recompute_y) {
+    return (recompute_y ? 5 : 4) * (size_t)kChan * RS + 2 * (size_t)kTT * NP + 7 * 4 * CC * (size_t)kThreads +
+           4 * 4 * kIt * (size_t)kThreads;
+  }
 };
 
 // kRecomputeY: dz needs y = <C, h> and the forward did not hand over its y_pre.
@@ -136,17 +154,18 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   float* dts = smem;                      // [kChan][RS] dt
   float* dtus = dts + kChan * RS;         // dt*u, overwritten by sGB
   float* gys = dtus + kChan * RS;         // dout * silu(z)
-  float* ys = gys + kChan * RS;           // <C, h>
-  float* das = ys + kChan * RS;           // <w, A*log2e>
-  float* Bs = das + kChan * RS;           // [kTT][NP] swizzled
+  float* das = gys + kChan * RS;          // <w, A*log2e>
+  float* ys = das + kChan * RS;           // <C, h> (only when recomputed here)
+  float* Bs = ys + (kRecomputeY ? kChan * RS : 0);  // [kTT][NP] swizzled
   float* Cs = Bs + kTT * NP;
-  float* dBw = Cs + kTT * NP;             // [kWarps][kTT][NP]
-  float* dCw = dBw + kWarps * kTT * NP;
-  float* hbs = dCw + kWarps * kTT * NP;   // [groups 1..7][kThreads][CC][4] state at the start of the group
+  float* hbs = Cs + kTT * NP;             // [groups 1..7][kThreads][CC][4] state at the start of the group
+  // raw u / delta / dout / z vectors of the tile, [tensor][item][thread]: written in P, read back in E by
+  // the same thread (instead of a second trip to L2 with its address arithmetic)
+  uint4* raws = reinterpret_cast<uint4*>(hbs + 7 * 4 * CC * kThreads) + threadIdx.x;
 
   const int N = p.dstate, L = p.seqlen;
   const int b = blockIdx.y, c0 = blockIdx.x * kChan;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int chl = tid / NG * CC, g = tid % NG;  // first of this thread's CC channels
   const int c = c0 + chl;
 
@@ -161,6 +180,14 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       reinterpret_cast<float*>(dAacc[k])[i] = 0.f;
     }
   }
+
+  // dB / dC: the state row and the first timestep (within a group of 4) this lane's butterfly survivors
+  // belong to
+  using CR = ChanReduce<NG>;
+  const int red_idx = CR::prefix(lane) * CR::R;
+  const int red_n = g * 4 + (red_idx >> 2), red_j = red_idx & 3;
+  const int64_t red_off = ((int64_t)b * N + red_n) * L + red_j;
+  const bool red_ok = red_n < N;
 
   const T* ub = reinterpret_cast<const T*>(p.u) + (int64_t)b * p.u_batch_stride;
   const T* db = reinterpret_cast<const T*>(p.delta) + (int64_t)b * p.delta_batch_stride;
@@ -226,6 +253,10 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
         const int cc = c0 + ich;
         const bool ok = cc < p.dim;
         float uv[VE], dv[VE], gv[VE];
+        raws[(0 * kIt + k) * kThreads] = ur[k];
+        raws[(1 * kIt + k) * kThreads] = dr[k];
+        raws[(2 * kIt + k) * kThreads] = gr[k];
+        if (zb) raws[(3 * kIt + k) * kThreads] = zr[k];
         {
           Io<T>::unpack(ur[k], uv);
           Io<T>::unpack(dr[k], dv);
@@ -238,11 +269,13 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           }
         }
         const float bias = (ok && p.delta_bias) ? p.delta_bias[cc] : 0.f;
+        // vector path: a vector is wholly inside or outside the sequence (seqlen % VE == 0)
+        const bool live = ok && (!kVec || t0 + it < L);
 #pragma unroll
         for (int i = 0; i < VE; ++i) {
           float x = dv[i] + bias;
           if (p.delta_softplus) x = softplus_f(x);
-          if (!ok || t0 + it + i >= L) x = 0.f;  // identity step (gy is 0 there: dout loads as 0)
+          if (!live || (!kVec && t0 + it + i >= L)) x = 0.f;  // identity step (gy is 0 there: dout loads as 0)
           dv[i] = x;
           uv[i] *= x;
         }
@@ -289,8 +322,6 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       float* yr = ys + chl * RS;
       float* dar = das + chl * RS;
       float* hb = hbs + tid * (4 * CC);
-      float* dBt = dBw + warp * kTT * NP;
-      float* dCt = dCw + warp * kTT * NP;
 
       float2 h[CC][2];
       float4 h0[CC];
@@ -426,57 +457,30 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           slice_reduce_store<NG>(sgb[k], g, dur + k * RS + 4 * s);
           slice_reduce_store<NG>(dda[k], g, dar + k * RS + 4 * s);
         }
-        chan_reduce_store<NG, NP>(dBv, lane, g, dBt + 4 * s * NP);
-        chan_reduce_store<NG, NP>(dCv, lane, g, dCt + 4 * s * NP);
+        {
+          const int tg = t0 + 4 * s + red_j;
+          const int nvalid = red_ok ? L - tg : 0;
+          chan_reduce_red<NG, kVec>(dBv, lane, p.dB + red_off + t0 + 4 * s, nvalid);
+          chan_reduce_red<NG, kVec>(dCv, lane, p.dC + red_off + t0 + 4 * s, nvalid);
+        }
       }
     }
     __syncthreads();
 
     // ---- E ----------------------------------------------------------------------------------------
-    // this tile's raw inputs are read again (L2 hits) and the next tile's are requested now; both arrive
-    // while the dB / dC tiles are flushed
-    uint4 eu[kIt], ed[kIt], eg[kIt], ez[kIt], ey[kIt];
+    // y_pre of this tile and the next tile's raw inputs / checkpoints are requested now
+    uint4 ey[kIt];
     const T* yb = p.y_pre ? reinterpret_cast<const T*>(p.y_pre) + (int64_t)b * p.y_batch_stride : nullptr;
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       const int idx = tid + k * kThreads;
       const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
       const int cc = c0 + ich;
-      eu[k] = ed[k] = eg[k] = ez[k] = ey[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (idx < Cfg::kItems && cc < p.dim) {
-        if (!kRecomputeY && zb && yb) ey[k] = load_raw<T, kVec>(yb + (int64_t)cc * p.y_dim_stride, t0 + it, L);
-        eu[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it, L);
-        ed[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it, L);
-        eg[k] = load_raw<T, kVec>(gob + (int64_t)cc * p.dout_dim_stride, t0 + it, L);
-        if (zb) ez[k] = load_raw<T, kVec>(zb + (int64_t)cc * p.z_dim_stride, t0 + it, L);
-      }
+      ey[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (!kRecomputeY && zb && yb && idx < Cfg::kItems && cc < p.dim)
+        ey[k] = load_raw<T, kVec>(yb + (int64_t)cc * p.y_dim_stride, t0 + it, L);
     }
     if (tile > 0) fetch_tile(tile - 1);
-    // dB / dC: sum the warps' tiles, one 16-byte RED per (state row, 4 timesteps)
-    for (int idx = tid; idx < 2 * NP * (kTT / 4); idx += kThreads) {
-      const int which = idx / (NP * (kTT / 4)), r = idx % (NP * (kTT / 4));
-      const int n = r % NP, tq = (r / NP) * 4;
-      if (n < N && t0 + tq < L) {
-        const float* w0 = (which ? dCw : dBw) + tq * NP + n;
-        float acc[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[i] = w0[i * NP];
-#pragma unroll
-          for (int w = 1; w < kWarps; ++w) acc[i] += w0[w * kTT * NP + i * NP];
-        }
-        float* dst = (which ? p.dC : p.dB) + ((int64_t)b * N + n) * L + t0 + tq;
-        if (kVec && t0 + tq + 3 < L) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]),
-                       "f"(acc[1]), "f"(acc[2]), "f"(acc[3])
-                       : "memory");
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (t0 + tq + i < L) atomicAdd(dst + i, acc[i]);
-        }
-      }
-    }
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       const int idx = tid + k * kThreads;
@@ -484,10 +488,10 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       const int cc = c0 + ich;
       if (idx < Cfg::kItems && cc < p.dim) {
         float uv[VE], dv[VE], gv[VE], zv[VE];
-        Io<T>::unpack(eu[k], uv);
-        Io<T>::unpack(ed[k], dv);
-        Io<T>::unpack(eg[k], gv);
-        if (zb) Io<T>::unpack(ez[k], zv);
+        Io<T>::unpack(raws[(0 * kIt + k) * kThreads], uv);
+        Io<T>::unpack(raws[(1 * kIt + k) * kThreads], dv);
+        Io<T>::unpack(raws[(2 * kIt + k) * kThreads], gv);
+        if (zb) Io<T>::unpack(raws[(3 * kIt + k) * kThreads], zv);
         const float bias = p.delta_bias ? p.delta_bias[cc] : 0.f;
         const float Dv = p.D ? p.D[cc] : 0.f;
         float dtv[VE], sgv[VE], yv[VE], dav[VE];
@@ -518,7 +522,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           const float x = dv[i] + bias;
           const float sp = (p.delta_softplus && x <= 20.f) ? sigmoid_f(x) : 1.f;
           o_du[i] = fmaf(dtv[i], sgv[i], gy * Dv);
-          const float dd = (t0 + it + i < L) ? fmaf(uv[i], sgv[i], dav[i] * kLn2) * sp : 0.f;
+          const float dd = (kVec ? t0 + it < L : t0 + it + i < L) ? fmaf(uv[i], sgv[i], dav[i] * kLn2) * sp : 0.f;
           o_dd[i] = dd;
           dbias_acc[k] += dd;
           dD_acc[k] = fmaf(gy, uv[i], dD_acc[k]);
@@ -566,7 +570,7 @@ template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY>
 static int launch_scan_bwd_y(const mtts_scan_bwd_params& p, cudaStream_t stream) {
   using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
-  const size_t smem = sizeof(float) * Cfg::kSmemFloats;
+  const size_t smem = sizeof(float) * Cfg::smem_floats(kRecomputeY);
   auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec, kRecomputeY>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
@@ -604,7 +608,8 @@ static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream)
                    vec_ok<T>(p.du, p.du_batch_stride, p.du_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.ddelta, p.ddelta_batch_stride, p.ddelta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.dz, p.dz_batch_stride, p.dz_dim_stride, p.seqlen) &&
-                   vec_ok<T>(p.y_pre, p.y_batch_stride, p.y_dim_stride, p.seqlen);
+                   vec_ok<T>(p.y_pre, p.y_batch_stride, p.y_dim_stride, p.seqlen) &&
+                   aligned16(p.dB) && aligned16(p.dC);  // 8-byte vector REDs
   return vec ? dispatch_scan_bwd_n<T, true>(p, stream) : dispatch_scan_bwd_n<T, false>(p, stream);
 }
 

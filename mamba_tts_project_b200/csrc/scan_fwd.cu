@@ -9,11 +9,15 @@
 //            cross-lane traffic is the <C, h> partial sum over the NG slices (a transposing
 //            butterfly: 3 SHFL per 4 timesteps at NG = 4);
 //   CTA    = kChan channels of one batch element, sequence walked in tiles of TT timesteps:
-//            P  every thread turns its 16-byte vectors of u / delta (prefetched into registers one
-//               tile ahead) into fp32 dt = softplus(delta + bias) and dt*u rows in shared memory, and
-//               transposes the tile of B / C to fp32 [t][n] (16-byte chunk XOR-swizzled);
+//            raw 16-byte vectors of u / delta / z / B / C travel global -> shared with cp.async
+//            (LDGSTS), one tile ahead, into slots PRIVATE to the thread that will consume them (no
+//            registers are held across M, no barrier is needed for them -- only cp.async.wait_group);
+//            P  every thread turns its vectors of u / delta into fp32 dt = softplus(delta + bias) and
+//               dt*u rows in shared memory, and transposes the tile of B / C to fp32 [t][n] (16-byte
+//               chunk XOR-swizzled);
 //            M  the scan proper: LDS.128 of dt, dt*u (per 4 timesteps) and B, C (per timestep, warp
-//               broadcast), y partials reduced over the NG lanes and stored to a shared y tile;
+//               broadcast), y partials reduced over the NG lanes and stored over the dt row (all its
+//               readers are the lanes of that reduction);
 //            E  out = (y + D u) * silu(z), packed and streamed out with 16-byte stores.
 //   Parallelism comes from channels x state slices (B*Di*NG threads); several small CTAs per SM overlap
 //   each other's P/E phases with M.
@@ -53,10 +57,30 @@ __device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, c
   }
 }
 
+// ---- cp.async (LDGSTS) staging into thread-private shared slots ----------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 16 bytes of row[t ..) into *slot: asynchronous when the row is vector-aligned, zeros when absent
+template <typename T, bool kVec>
+__device__ __forceinline__ void stage_raw(uint4* slot, const T* __restrict__ row, int t, int len, bool ok) {
+  if (!ok || t >= len) {
+    *slot = make_uint4(0u, 0u, 0u, 0u);
+  } else if constexpr (kVec) {
+    cp_async16(slot, row + t);
+  } else {
+    *slot = load_raw<T, false>(row, t, len);
+  }
+}
+
 }  // namespace
 
 // CC = channels per thread: every LDS of a B / C chunk then feeds CC recurrences (register tiling of
-// the shared operands -- the kernel is bound by shared-memory wavefronts).
+// the shared operands -- shared-memory wavefronts and MUFU are the two busy pipes).
 template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
 struct ScanFwdCfg {
   static constexpr int VE = Io<T>::kVecElems;
@@ -68,15 +92,18 @@ struct ScanFwdCfg {
   static constexpr int kVecPerRow = TT / VE;
   static constexpr int kItems = kChan * kVecPerRow;                   // u/delta/z vectors per tile
   static constexpr int kIt = (kItems + kThreads - 1) / kThreads;      // ... per thread
-  static constexpr int kBCItems = NP * kVecPerRow;                    // B (or C) vectors per tile
+  static constexpr int kBCItems = 2 * kChunks * kVecPerRow;           // (tensor, 4-row chunk, vector of timesteps)
   static constexpr int kBC = (kBCItems + kThreads - 1) / kThreads;
-  static constexpr size_t kSmemFloats = 3 * (size_t)kChan * RS + 2 * (size_t)TT * NP;
+  // fp32 rows dt (later y), dt*u; fp32 B, C tiles; raw slots: u (two tiles), delta, z, B, C
+  static constexpr size_t kSmemFloats = 2 * (size_t)kChan * RS + 2 * (size_t)TT * NP;
+  static constexpr size_t kRawVecs = (size_t)kThreads * (4 * kIt + 4 * kBC);
+  static constexpr size_t kSmemBytes = 4 * kSmemFloats + 16 * kRawVecs;
   static_assert(G % 4 == 0 && (NG & (NG - 1)) == 0 && NG <= 32 && TT % VE == 0 && TT % 4 == 0, "cfg");
   static_assert(kChan % CC == 0 && kThreads % 32 == 0, "whole warps");
 };
 
-template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
-__global__ void __launch_bounds__(kChan / CC * NG, (G <= 4 && CC == 1) ? 512 / (kChan * NG) : 1)
+template <typename T, int G, int NG, int CC, int kChan, int TT, int kMinBlocks, bool kVec>
+__global__ void __launch_bounds__(kChan / CC * NG, kMinBlocks)
 scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   using Cfg = ScanFwdCfg<T, G, NG, CC, kChan, TT, kVec>;
   constexpr int VE = Cfg::VE, kThreads = Cfg::kThreads, NP = Cfg::NP, RS = Cfg::RS;
@@ -84,11 +111,16 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   constexpr int Q = G / 4;
 
   extern __shared__ __align__(16) float smem[];
-  float* dts = smem;                  // [kChan][RS]  dt
+  float* dts = smem;                  // [kChan][RS]  dt, overwritten by <C, h> group by group
   float* dtus = dts + kChan * RS;     // [kChan][RS]  dt * u
-  float* ys = dtus + kChan * RS;      // [kChan][RS]  <C, h>
-  float* Bs = ys + kChan * RS;        // [TT][NP]     swizzled
+  float* ys = dts;
+  float* Bs = dtus + kChan * RS;      // [TT][NP]     swizzled
   float* Cs = Bs + TT * NP;
+  // raw slots, [item][thread]: a thread only ever touches its own
+  uint4* rawU = reinterpret_cast<uint4*>(Cs + TT * NP) + threadIdx.x;  // [2][kIt]
+  uint4* rawD = rawU + 2 * kIt * kThreads;                             // [kIt]
+  uint4* rawZ = rawD + kIt * kThreads;                                 // [kIt]
+  uint4* rawBC = rawZ + kIt * kThreads;                                // [kBC][4 rows]
 
   const int N = p.dstate, L = p.seqlen;
   const int b = blockIdx.y, c0 = blockIdx.x * kChan;
@@ -121,75 +153,80 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   const T* Bb = reinterpret_cast<const T*>(p.B) + (int64_t)b * p.B_batch_stride;
   const T* Cb = reinterpret_cast<const T*>(p.C) + (int64_t)b * p.C_batch_stride;
 
-  int it_ch[kIt], it_t[kIt];
+  auto item_ch = [&](int k) { return (tid + k * kThreads) / kVecPerRow; };
+  auto item_t = [&](int k) { return ((tid + k * kThreads) % kVecPerRow) * VE; };
+  auto item_ok = [&](int k) { return tid + k * kThreads < Cfg::kItems && c0 + item_ch(k) < p.dim; };
   float it_bias[kIt], it_D[kIt];
-  bool it_ok[kIt];
 #pragma unroll
   for (int k = 0; k < kIt; ++k) {
-    const int idx = tid + k * kThreads;
-    it_ch[k] = idx / kVecPerRow;
-    it_t[k] = (idx % kVecPerRow) * VE;
-    it_ok[k] = idx < Cfg::kItems && c0 + it_ch[k] < p.dim;
-    it_bias[k] = (it_ok[k] && p.delta_bias) ? p.delta_bias[c0 + it_ch[k]] : 0.f;
-    it_D[k] = (it_ok[k] && p.D) ? p.D[c0 + it_ch[k]] : 0.f;
+    it_bias[k] = (item_ok(k) && p.delta_bias) ? p.delta_bias[c0 + item_ch(k)] : 0.f;
+    it_D[k] = (item_ok(k) && p.D) ? p.D[c0 + item_ch(k)] : 0.f;
   }
-  int bc_n[kBC], bc_t[kBC];
-  bool bc_ok[kBC];
-#pragma unroll
-  for (int k = 0; k < kBC; ++k) {
-    const int idx = tid + k * kThreads;
-    bc_n[k] = idx / kVecPerRow;
-    bc_t[k] = (idx % kVecPerRow) * VE;
-    bc_ok[k] = idx < Cfg::kBCItems;
-  }
+  // B / C item = (tensor, chunk of 4 dstate rows, 16-byte vector of timesteps): 4 raw vectors -> VE STS.128
+  constexpr int kBCPer = Cfg::kChunks * kVecPerRow;
+  auto bc_which = [&](int k) { return (tid + k * kThreads) / kBCPer; };
+  auto bc_chunk = [&](int k) { return ((tid + k * kThreads) % kBCPer) / kVecPerRow; };
+  auto bc_t = [&](int k) { return ((tid + k * kThreads) % kVecPerRow) * VE; };
 
-  uint4 u_nx[kIt], d_nx[kIt], z_cur[kIt], u_cur[kIt], B_nx[kBC], C_nx[kBC];
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-
-  auto prefetch = [&](int t0) {
+  // tile at t0: u -> rawU[ub], delta, B, C (consumed by the next P); zt0 >= 0: z of that tile (for E)
+  auto stage = [&](int t0, int ubuf, int zt0) {
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
-      u_nx[k] = d_nx[k] = zero4;
-      if (it_ok[k]) {
-        const int cc = c0 + it_ch[k];
-        u_nx[k] = load_raw<T, kVec>(ub + (int64_t)cc * p.u_dim_stride, t0 + it_t[k], L);
-        d_nx[k] = load_raw<T, kVec>(db + (int64_t)cc * p.delta_dim_stride, t0 + it_t[k], L);
-      }
+      const bool ok = item_ok(k);
+      const int64_t cc = ok ? c0 + item_ch(k) : 0;
+      stage_raw<T, kVec>(rawU + (ubuf * kIt + k) * kThreads, ub + cc * p.u_dim_stride, t0 + item_t(k), L,
+                         ok && t0 >= 0);
+      stage_raw<T, kVec>(rawD + k * kThreads, db + cc * p.delta_dim_stride, t0 + item_t(k), L, ok && t0 >= 0);
+      if (zb && zt0 >= 0)
+        stage_raw<T, kVec>(rawZ + k * kThreads, zb + cc * p.z_dim_stride, zt0 + item_t(k), L, ok);
     }
+    if (t0 >= 0) {
 #pragma unroll
-    for (int k = 0; k < kBC; ++k) {
-      B_nx[k] = C_nx[k] = zero4;
-      if (bc_ok[k] && bc_n[k] < N) {
-        B_nx[k] = load_raw<T, kVec>(Bb + (int64_t)bc_n[k] * p.B_state_stride, t0 + bc_t[k], L);
-        C_nx[k] = load_raw<T, kVec>(Cb + (int64_t)bc_n[k] * p.C_state_stride, t0 + bc_t[k], L);
+      for (int k = 0; k < kBC; ++k) {
+        if (tid + k * kThreads < Cfg::kBCItems) {
+          const bool isC = bc_which(k) != 0;
+          const T* src = isC ? Cb : Bb;
+          const int64_t rs = isC ? p.C_state_stride : p.B_state_stride;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = bc_chunk(k) * 4 + i;
+            stage_raw<T, kVec>(rawBC + (k * 4 + i) * kThreads, src + (int64_t)(n < N ? n : 0) * rs, t0 + bc_t(k), L,
+                               n < N);
+          }
+        }
       }
     }
+    cp_async_commit();
   };
 
-  prefetch(0);
+  stage(0, 0, -1);
+  cp_async_wait_all();
   const int ntiles = (L + TT - 1) / TT;
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int t0 = tile * TT;
+    const int ubuf = tile & 1;
 
-    // ---- P: registers -> shared fp32 tiles --------------------------------------------------------
+    // ---- P: raw slots -> shared fp32 tiles --------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       if (tid + k * kThreads < Cfg::kItems) {
+        const int ich = item_ch(k), it = item_t(k);
+        // vector path: a vector is wholly inside or outside the sequence (seqlen % VE == 0)
+        const bool live = item_ok(k) && (!kVec || t0 + it < L);
         float uv[VE], dv[VE];
-        Io<T>::unpack(u_nx[k], uv);
-        Io<T>::unpack(d_nx[k], dv);
-        u_cur[k] = u_nx[k];
+        Io<T>::unpack(rawU[(ubuf * kIt + k) * kThreads], uv);
+        Io<T>::unpack(rawD[k * kThreads], dv);
 #pragma unroll
         for (int i = 0; i < VE; ++i) {
           float x = dv[i] + it_bias[k];
           if (p.delta_softplus) x = softplus_f(x);
-          if (!it_ok[k] || t0 + it_t[k] + i >= L) x = 0.f;  // identity step: decay 1, input 0
+          if (!live || (!kVec && t0 + it + i >= L)) x = 0.f;  // identity step: decay 1, input 0
           dv[i] = x;
           uv[i] *= x;
         }
-        float* d0 = dts + it_ch[k] * RS + it_t[k];
-        float* d1 = dtus + it_ch[k] * RS + it_t[k];
+        float* d0 = dts + ich * RS + it;
+        float* d1 = dtus + ich * RS + it;
 #pragma unroll
         for (int i = 0; i < VE; i += 4) {
           *reinterpret_cast<float4*>(d0 + i) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
@@ -199,32 +236,24 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
     }
 #pragma unroll
     for (int k = 0; k < kBC; ++k) {
-      if (bc_ok[k]) {
-        float bv[VE], cv[VE];
-        Io<T>::unpack(B_nx[k], bv);
-        Io<T>::unpack(C_nx[k], cv);
-        const int n = bc_n[k];
+      if (tid + k * kThreads < Cfg::kBCItems) {
+        float rows[4][VE];
 #pragma unroll
-        for (int i = 0; i < VE; ++i) {
-          const int t = bc_t[k] + i;
-          const int pos = t * NP + (((n >> 2) ^ ((t >> 3) & Cfg::kSwz)) << 2) + (n & 3);
-          Bs[pos] = bv[i];
-          Cs[pos] = cv[i];
+        for (int i = 0; i < 4; ++i) Io<T>::unpack(rawBC[(k * 4 + i) * kThreads], rows[i]);
+        float* dst = bc_which(k) ? Cs : Bs;
+        const int chunk = bc_chunk(k), tv = bc_t(k);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const int t = tv + e;
+          *reinterpret_cast<float4*>(dst + t * NP + ((chunk ^ ((t >> 3) & Cfg::kSwz)) << 2)) =
+              make_float4(rows[0][e], rows[1][e], rows[2][e], rows[3][e]);
         }
       }
     }
     __syncthreads();
 
-    // ---- prefetch the next tile (and this tile's z) while M runs -----------------------------------
-    if (zb) {
-#pragma unroll
-      for (int k = 0; k < kIt; ++k) {
-        z_cur[k] = zero4;
-        if (it_ok[k])
-          z_cur[k] = load_raw<T, kVec>(zb + (int64_t)(c0 + it_ch[k]) * p.z_dim_stride, t0 + it_t[k], L);
-      }
-    }
-    if (tile + 1 < ntiles) prefetch(t0 + TT);
+    // ---- request the next tile (and this tile's z) while M runs ------------------------------------
+    stage(tile + 1 < ntiles ? t0 + TT : -1, ubuf ^ 1, t0);
 
     // ---- M: the recurrence -------------------------------------------------------------------------
     // (issuing the exps a group ahead was measured and lost to plain unrolling: the kernel is bound by
@@ -291,41 +320,45 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
 #pragma unroll
           for (int k = 0; k < CC; ++k) yp[k][j] = acc[k].x + acc[k].y;
         }
-        // sum the partials over the NG lanes of each channel
+        // sum the partials over the NG lanes of each channel; y replaces dt of the same 4 timesteps, whose
+        // only readers were these lanes (same warp, before the shuffles)
 #pragma unroll
         for (int k = 0; k < CC; ++k) slice_reduce_store<NG>(yp[k], g, yr + k * RS + t4);
       }
     }
+    cp_async_wait_all();  // own slots: z of this tile, raw inputs of the next
     __syncthreads();
 
     // ---- E: gate and stream out --------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
-      if (it_ok[k]) {
+      if (item_ok(k)) {
+        const int ich = item_ch(k), it = item_t(k);
+        const float Dv = it_D[k];
         float uv[VE], yv[VE];
-        Io<T>::unpack(u_cur[k], uv);
-        const float* y0 = ys + it_ch[k] * RS + it_t[k];
+        Io<T>::unpack(rawU[(ubuf * kIt + k) * kThreads], uv);
+        const float* y0 = ys + ich * RS + it;
 #pragma unroll
         for (int i = 0; i < VE; i += 4) {
           const float4 v = lds128(y0 + i);
           yv[i] = v.x; yv[i + 1] = v.y; yv[i + 2] = v.z; yv[i + 3] = v.w;
         }
 #pragma unroll
-        for (int i = 0; i < VE; ++i) yv[i] = fmaf(it_D[k], uv[i], yv[i]);
+        for (int i = 0; i < VE; ++i) yv[i] = fmaf(Dv, uv[i], yv[i]);
         if (p.y_pre)  // the backward's dz needs y before the gate
           store_raw<T, kVec>(reinterpret_cast<T*>(p.y_pre) + (int64_t)b * p.y_batch_stride +
-                                 (int64_t)(c0 + it_ch[k]) * p.y_dim_stride, t0 + it_t[k], L, yv);
+                                 (int64_t)(c0 + ich) * p.y_dim_stride, t0 + it, L, yv);
         if (zb) {
           float zv[VE];
-          Io<T>::unpack(z_cur[k], zv);
+          Io<T>::unpack(rawZ[k * kThreads], zv);
 #pragma unroll
           for (int i = 0; i < VE; ++i) yv[i] *= silu_f(zv[i]);
         }
-        store_raw<T, kVec>(ob + (int64_t)(c0 + it_ch[k]) * p.out_dim_stride, t0 + it_t[k], L, yv);
+        store_raw<T, kVec>(ob + (int64_t)(c0 + ich) * p.out_dim_stride, t0 + it, L, yv);
       }
     }
-    // no barrier needed here: the next P writes dts/dtus/Bs/Cs (last read in M, before the barrier
-    // above) and the next M writes ys only after the next P's barrier.
+    // no barrier needed here: the next P writes the dt rows of its OWN items (read as y by the same thread
+    // in E), dtus/Bs/Cs were last read in M (before the barrier above), raw slots are thread-private.
   }
 
   if (p.last_state) {
@@ -341,12 +374,12 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
   }
 }
 
-template <typename T, int G, int NG, int CC, int kChan, int TT, bool kVec>
+template <typename T, int G, int NG, int CC, int kChan, int TT, int kMinBlocks, bool kVec>
 static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
   using Cfg = ScanFwdCfg<T, G, NG, CC, kChan, TT, kVec>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
-  const size_t smem = sizeof(float) * Cfg::kSmemFloats;
-  auto kern = scan_fwd_kernel<T, G, NG, CC, kChan, TT, kVec>;
+  const size_t smem = Cfg::kSmemBytes;
+  auto kern = scan_fwd_kernel<T, G, NG, CC, kChan, TT, kMinBlocks, kVec>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + kChan - 1) / kChan, p.batch);
@@ -354,23 +387,28 @@ static int launch_scan_fwd(const mtts_scan_fwd_params& p, cudaStream_t stream) {
   return launch_status();
 }
 
-// G states per thread x NG slices cover the (padded) dstate; TT scales with the bytes per element so
-// that the register-resident prefetch stays at two vectors per thread and stream.
+// G states per thread x NG slices cover the (padded) dstate.  Tiles are 32 timesteps (= the checkpoint
+// interval): shared memory per channel -- raw slots plus two fp32 rows -- is what limits the resident warps.
+// Measured on B200 (bf16, C4 shape B 32 x d_inner 2048 x T 4096; C2 layer shape B 16 x 1024 x 2048):
+//   N = 16: 8 states x 2 slices, 1 channel per thread   1.57 ms / 0.272 ms   <- selected
+//           4 x 4, 2 channels per thread                1.61 ms / 0.285 ms
+//           4 x 4, 1 channel (the round-1a mapping)     1.92 ms / 0.290 ms
+//           8 x 2 or 16 x 1 with 1-warp CTAs            1.97-2.0 ms / 0.35 ms
+//   N = 64: 8 x 8, 2 channels, 128 threads              5.69 ms              <- selected
+//           8 x 8, 2 channels, 64 threads  5.93;  4 x 16, 2 channels  6.65;  4 x 16, 1 channel  8.2-10.6
+// i.e. fewer, fatter threads win as long as >= 12 warps stay resident: every LDS of dt / dt*u feeds 8 states,
+// every LDS of a B / C chunk feeds 2 channels (wide states), and the slice butterfly shrinks.
 template <typename T, bool kVec>
 static int dispatch_scan_fwd_n(const mtts_scan_fwd_params& p, cudaStream_t stream) {
-  constexpr int TT = Io<T>::kVecElems * 8;  // 64 (bf16) / 32 (fp32)
+  constexpr int TT = 32;
   const int N = p.dstate;
-  if (N <= 4) return launch_scan_fwd<T, 4, 1, 1, 64, TT / 4, kVec>(p, stream);
-  if (N <= 8) return launch_scan_fwd<T, 4, 2, 1, 32, TT / 2, kVec>(p, stream);
-  // CC = 2 (<T, 4, 4, 2, 16, TT / 2>) was measured at the C4 shape: 1.97 ms vs 1.87 ms for CC = 1 -- the
-  // halved LDS traffic is paid for with half the resident warps, as in the backward.
-  if (N <= 16) return launch_scan_fwd<T, 4, 4, 1, 16, TT, kVec>(p, stream);
-  // wider states: still 4 rows per thread, more slices per channel (measured at N = 64, C4 shape: 4 x 16
-  // slices 7.9 ms, 8 x 8 10.5 ms, 16 x 4 9.1 ms -- registers, hence resident warps, decide)
-  if (N <= 32) return launch_scan_fwd<T, 4, 8, 1, 8, TT, kVec>(p, stream);
-  if (N <= 64) return launch_scan_fwd<T, 4, 16, 1, 8, TT, kVec>(p, stream);
-  if (N <= 128) return launch_scan_fwd<T, 4, 32, 1, 4, TT, kVec>(p, stream);
-  return launch_scan_fwd<T, 8, 32, 1, 4, TT, kVec>(p, stream);
+  if (N <= 4) return launch_scan_fwd<T, 4, 1, 1, 64, TT, 4, kVec>(p, stream);
+  if (N <= 8) return launch_scan_fwd<T, 4, 2, 1, 32, TT, 4, kVec>(p, stream);
+  if (N <= 16) return launch_scan_fwd<T, 8, 2, 1, 32, TT, 8, kVec>(p, stream);
+  if (N <= 32) return launch_scan_fwd<T, 8, 4, 2, 32, TT, 4, kVec>(p, stream);
+  if (N <= 64) return launch_scan_fwd<T, 8, 8, 2, 32, TT, 3, kVec>(p, stream);
+  if (N <= 128) return launch_scan_fwd<T, 8, 16, 2, 16, TT, 3, kVec>(p, stream);
+  return launch_scan_fwd<T, 8, 32, 1, 4, TT, 1, kVec>(p, stream);
 }
 
 template <typename T>

@@ -51,10 +51,8 @@ def main():
     dev = "cuda"
     rows = []
     only = tuple(int(v) for v in args.only.split(",")) if args.only else None
-    for N in (16, 64):
-        for T in (4096, 16384, 65536):
-            if only and (N, T) != only:
-                continue
+    for N in ((only[0],) if only else (16, 64)):
+        for T in ((only[1],) if only else (4096, 16384, 65536)):
             B, Di = args.tokens // T, args.dim
             u = torch.randn(B, Di, T, device=dev, dtype=dt).requires_grad_()
             delta = (0.5 * torch.rand(B, Di, T, device=dev)).to(dt).requires_grad_()
