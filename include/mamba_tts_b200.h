@@ -273,6 +273,45 @@ typedef struct {
 int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * cross_attn_block_decode -- the whole cross-attention branch of decode_step for one new token in ONE
+ * launch (mamba_decoder.py:67-81 with T_q = 1; what the eager path runs as add_layernorm + q Linear +
+ * cross_attn_decode + out_proj Linear + add_layernorm):
+ *   x1 = x + delta;  hq = LN(x1; lnq);  q = wq hq + bq;  a = softmax(q k^T / sqrt(head_dim) + mask) v;
+ *   o = wo a + bo;   x_out = x1 + o;    out = film_gamma * LN(x_out; lno) + film_beta
+ *   x, x_out (batch, d) fp32 residual stream (x_out may alias x); delta (batch, d) io dtype or NULL;
+ *   wq, wo (d, d) row-major [out][in] and bq, bo (d) in the io dtype (nn.MultiheadAttention's
+ *   in_proj_weight[0:d] / out_proj); k, v (batch, t_kv, d); mask as in cross_attn_decode;
+ *   LN weights / biases and film_gamma / film_beta (batch, d) fp32 (FiLM optional); out (batch, d) io dtype.
+ * wo == NULL selects the front half only: x_out = x1, out = a (the caller runs the out projection and
+ * the second add_layernorm itself); bo / lno / film are then ignored.
+ * One thread-block cluster of `heads` CTAs per batch element.  Supported: heads = 8, head_dim = 64,
+ * t_kv <= 256; anything else returns MTTS_ERR_UNSUPPORTED and the caller uses the separate ops.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, heads, head_dim, t_kv;
+  int32_t io_dtype;
+  float eps_q, eps_o;
+  const float* x;
+  const void* delta; /* or NULL */
+  float* x_out;      /* or NULL */
+  const float* lnq_weight;
+  const float* lnq_bias;
+  const void* wq;
+  const void* bq;
+  const void* k;
+  const void* v;
+  const uint8_t* mask; /* or NULL */
+  const void* wo;
+  const void* bo;
+  const float* lno_weight;
+  const float* lno_bias;
+  const float* film_gamma; /* both or neither */
+  const float* film_beta;
+  void* out;
+} mtts_cross_attn_block_params;
+int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * add_layernorm_fwd / add_layernorm_bwd -- residual add + LayerNorm (eps, affine) + optional FiLM:
  * the memory-bound glue of mamba_decoder.py:59,64,67,78,81-86,89 in one pass per tensor.
  *   x_out = x + delta                 (x, x_out: fp32 residual stream; delta: io dtype, optional)

@@ -114,11 +114,16 @@ GemmBf16Params = _struct("GemmBf16Params", """
 BiasGeluParams = _struct("BiasGeluParams", """
     i:rows i:cols i:io_dtype i:reserved l:ld p:x p:bias p:dout p:out p:colsum""")
 
-# declaration order of the header == argument of mtts_sizeof_params
+CrossAttnBlockParams = _struct("CrossAttnBlockParams", """
+    i:batch i:heads i:head_dim i:t_kv i:io_dtype f:eps_q f:eps_o
+    p:x p:delta p:x_out p:lnq_weight p:lnq_bias p:wq p:bq p:k p:v p:mask p:wo p:bo
+    p:lno_weight p:lno_bias p:film_gamma p:film_beta p:out""")
+
+# argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
-                 GemmBf16Params, BiasGeluParams]
+                 GemmBf16Params, BiasGeluParams, CrossAttnBlockParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -134,6 +139,7 @@ ENTRY_POINTS = {
     "mtts_selective_state_update": StateUpdateParams,
     "mtts_mamba_decode_step": DecodeStepParams,
     "mtts_cross_attn_decode": CrossAttnDecodeParams,
+    "mtts_cross_attn_block_decode": CrossAttnBlockParams,
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,

@@ -37,6 +37,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 10: return (int)sizeof(mtts_skinny_linear_params);
     case 11: return (int)sizeof(mtts_gemm_bf16_params);
     case 12: return (int)sizeof(mtts_bias_gelu_params);
+    case 13: return (int)sizeof(mtts_cross_attn_block_params);
     default: return -1;
   }
 }

@@ -776,6 +776,331 @@ static int launch_decode_step(const mtts_decode_step_params& p, cudaStream_t s) 
   return launch_status();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The whole cross-attention branch of one decode step as ONE launch (mamba_decoder.py:67-81 with T_q = 1):
+//   x1 = x + delta;  hq = LN2(x1);  q = Wq hq + bq;  a = softmax(q K^T / sqrt(dh) + mask) V;
+//   o = Wo a + bo;   x2 = x1 + o;   out = FiLM(LN3(x2))
+// A thread-block cluster of `heads` CTAs owns one batch element, CTA = one head.  Every CTA normalises
+// the (tiny) row itself, projects its own 64 query features straight from L2-resident Wq rows while its
+// K / V rows are in flight from HBM, and after the attention multiplies its head's slice of Wo; the
+// per-head partial rows are summed through distributed shared memory, after which every CTA holds the
+// complete x2 row, normalises it and writes its own 64-column slice.  Replaces LayerNorm + q GEMM +
+// attention + o GEMM + LayerNorm (5 launches, 4 of them a few microseconds of pure latency) per layer.
+// Rounding points mirror the unfused path: hq, q, q*scale, a, o are rounded to the io dtype.
+constexpr int kXBlockThreads = 256;
+
+__device__ __forceinline__ float block_sum256(float v, float* red, int lane, int warp) {
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kXBlockThreads / 32; ++w) s += red[w];
+  __syncthreads();
+  return s;
+}
+
+template <typename T, int kLPR, int kIt, int kHeads, int kQBatch, bool kFull>
+__global__ void __launch_bounds__(kXBlockThreads, sizeof(T) == 2 ? 4 : 2)
+cross_attn_block_decode_kernel(const mtts_cross_attn_block_params p) {
+  constexpr int VE = Io<T>::kVecElems;
+  constexpr int kWarps = kXBlockThreads / 32;
+  constexpr int kRPW = 32 / kLPR;
+  constexpr int kDh = kLPR * VE;
+  constexpr int Dm = kHeads * kDh;
+  constexpr int EPT = Dm / kXBlockThreads;      // row elements per thread
+  constexpr int kRowVecs = Dm / VE;             // 16-byte vectors per Wq row
+  constexpr int kQPass = (kRowVecs + 31) / 32;  // ... per lane
+  constexpr int kQRows = kDh / kWarps;          // query features per warp
+  constexpr int kSegVecs = kDh / VE;            // vectors per Wo row segment (= kLPR)
+  constexpr int kORowsPerPass = kXBlockThreads / kSegVecs;
+  constexpr int kOPass = Dm / kORowsPerPass;
+  static_assert(Dm % kXBlockThreads == 0 && kDh % kWarps == 0 && kQRows % kQBatch == 0, "shape");
+  static_assert(Dm % kORowsPerPass == 0 && kRowVecs % 32 == 0, "shape");
+
+  __shared__ __align__(16) float hq_s[Dm];
+  __shared__ __align__(16) float opart_s[Dm];
+  __shared__ __align__(16) float q_s[kDh];
+  __shared__ __align__(16) float a_s[kDh];
+  __shared__ __align__(16) float acc_s[kWarps * kDh];
+  __shared__ float red_s[kWarps];
+  __shared__ float sum_s[kWarps];
+
+  const int h = blockIdx.x, b = blockIdx.y;  // cluster = the kHeads CTAs of one batch element, rank == head
+  const int Tk = p.t_kv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % kLPR, rsel = lane / kLPR;
+  const float scale = rsqrtf((float)kDh);
+
+  // ---- K / V rows of this head: pulled from HBM into L2 now (no registers), loaded after the query
+  //      projection -- four CTAs per SM stay resident and the whole grid is one wave ----------------------
+  const T* Kb = reinterpret_cast<const T*>(p.k) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const T* Vb = reinterpret_cast<const T*>(p.v) + (int64_t)b * Tk * Dm + h * kDh + sub * VE;
+  const uint8_t* mk = p.mask ? p.mask + (int64_t)b * Tk : nullptr;
+  if (sub == 0) {  // one prefetch per 128-byte row segment (kDh * sizeof(T) bytes, line aligned for bf16 x 64)
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int t = (it * kWarps + warp) * kRPW + rsel;
+      if (t < Tk) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Kb + (int64_t)t * Dm));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Vb + (int64_t)t * Dm));
+        if (kDh * sizeof(T) > 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Kb + (int64_t)t * Dm) + 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(Vb + (int64_t)t * Dm) + 128));
+        }
+      }
+    }
+  }
+
+  // ---- x1 = x + delta, hq = LN2(x1) (two-pass statistics, like add_layernorm_fwd) ------------------------
+  const int e0 = tid * EPT;
+  float x1[EPT];
+  {
+    const float* xr = p.x + (int64_t)b * Dm + e0;
+    const T* dl = p.delta ? reinterpret_cast<const T*>(p.delta) + (int64_t)b * Dm + e0 : nullptr;
+    float s = 0.f, lw[EPT], lb[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      x1[i] = xr[i] + (dl ? Io<T>::to_f(dl[i]) : 0.f);
+      lw[i] = p.lnq_weight[e0 + i];  // requested before the reductions: one round trip less
+      lb[i] = p.lnq_bias[e0 + i];
+      s += x1[i];
+    }
+    const float mean = block_sum256(s, red_s, lane, warp) / (float)Dm;
+    float qd = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) qd = fmaf(x1[i] - mean, x1[i] - mean, qd);
+    const float rstd = rsqrtf(block_sum256(qd, red_s, lane, warp) / (float)Dm + p.eps_q);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const float y = fmaf((x1[i] - mean) * rstd, lw[i], lb[i]);
+      hq_s[e0 + i] = Io<T>::to_f(Io<T>::from_f(y));
+    }
+  }
+  __syncthreads();
+
+  // ---- q = Wq[h*dh .. , :] hq + bq: warp = kQRows features, lanes along the row ---------------------------
+  {
+    const T* wq = reinterpret_cast<const T*>(p.wq) + (int64_t)(h * kDh + warp * kQRows) * Dm;
+#pragma unroll
+    for (int r0 = 0; r0 < kQRows; r0 += kQBatch) {
+      uint4 wv[kQBatch][kQPass];
+#pragma unroll
+      for (int r = 0; r < kQBatch; ++r)
+#pragma unroll
+        for (int ps = 0; ps < kQPass; ++ps)
+          wv[r][ps] = ldg16(wq + (int64_t)(r0 + r) * Dm + (ps * 32 + lane) * VE);
+#pragma unroll
+      for (int r = 0; r < kQBatch; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < kQPass; ++ps) {
+          float wf[VE];
+          Io<T>::unpack(wv[r][ps], wf);
+          const float* hv = hq_s + (ps * 32 + lane) * VE;
+#pragma unroll
+          for (int i = 0; i < VE; ++i) acc = fmaf(wf[i], hv[i], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const int j = warp * kQRows + r0 + r;
+          const float qb = acc + Io<T>::to_f(reinterpret_cast<const T*>(p.bq)[h * kDh + j]);
+          q_s[j] = Io<T>::to_f(Io<T>::from_f(Io<T>::to_f(Io<T>::from_f(qb)) * scale));
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- attention over the cached rows (cross_attn_decode_cached_kernel) -----------------------------------
+  uint4 kraw[kIt], vraw[kIt];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    if (t < Tk) {
+      kraw[it] = ldg16_stream(Kb + (int64_t)t * Dm);
+      vraw[it] = ldg16_stream(Vb + (int64_t)t * Dm);
+    } else {
+      kraw[it] = make_uint4(0, 0, 0, 0);
+      vraw[it] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  float qv[VE];
+#pragma unroll
+  for (int j = 0; j < VE; ++j) qv[j] = q_s[sub * VE + j];
+  float sc[kIt];
+  float lmax = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    float kv[VE];
+    Io<T>::unpack(kraw[it], kv);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VE; ++j) s = fmaf(kv[j], qv[j], s);
+#pragma unroll
+    for (int o = kLPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t >= Tk || (mk && !mk[t])) s = -INFINITY;
+    sc[it] = s;
+    lmax = fmaxf(lmax, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if (lane == 0) red_s[warp] = lmax;
+  __syncthreads();
+  float gmax = red_s[0];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) gmax = fmaxf(gmax, red_s[w]);
+  float acc[VE];
+#pragma unroll
+  for (int j = 0; j < VE; ++j) acc[j] = 0.f;
+  float lsum = 0.f;
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int t = (it * kWarps + warp) * kRPW + rsel;
+    const float pt = (t < Tk) ? ex2f((sc[it] - gmax) * kLog2e) : 0.f;
+    float vv[VE];
+    Io<T>::unpack(vraw[it], vv);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc[j] = fmaf(pt, vv[j], acc[j]);
+    lsum += pt;
+  }
+#pragma unroll
+  for (int o = kLPR; o < 32; o <<= 1) {
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (rsel == 0) {
+#pragma unroll
+    for (int j = 0; j < VE; ++j) acc_s[warp * kDh + sub * VE + j] = acc[j];
+  }
+  if (lane == 0) sum_s[warp] = lsum;
+  __syncthreads();
+  if (tid < kDh) {
+    float gsum = 0.f, a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      gsum += sum_s[w];
+      a += acc_s[w * kDh + tid];
+    }
+    const T aT = Io<T>::from_f(a * (1.f / gsum));
+    a_s[tid] = Io<T>::to_f(aT);
+    if constexpr (!kFull) reinterpret_cast<T*>(p.out)[(int64_t)b * Dm + h * kDh + tid] = aT;
+  }
+  const bool mine = (e0 / kDh) == h;  // this CTA writes its own head-sized slice of the row
+  if constexpr (!kFull) {  // front half only: x_out = x1, out = attention output; o-proj and LN3 follow separately
+    if (mine && p.x_out) {
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) p.x_out[(int64_t)b * Dm + e0 + i] = x1[i];
+    }
+    return;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  __syncthreads();
+
+  // ---- this head's share of o = Wo a: kSegVecs lanes per output row, 128-byte row segments ---------------
+  {
+    const int seg = tid % kSegVecs, rgrp = tid / kSegVecs;
+    const T* wo = reinterpret_cast<const T*>(p.wo) + h * kDh + seg * VE;
+    float av[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) av[i] = a_s[seg * VE + i];
+    constexpr int kOBatch = kOPass < 8 ? kOPass : 8;
+#pragma unroll
+    for (int p0 = 0; p0 < kOPass; p0 += kOBatch) {
+      uint4 wv[kOBatch];
+#pragma unroll
+      for (int ps = 0; ps < kOBatch; ++ps) wv[ps] = ldg16(wo + (int64_t)((p0 + ps) * kORowsPerPass + rgrp) * Dm);
+#pragma unroll
+      for (int ps = 0; ps < kOBatch; ++ps) {
+        float wf[VE];
+        Io<T>::unpack(wv[ps], wf);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VE; ++i) s = fmaf(wf[i], av[i], s);
+#pragma unroll
+        for (int o = kSegVecs / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (seg == 0) opart_s[(p0 + ps) * kORowsPerPass + rgrp] = s;
+      }
+    }
+  }
+  cluster.sync();
+
+  // ---- x2 = x1 + (sum of the heads' partial rows + bo), complete row in every CTA ---------------------------
+  float x2[EPT];
+  {
+    float o[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < kHeads; ++r) {
+      const float* rp = cluster.map_shared_rank(opart_s, r) + e0;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) o[i] += rp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const float ob = o[i] + Io<T>::to_f(reinterpret_cast<const T*>(p.bo)[e0 + i]);
+      x2[i] = x1[i] + Io<T>::to_f(Io<T>::from_f(ob));
+    }
+  }
+  if (mine && p.x_out) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) p.x_out[(int64_t)b * Dm + e0 + i] = x2[i];
+  }
+  // ---- out = FiLM(LN3(x2)) ------------------------------------------------------------------------------------
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) s += x2[i];
+    const float mean = block_sum256(s, red_s, lane, warp) / (float)Dm;
+    float qd = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) qd = fmaf(x2[i] - mean, x2[i] - mean, qd);
+    const float rstd = rsqrtf(block_sum256(qd, red_s, lane, warp) / (float)Dm + p.eps_o);
+    if (mine) {
+      T* out = reinterpret_cast<T*>(p.out) + (int64_t)b * Dm + e0;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        float w = p.lno_weight[e0 + i], bb = p.lno_bias[e0 + i];
+        if (p.film_gamma) {  // out = gamma (xhat w + b) + beta, folded like add_layernorm_fwd
+          const float gm = p.film_gamma[(int64_t)b * Dm + e0 + i], bt = p.film_beta[(int64_t)b * Dm + e0 + i];
+          w *= gm;
+          bb = fmaf(gm, bb, bt);
+        }
+        out[i] = Io<T>::from_f(fmaf((x2[i] - mean) * rstd, w, bb));
+      }
+    }
+  }
+  cluster.sync();  // nobody leaves while its partial row may still be read
+}
+
+template <typename T, int kLPR, int kIt, int kHeads, int kQBatch>
+static int launch_xattn_block(const mtts_cross_attn_block_params& p, cudaStream_t s) {
+  if (!p.wo) {  // front half: independent CTAs
+    cross_attn_block_decode_kernel<T, kLPR, kIt, kHeads, kQBatch, false>
+        <<<dim3(kHeads, p.batch), kXBlockThreads, 0, s>>>(p);
+    return launch_status();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kHeads, p.batch);
+  cfg.blockDim = dim3(kXBlockThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kHeads;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, cross_attn_block_decode_kernel<T, kLPR, kIt, kHeads, kQBatch, true>, p);
+  if (e != cudaSuccess) return -static_cast<int>(e);
+  return launch_status();
+}
+
 }  // namespace mtts
 
 extern "C" int mtts_selective_state_update(const mtts_state_update_params* p, mtts_stream_t stream) {
@@ -842,4 +1167,28 @@ extern "C" int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mt
     mtts::cross_attn_decode_generic_kernel<__nv_bfloat16><<<grid, mtts::kAttnThreads, smem, s>>>(*p);
   }
   return mtts::launch_status();
+}
+
+extern "C" int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* p, mtts_stream_t stream) {
+  if (!p || !p->x || !p->lnq_weight || !p->lnq_bias || !p->wq || !p->bq || !p->k || !p->v || !p->out)
+    return MTTS_ERR_NULL;
+  if (p->wo && (!p->bo || !p->lno_weight || !p->lno_bias)) return MTTS_ERR_NULL;
+  if ((p->film_gamma == nullptr) != (p->film_beta == nullptr)) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->t_kv < 1 || p->batch > 65535) return MTTS_ERR_SHAPE;
+  // one instantiation per supported decoder shape: 8 heads x 64 features, cached rows
+  if (p->heads != 8 || p->head_dim != 64) return MTTS_ERR_UNSUPPORTED;
+  if (!mtts::aligned16(p->k) || !mtts::aligned16(p->v) || !mtts::aligned16(p->wq) ||
+      (p->wo && !mtts::aligned16(p->wo)))
+    return MTTS_ERR_ALIGN;
+  if (p->batch == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->io_dtype) {
+    case MTTS_BF16:
+      if (p->t_kv > 8 * 8 * 4) return MTTS_ERR_UNSUPPORTED;
+      return mtts::launch_xattn_block<__nv_bfloat16, 8, 8, 8, 8>(*p, s);
+    case MTTS_F32:
+      if (p->t_kv > 16 * 8 * 2) return MTTS_ERR_UNSUPPORTED;
+      return mtts::launch_xattn_block<float, 16, 16, 8, 2>(*p, s);
+    default: return MTTS_ERR_DTYPE;
+  }
 }

@@ -18,6 +18,7 @@ Decisions on the reference's defects are listed in DESIGN.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -187,6 +188,15 @@ class GenerationContext:
                                 (decoder.layers[0].mamba.d_inner, decoder.layers[0].ff[0].out_features)) \
                 and decoder.layers[0].mamba.d_inner % 16 == 0 \
                 and decoder.layers[0].ff[0].out_features % 16 == 0
+            # the front of the cross-attention branch (residual add + LN + q projection + attention) as one
+            # launch where the kernel exists (8 heads x 64, t_kv <= 256).  MTTS_FUSED_ATTENTION=0 keeps the
+            # separate launches, =2 runs the whole branch incl. out projection + LN + FiLM as one cluster
+            # launch (the parity tests run all three).  Measured at B 64 inside the replayed graph:
+            # 0: 749 us/step, 1: 674 us/step, 2: 704 us/step -- the per-(batch, head) out projection pulls
+            # another 32 MB of weight rows through L2 and two cluster barriers, more than the two launches cost.
+            self.fused_attention = int(os.environ.get("MTTS_FUSED_ATTENTION", "1")) \
+                if ops.cross_attn_block_decode_supported(dtype, memory.shape[2], self.layers[0].heads,
+                                                         memory.shape[1]) else 0
             self.tok = decoder.token_embed.weight.detach().float().contiguous()
             self.pos = decoder.pos_embed.weight.detach().float().contiguous()
 
@@ -270,13 +280,25 @@ class MambaTTSDecoder(nn.Module):
                                       lw.mamba["conv_b"], lw.mamba["x_proj"], lw.mamba["dt_proj"],
                                       lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"])
             m = F.linear(y, lw.mamba["out_proj"], lw.mamba["out_bias"])
-            x, h = ops.add_layernorm(x, m, lw.ln2[0], lw.ln2[1], lw.ln2[2], out_dtype=dt,
-                                     inplace=True)
-            q = F.linear(h, lw.wq, lw.bq)
-            a = ops.cross_attn_decode(q, lw.k, lw.v, lw.heads, mask=ctx.mask)
-            o = F.linear(a, lw.wo, lw.bo)
-            x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
-                                     beta=lw.beta, out_dtype=dt, inplace=True)
+            if ctx.fused_attention == 2:
+                # residual add + LN + q projection + attention + out projection + residual add + LN + FiLM:
+                # one cluster launch instead of five
+                h = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads, lw.wo,
+                                                lw.bo, lw.ln3, mask=ctx.mask, gamma=lw.gamma, beta=lw.beta)
+            elif ctx.fused_attention == 1:
+                # residual add + LN + q projection + attention in one launch of independent (batch, head) CTAs
+                a = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads, mask=ctx.mask)
+                o = F.linear(a, lw.wo, lw.bo)
+                x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
+                                         beta=lw.beta, out_dtype=dt, inplace=True)
+            else:
+                x, h = ops.add_layernorm(x, m, lw.ln2[0], lw.ln2[1], lw.ln2[2], out_dtype=dt,
+                                         inplace=True)
+                q = F.linear(h, lw.wq, lw.bq)
+                a = ops.cross_attn_decode(q, lw.k, lw.v, lw.heads, mask=ctx.mask)
+                o = F.linear(a, lw.wo, lw.bo)
+                x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
+                                         beta=lw.beta, out_dtype=dt, inplace=True)
             f = F.gelu(F.linear(h, lw.w1, lw.b1))
             delta = F.linear(f, lw.w2, lw.b2)
         _, h = ops.add_layernorm(x, delta, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], out_dtype=dt,

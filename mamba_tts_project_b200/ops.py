@@ -22,7 +22,8 @@ from ._lib import ptr
 
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
-           "add_layernorm", "skinny_linear", "gemm_bf16", "bias_gelu", "colsum", "linear"]
+           "add_layernorm", "skinny_linear", "gemm_bf16", "bias_gelu", "colsum", "linear",
+           "cross_attn_block_decode", "cross_attn_block_decode_supported"]
 
 
 def _unit_last_stride(t):
@@ -521,6 +522,50 @@ def cross_attn_decode(q, k, v, heads, mask=None, out=None):
                                    io_dtype=_lib.io_dtype(q), q=ptr(q), k=ptr(k), v=ptr(v),
                                    mask=ptr(m8), out=ptr(o))
     _lib.call("mtts_cross_attn_decode", p)
+    return o
+
+
+def cross_attn_block_decode_supported(dtype, d_model, heads, t_kv):
+    """Shapes ``cross_attn_block_decode`` has a kernel for (else use the separate ops)."""
+    return dtype in (torch.bfloat16, torch.float32) and heads == 8 and d_model == 512 and t_kv <= 256
+
+
+def cross_attn_block_decode(x, delta, lnq, wq, bq, k, v, heads, wo=None, bo=None, lno=None, mask=None,
+                            gamma=None, beta=None, out=None):
+    """One launch for the cross-attention branch of a decode step (``mtts_cross_attn_block_decode``):
+    x (batch, d) fp32 residual stream, updated IN PLACE to x + delta + o; delta (batch, d) or None;
+    lnq / lno = (weight, bias, eps) of the LayerNorms before the attention / before the FFN; wq, bq, wo,
+    bo in the io dtype; k, v (batch, t_kv, d); gamma, beta (batch, d) fp32 FiLM or None.
+    Returns FiLM(LN(x_new; lno)) (batch, d) in the io dtype.  With wo=None only the front half runs:
+    x <- x + delta and the attention output (before the out projection) is returned."""
+    _lib.require_cuda(x, delta, wq, bq, k, v, wo, bo, mask, gamma, beta)
+    batch, dm = x.shape
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError("the residual stream x must be contiguous fp32")
+    dt = k.dtype
+    front_only = wo is None  # x <- x + delta, returns the attention output (before the out projection)
+    for t in (wq, bq, v) + (() if front_only else (wo, bo)) + (() if delta is None else (delta,)):
+        if t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError("delta, wq, bq, wo, bo, k, v must be contiguous and share a dtype")
+    if k.shape != v.shape or k.shape[0] != batch or k.shape[2] != dm or not k.is_contiguous():
+        raise RuntimeError("k, v must be contiguous (batch, t_kv, d_model)")
+    if wq.shape != (dm, dm) or bq.shape != (dm,) or (
+            not front_only and (wo.shape != (dm, dm) or bo.shape != (dm,))):
+        raise RuntimeError("wq, wo must be (d, d); bq, bo (d)")
+    if (gamma is None) != (beta is None):
+        raise RuntimeError("gamma and beta come together")
+    m8 = None
+    if mask is not None:
+        m8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
+    o = out if out is not None else torch.empty(batch, dm, device=x.device, dtype=dt)
+    p = _lib.CrossAttnBlockParams(
+        batch=batch, heads=heads, head_dim=dm // heads, t_kv=k.shape[1], io_dtype=_lib.io_dtype(k),
+        eps_q=lnq[2], eps_o=0.0 if front_only else lno[2], x=ptr(x), delta=ptr(delta), x_out=ptr(x),
+        lnq_weight=ptr(lnq[0]), lnq_bias=ptr(lnq[1]), wq=ptr(wq), bq=ptr(bq), k=ptr(k), v=ptr(v),
+        mask=ptr(m8), wo=ptr(wo), bo=ptr(bo), lno_weight=None if front_only else ptr(lno[0]),
+        lno_bias=None if front_only else ptr(lno[1]),
+        film_gamma=ptr(gamma), film_beta=ptr(beta), out=ptr(o))
+    _lib.call("mtts_cross_attn_block_decode", p)
     return o
 
 

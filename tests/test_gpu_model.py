@@ -221,6 +221,52 @@ def test_decoder_bf16_decode_tracks_fp32():
             check(f"bf16 step logits (fused={fused})", torch.cat(got, 1), torch.cat(ref_lg, 1), 4e-2)
 
 
+@pytest.mark.parametrize("fused", ["2", "1", "0"], ids=["one_launch", "fused_front", "separate_ops"])
+def test_decoder_d512_decode_vs_oracle(fused, monkeypatch):
+    """The decoder's serving shape (d_model 512, 8 heads, [ref || text] of 96 rows, key-padding mask): the
+    one-launch cross-attention branch and the five separate launches both reproduce the oracle's
+    decode_step -- identical greedy ids in fp32, bf16 inside its tolerance."""
+    monkeypatch.setenv("MTTS_FUSED_ATTENTION", fused)
+    cfg = dict(vocab_size_audio=256, d_model=512, n_layers=2, n_heads=8, d_ff=1024, d_style=64,
+               max_len=256, num_quantizers=1)
+    ref, dec = _make_pair(cfg, seed=11)
+    torch.manual_seed(3)
+    B = 5
+    text, refh, z = torch.randn(B, 64, 512), torch.randn(B, 32, 512), torch.randn(B, 64)
+    tmask = torch.rand(B, 64) > 0.2
+    tmask[:, 0] = True
+    tok0 = torch.randint(0, 256, (B, 1))
+    with torch.no_grad():
+        states, tok, ref_lg, toks = None, tok0, [], [tok0]
+        for i in range(10):
+            lg, states = ref.decode_step(tok, text, z, states, i, text_mask=tmask, ref_hidden=refh)
+            tok = lg.argmax(-1)
+            toks.append(tok)
+            ref_lg.append(lg)
+        ref_lg = torch.cat(ref_lg, 1)
+        # fp32, reference signature
+        states, tok, got, ids = None, tok0.cuda(), [], []
+        for i in range(10):
+            lg, states = dec.decode_step(tok, text.cuda(), z.cuda(), states, i, text_mask=tmask.cuda(),
+                                         ref_hidden=refh.cuda())
+            tok = lg.argmax(-1)
+            got.append(lg)
+            ids.append(tok)
+        assert dec._gen_ctx.fused_attention == int(fused)
+        check("fp32 step logits", torch.cat(got, 1), ref_lg, FP32_TOL)
+        assert torch.equal(torch.cat(ids, 1).cpu(), torch.cat(toks[1:], 1)), "greedy ids differ on the fp32 path"
+        # bf16, teacher-forced on the oracle's tokens
+        ctx = dec.prepare_generation(text.cuda(), z.cuda(), text_mask=tmask.cuda(), ref_hidden=refh.cuda(),
+                                     dtype=torch.bfloat16)
+        assert ctx.fused_attention == int(fused)
+        st = dec.allocate_states(B, torch.bfloat16)
+        got = []
+        for i in range(10):
+            x = (ctx.tok[toks[i][:, 0].cuda()] + ctx.pos[i]).float()
+            got.append(dec._step_core(ctx, x.contiguous(), st)[:, None])
+        check("bf16 step logits", torch.cat(got, 1), ref_lg, 4e-2)
+
+
 def test_decoder_multi_quantizer_tokens():
     cfg = dict(vocab_size_audio=32, d_model=64, n_layers=1, n_heads=4, d_ff=64, d_style=16,
                max_len=64, num_quantizers=3)

@@ -353,6 +353,70 @@ def test_cross_attn_decode_vs_torch(shape, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("case", [(64, 256, True, True), (3, 77, False, True), (5, 256, True, False), (1, 8, False, False)],
+                         ids=["c3", "ragged", "nofilm", "tiny"])
+def test_cross_attn_block_decode_vs_torch(case, dtype):
+    """The one-launch cross-attention branch (cluster of 8 head CTAs per batch element) against the same
+    chain in plain PyTorch, rounding to the io dtype where the separate ops do (mamba_decoder.py:67-81)."""
+    from mamba_tts_project_b200 import cross_attn_block_decode
+    import torch.nn.functional as F
+    batch, Tk, use_mask, film = case
+    dm, heads, dh = 512, 8, 64
+    g = torch.Generator().manual_seed(1000 + Tk)
+    rn = lambda *sh: torch.randn(*sh, generator=g)
+    x, delta = rn(batch, dm), rn(batch, dm).to(dtype)
+    lnq = (1 + 0.1 * rn(dm), 0.1 * rn(dm), 1e-5)
+    lno = (1 + 0.1 * rn(dm), 0.1 * rn(dm), 1e-5)
+    wq, wo = (rn(dm, dm) * dm ** -0.5).to(dtype), (rn(dm, dm) * dm ** -0.5).to(dtype)
+    bq, bo = (0.1 * rn(dm)).to(dtype), (0.1 * rn(dm)).to(dtype)
+    k, v = rn(batch, Tk, dm).to(dtype), rn(batch, Tk, dm).to(dtype)
+    gamma, beta = (rn(batch, dm), rn(batch, dm)) if film else (None, None)
+    mask = None
+    if use_mask:
+        mask = torch.rand(batch, Tk, generator=g) > 0.3
+        mask[:, 0] = True
+    rd = lambda t: t.to(dtype).float()  # the rounding a separate kernel's output would get
+    x1 = x + delta.float()
+    hq = rd(F.layer_norm(x1, (dm,), lnq[0], lnq[1], lnq[2]))
+    q = rd(hq @ wq.float().T + bq.float())
+    qh = rd(q * dh ** -0.5).view(batch, heads, 1, dh)
+    kh = k.float().view(batch, Tk, heads, dh).transpose(1, 2)
+    vh = v.float().view(batch, Tk, heads, dh).transpose(1, 2)
+    sc = qh @ kh.transpose(-1, -2)
+    if mask is not None:
+        sc = sc.masked_fill(~mask[:, None, None, :], float("-inf"))
+    a = rd((torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(batch, dm))
+    o = rd(a @ wo.float().T + bo.float())
+    x2 = x1 + o
+    ref = F.layer_norm(x2, (dm,), lno[0], lno[1], lno[2])
+    if film:
+        ref = gamma * ref + beta
+    dev = lambda t: None if t is None else t.cuda()
+    xg = x.cuda()
+    for with_delta in (True, False):
+        xg = x.cuda() if with_delta else x1.cuda()
+        out = cross_attn_block_decode(xg, dev(delta) if with_delta else None,
+                                      (dev(lnq[0]), dev(lnq[1]), lnq[2]), dev(wq), dev(bq), dev(k), dev(v), heads,
+                                      dev(wo), dev(bo), (dev(lno[0]), dev(lno[1]), lno[2]), mask=dev(mask),
+                                      gamma=dev(gamma), beta=dev(beta))
+        check("x_out", xg, x2, tol(dtype))
+        check("out", out, ref, tol(dtype))
+
+
+def test_cross_attn_block_decode_unsupported_shapes_raise():
+    from mamba_tts_project_b200 import cross_attn_block_decode
+    from mamba_tts_project_b200.ops import cross_attn_block_decode_supported
+    assert not cross_attn_block_decode_supported(torch.bfloat16, 1024, 16, 256)
+    assert not cross_attn_block_decode_supported(torch.bfloat16, 512, 8, 257)
+    dm, heads, Tk, dt = 256, 8, 16, torch.bfloat16
+    z = lambda *sh: torch.zeros(*sh, device="cuda", dtype=dt)
+    f = lambda *sh: torch.ones(*sh, device="cuda")
+    with pytest.raises(RuntimeError):  # head_dim 32: no kernel, no silent fallback
+        cross_attn_block_decode(f(2, dm), None, (f(dm), f(dm), 1e-5), z(dm, dm), z(dm), z(2, Tk, dm), z(2, Tk, dm),
+                                heads, z(dm, dm), z(dm), (f(dm), f(dm), 1e-5))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(4, 3, 200), (2, 64, 512), (3, 5, 1024), (1, 7, 64)],
                          ids=["d200", "d512", "d1024", "d64"])
 @pytest.mark.parametrize("film", [False, True], ids=["plain", "film"])
