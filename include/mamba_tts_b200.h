@@ -312,6 +312,39 @@ typedef struct {
 int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * decode_embed / decode_greedy -- the token plumbing around one decode step of a greedy generation loop
+ * (the missing caller of decode_step; embedding sum of mamba_decoder.py:218-221, argmax over
+ * the logits of :254-256), with every counter resident on the device so a step is CUDA-graph replayable:
+ *   embed:  x[b, :] = tok_embed[tok[b], :] + pos_embed[*pos, :]  (fp32);  then *step += 1
+ *   greedy: tok[b] = argmax_v logits[b, v] (lowest index on ties); out[b, *step] = tok[b];  then *pos += 1
+ * tok (batch) int64 ids (caller guarantees 0 <= id < vocab rows of tok_embed); pos, step: device int64
+ * scalars (step = column of `out` being generated, -1 before the first embed).  dim % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, dim;
+  const int64_t* tok;
+  const int64_t* pos;
+  const float* tok_embed;
+  const float* pos_embed;
+  float* x;      /* (batch, dim) */
+  int64_t* step; /* incremented after the gather, or NULL */
+} mtts_decode_embed_params;
+int mtts_decode_embed(const mtts_decode_embed_params* p, mtts_stream_t stream);
+
+typedef struct {
+  int32_t batch, vocab;
+  int32_t io_dtype;
+  int32_t reserved;
+  const void* logits; /* (batch, vocab) contiguous, io dtype */
+  int64_t* tok;       /* (batch) */
+  int64_t* out;       /* (batch, out_stride) or NULL */
+  int64_t out_stride;
+  const int64_t* step;
+  int64_t* pos;       /* incremented after the argmax, or NULL */
+} mtts_decode_greedy_params;
+int mtts_decode_greedy(const mtts_decode_greedy_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * add_layernorm_fwd / add_layernorm_bwd -- residual add + LayerNorm (eps, affine) + optional FiLM:
  * the memory-bound glue of mamba_decoder.py:59,64,67,78,81-86,89 in one pass per tensor.
  *   x_out = x + delta                 (x, x_out: fp32 residual stream; delta: io dtype, optional)

@@ -119,11 +119,17 @@ CrossAttnBlockParams = _struct("CrossAttnBlockParams", """
     p:x p:delta p:x_out p:lnq_weight p:lnq_bias p:wq p:bq p:k p:v p:mask p:wo p:bo
     p:lno_weight p:lno_bias p:film_gamma p:film_beta p:out""")
 
+DecodeEmbedParams = _struct("DecodeEmbedParams", """
+    i:batch i:dim p:tok p:pos p:tok_embed p:pos_embed p:x p:step""")
+
+DecodeGreedyParams = _struct("DecodeGreedyParams", """
+    i:batch i:vocab i:io_dtype i:reserved p:logits p:tok p:out l:out_stride p:step p:pos""")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
-                 GemmBf16Params, BiasGeluParams, CrossAttnBlockParams]
+                 GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -140,6 +146,8 @@ ENTRY_POINTS = {
     "mtts_mamba_decode_step": DecodeStepParams,
     "mtts_cross_attn_decode": CrossAttnDecodeParams,
     "mtts_cross_attn_block_decode": CrossAttnBlockParams,
+    "mtts_decode_embed": DecodeEmbedParams,
+    "mtts_decode_greedy": DecodeGreedyParams,
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,

@@ -38,6 +38,8 @@ extern "C" int mtts_sizeof_params(int which) {
     case 11: return (int)sizeof(mtts_gemm_bf16_params);
     case 12: return (int)sizeof(mtts_bias_gelu_params);
     case 13: return (int)sizeof(mtts_cross_attn_block_params);
+    case 14: return (int)sizeof(mtts_decode_embed_params);
+    case 15: return (int)sizeof(mtts_decode_greedy_params);
     default: return -1;
   }
 }

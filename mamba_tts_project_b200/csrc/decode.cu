@@ -1101,6 +1101,59 @@ static int launch_xattn_block(const mtts_cross_attn_block_params& p, cudaStream_
   return launch_status();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Token plumbing of the generation loop (the caller side of mamba_decoder.py:218-221,254-256): two launches
+// instead of the nine ATen ones (2 gathers, add, cast, argmax, 2 copies, 2 counter increments).
+//   embed:  x[b, :] = tok_embed[tok[b], :] + pos_embed[*pos, :];  *step += 1   (step = column being generated)
+//   greedy: tok[b] = out[b, *step] = argmax_v logits[b, v] (lowest index on ties);  *pos += 1
+// Each counter is bumped by the kernel that does NOT read it, so stream order alone makes it race-free.
+__global__ void __launch_bounds__(128)
+decode_embed_kernel(const mtts_decode_embed_params p) {
+  const int b = blockIdx.x;
+  const int64_t tk = p.tok[b], ps = *p.pos;
+  const float* te = p.tok_embed + tk * p.dim;
+  const float* pe = p.pos_embed + ps * p.dim;
+  float* x = p.x + (int64_t)b * p.dim;
+  for (int e = threadIdx.x * 4; e < p.dim; e += 128 * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(te + e);
+    const float4 c = *reinterpret_cast<const float4*>(pe + e);
+    *reinterpret_cast<float4*>(x + e) = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+  if (b == 0 && threadIdx.x == 0 && p.step) *p.step += 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_greedy_kernel(const mtts_decode_greedy_params p) {
+  __shared__ float bv_s[8];
+  __shared__ int bi_s[8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const T* lg = reinterpret_cast<const T*>(p.logits) + (int64_t)b * p.vocab;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < p.vocab; v += 256) {
+    const float x = Io<T>::to_f(lg[v]);
+    if (x > bv || (x == bv && v < bi)) { bv = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { bv_s[warp] = bv; bi_s[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+      if (bv_s[w] > bv || (bv_s[w] == bv && bi_s[w] < bi)) { bv = bv_s[w]; bi = bi_s[w]; }
+    if (bi == 0x7fffffff) bi = 0;  // all NaN / -inf row
+    p.tok[b] = bi;
+    if (p.out) p.out[(int64_t)b * p.out_stride + *p.step] = bi;
+    if (b == 0 && p.pos) *p.pos += 1;
+  }
+}
 }  // namespace mtts
 
 extern "C" int mtts_selective_state_update(const mtts_state_update_params* p, mtts_stream_t stream) {
@@ -1191,4 +1244,27 @@ extern "C" int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* 
       return mtts::launch_xattn_block<float, 16, 16, 8, 2>(*p, s);
     default: return MTTS_ERR_DTYPE;
   }
+}
+
+extern "C" int mtts_decode_embed(const mtts_decode_embed_params* p, mtts_stream_t stream) {
+  if (!p || !p->tok || !p->pos || !p->tok_embed || !p->pos_embed || !p->x) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->dim < 4 || p->dim % 4 != 0 || p->batch > 65535) return MTTS_ERR_SHAPE;
+  if (!mtts::aligned16(p->tok_embed) || !mtts::aligned16(p->pos_embed) || !mtts::aligned16(p->x)) return MTTS_ERR_ALIGN;
+  if (p->batch == 0) return MTTS_OK;
+  mtts::decode_embed_kernel<<<p->batch, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  return mtts::launch_status();
+}
+
+extern "C" int mtts_decode_greedy(const mtts_decode_greedy_params* p, mtts_stream_t stream) {
+  if (!p || !p->logits || !p->tok) return MTTS_ERR_NULL;
+  if (p->out && !p->step) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->vocab < 1 || p->batch > 65535) return MTTS_ERR_SHAPE;
+  if (p->batch == 0) return MTTS_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (p->io_dtype) {
+    case MTTS_F32: mtts::decode_greedy_kernel<float><<<p->batch, 256, 0, s>>>(*p); break;
+    case MTTS_BF16: mtts::decode_greedy_kernel<__nv_bfloat16><<<p->batch, 256, 0, s>>>(*p); break;
+    default: return MTTS_ERR_DTYPE;
+  }
+  return mtts::launch_status();
 }

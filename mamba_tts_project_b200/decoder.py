@@ -373,14 +373,22 @@ class MambaTTSDecoder(nn.Module):
         if not greedy and use_cuda_graph:
             use_cuda_graph = False  # sampling draws host-side RNG state per step
 
+        if int(tok.min()) < 0 or int(tok.max()) >= ctx.tok.shape[0] or start_index + n_steps > ctx.pos.shape[0]:
+            raise IndexError("first_token / positions outside the embedding tables")
+        xbuf = torch.empty(B, ctx.tok.shape[1], dtype=torch.float32, device=dev)
+        if greedy:
+            col.fill_(-1)  # decode_embed bumps it at the start of every step
+
         def one_step():
+            if greedy:  # token plumbing as two library launches, counters stay on the device
+                ops.decode_embed(tok, pos, ctx.tok, ctx.pos, xbuf, step=col)
+                logits = self._step_core(ctx, xbuf, states)
+                ops.decode_greedy(logits, tok, out=out, step=col, pos=pos)
+                return
             x = (ctx.tok.index_select(0, tok) + ctx.pos.index_select(0, pos)).float()
             logits = self._step_core(ctx, x, states)
-            if greedy:
-                nxt = logits.argmax(dim=-1)
-            else:
-                probs = torch.softmax(logits.float() / temperature, dim=-1)
-                nxt = torch.multinomial(probs, 1, generator=generator)[:, 0]
+            probs = torch.softmax(logits.float() / temperature, dim=-1)
+            nxt = torch.multinomial(probs, 1, generator=generator)[:, 0]
             tok.copy_(nxt)
             out.index_copy_(1, col, nxt[:, None])
             pos.add_(1)
@@ -408,7 +416,7 @@ class MambaTTSDecoder(nn.Module):
             s.copy_(s0)
         tok.copy_(first_token[:, 0])
         pos.fill_(start_index)
-        col.zero_()
+        col.fill_(-1 if greedy else 0)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             one_step()

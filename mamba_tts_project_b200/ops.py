@@ -23,7 +23,7 @@ from ._lib import ptr
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
            "add_layernorm", "skinny_linear", "gemm_bf16", "bias_gelu", "colsum", "linear",
-           "cross_attn_block_decode", "cross_attn_block_decode_supported"]
+           "cross_attn_block_decode", "cross_attn_block_decode_supported", "decode_embed", "decode_greedy"]
 
 
 def _unit_last_stride(t):
@@ -567,6 +567,42 @@ def cross_attn_block_decode(x, delta, lnq, wq, bq, k, v, heads, wo=None, bo=None
         film_gamma=ptr(gamma), film_beta=ptr(beta), out=ptr(o))
     _lib.call("mtts_cross_attn_block_decode", p)
     return o
+
+
+def decode_embed(tok, pos, tok_embed, pos_embed, x, step=None):
+    """x[b] = tok_embed[tok[b]] + pos_embed[pos] into the static fp32 buffer x (batch, d); then step += 1.
+    tok (batch) int64, pos / step one-element int64 device tensors (``mtts_decode_embed``)."""
+    _lib.require_cuda(tok, pos, tok_embed, pos_embed, x, step)
+    if tok.dtype != torch.long or pos.dtype != torch.long or (step is not None and step.dtype != torch.long):
+        raise RuntimeError("tok, pos, step must be int64")
+    if tok_embed.dtype != torch.float32 or pos_embed.dtype != torch.float32 or x.dtype != torch.float32:
+        raise RuntimeError("embedding tables and x must be fp32")
+    if not (tok.is_contiguous() and tok_embed.is_contiguous() and pos_embed.is_contiguous() and x.is_contiguous()):
+        raise RuntimeError("operands must be contiguous")
+    batch, dim = x.shape
+    if tok.shape != (batch,) or tok_embed.shape[1] != dim or pos_embed.shape[1] != dim:
+        raise RuntimeError("shape mismatch")
+    p = _lib.DecodeEmbedParams(batch=batch, dim=dim, tok=ptr(tok), pos=ptr(pos), tok_embed=ptr(tok_embed),
+                               pos_embed=ptr(pos_embed), x=ptr(x), step=ptr(step))
+    _lib.call("mtts_decode_embed", p)
+    return x
+
+
+def decode_greedy(logits, tok, out=None, step=None, pos=None):
+    """tok[b] = argmax logits[b] (lowest index on ties), out[b, step] = tok[b]; then pos += 1
+    (``mtts_decode_greedy``).  logits (batch, vocab) fp32 / bf16; tok (batch), out (batch, n) int64."""
+    _lib.require_cuda(logits, tok, out, step, pos)
+    if not logits.is_contiguous() or logits.dim() != 2 or tok.shape != (logits.shape[0],):
+        raise RuntimeError("logits must be contiguous (batch, vocab), tok (batch)")
+    if tok.dtype != torch.long or (out is not None and (out.dtype != torch.long or out.stride(1) != 1)):
+        raise RuntimeError("tok / out must be int64, out unit-stride along steps")
+    if out is not None and step is None:
+        raise RuntimeError("out needs the step counter")
+    p = _lib.DecodeGreedyParams(batch=logits.shape[0], vocab=logits.shape[1], io_dtype=_lib.io_dtype(logits),
+                                reserved=0, logits=ptr(logits), tok=ptr(tok), out=ptr(out),
+                                out_stride=0 if out is None else out.stride(0), step=ptr(step), pos=ptr(pos))
+    _lib.call("mtts_decode_greedy", p)
+    return tok
 
 
 class _AddLayerNormFn(torch.autograd.Function):

@@ -403,6 +403,32 @@ def test_cross_attn_block_decode_vs_torch(case, dtype):
         check("out", out, ref, tol(dtype))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_decode_embed_and_greedy_vs_torch(dtype):
+    """Token plumbing of the generation loop: gather-add of the two embeddings and the argmax (lowest index on
+    ties, as torch.argmax on CUDA), with the position / column counters living on the device."""
+    from mamba_tts_project_b200.ops import decode_embed, decode_greedy
+    g = torch.Generator().manual_seed(7)
+    B, D, V, L = 9, 64, 777, 40
+    te, pe = torch.randn(V, D, generator=g).cuda(), torch.randn(L, D, generator=g).cuda()
+    tok = torch.randint(0, V, (B,), generator=g).cuda()
+    pos = torch.full((1,), 5, dtype=torch.long, device="cuda")
+    col = torch.full((1,), -1, dtype=torch.long, device="cuda")
+    x = torch.empty(B, D, device="cuda")
+    out = torch.full((B, 6), -7, dtype=torch.long, device="cuda")
+    for step in range(3):
+        decode_embed(tok, pos, te, pe, x, step=col)
+        assert torch.equal(x, te[tok] + pe[5 + step]) and int(col) == step and int(pos) == 5 + step
+        logits = torch.randn(B, V, generator=g).to(dtype).cuda()
+        logits[0, 100] = logits[0, 300] = 50.0   # tie: lowest index wins
+        logits[1, V - 1] = 60.0                  # last column
+        ref = logits.float().argmax(-1)
+        assert int(ref[0]) == 100
+        decode_greedy(logits, tok, out=out, step=col, pos=pos)
+        assert torch.equal(tok, ref) and torch.equal(out[:, step], ref) and int(pos) == 6 + step
+    assert bool((out[:, 3:] == -7).all())
+
+
 def test_cross_attn_block_decode_unsupported_shapes_raise():
     from mamba_tts_project_b200 import cross_attn_block_decode
     from mamba_tts_project_b200.ops import cross_attn_block_decode_supported
