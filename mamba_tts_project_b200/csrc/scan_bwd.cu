@@ -122,31 +122,34 @@ __device__ __forceinline__ void chan_reduce_red(float (&v)[16], int lane, float*
 
 // CC = channels per thread (register tiling of the B / C operands: every LDS of a B / C chunk feeds CC
 // recurrences, and the dB / dC contributions of the CC channels are summed in-thread before the
-// butterfly), kWarps = warps per CTA.
-template <typename T, int NG, int CC, int kWarps, bool kVec>
+// butterfly), kWarps = warps per CTA along the channels, NS = warps along the state dimension: NS chunks of
+// 4 * NG states share one CTA's P / E phases and its dt / dt*u / gy rows (wide states).
+template <typename T, int NG, int CC, int kWarps, bool kVec, int NS = 1>
 struct ScanBwdCfg {
   static constexpr int VE = Io<T>::kVecElems;
-  static constexpr int kThreads = 32 * kWarps;
-  static constexpr int kChan = kThreads / NG * CC;
-  static constexpr int NP = 4 * NG;
+  static constexpr int kCThreads = 32 * kWarps;  // threads of one state chunk
+  static constexpr int kThreads = kCThreads * NS;
+  static constexpr int kChan = kCThreads / NG * CC;
+  static constexpr int NP = 4 * NG * NS;
   static constexpr int kSwz = NG >= 4 ? 3 : NG - 1;
   static constexpr int RS = kTT + 4;
   static constexpr int kVecPerRow = kTT / VE;
   static constexpr int kItems = kChan * kVecPerRow;
   static constexpr int kIt = (kItems + kThreads - 1) / kThreads;
-  static constexpr int kBCItems = NG * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
-  // dt, dtu (-> sGB), gy, ddtA (, y) rows; B, C tiles; group-start states; raw u / delta / dout / z slots
+  static constexpr int kBCItems = NG * NS * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
+  // dt, dtu (-> sGB when NS == 1), gy rows; per state chunk: ddtA (, y) (, sGB when NS > 1) rows; B, C tiles;
+  // group-start states; raw u / delta / dout / z slots
   static constexpr size_t smem_floats(bool recompute_y) {
-    return (recompute_y ? 5 : 4) * (size_t)kChan * RS + 2 * (size_t)kTT * NP + 7 * 4 * CC * (size_t)kThreads +
-           4 * 4 * kIt * (size_t)kThreads;
+    return (3 + NS * ((recompute_y ? 2 : 1) + (NS > 1 ? 1 : 0))) * (size_t)kChan * RS + 2 * (size_t)kTT * NP +
+           7 * 4 * CC * (size_t)kThreads + 4 * 4 * kIt * (size_t)kThreads;
   }
 };
 
 // kRecomputeY: dz needs y = <C, h> and the forward did not hand over its y_pre.
-template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY>
-__global__ void __launch_bounds__(32 * kWarps, (NG == 4 && CC == 1) ? 7 : 1)
+template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY, int NS>
+__global__ void __launch_bounds__(32 * kWarps * NS, (NG == 4 && CC == 1) ? 7 : 1)
 scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
-  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
+  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec, NS>;
   constexpr int VE = Cfg::VE, kChan = Cfg::kChan, NP = Cfg::NP, RS = Cfg::RS;
   constexpr int kIt = Cfg::kIt, kVecPerRow = Cfg::kVecPerRow, kThreads = Cfg::kThreads;
 
@@ -154,9 +157,10 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   float* dts = smem;                      // [kChan][RS] dt
   float* dtus = dts + kChan * RS;         // dt*u, overwritten by sGB
   float* gys = dtus + kChan * RS;         // dout * silu(z)
-  float* das = gys + kChan * RS;          // <w, A*log2e>
-  float* ys = das + kChan * RS;           // <C, h> (only when recomputed here)
-  float* Bs = ys + (kRecomputeY ? kChan * RS : 0);  // [kTT][NP] swizzled
+  float* das = gys + kChan * RS;          // [NS][kChan][RS] <w, A*log2e> over the chunk's states
+  float* ys = das + NS * kChan * RS;      // [NS] <C, h> (only when recomputed here)
+  float* sgs = ys + (kRecomputeY ? NS * kChan * RS : 0);  // [NS] <G, B>; a single chunk reuses the dt*u rows
+  float* Bs = sgs + (NS > 1 ? NS * kChan * RS : 0);      // [kTT][NP] swizzled
   float* Cs = Bs + kTT * NP;
   float* hbs = Cs + kTT * NP;             // [groups 1..7][kThreads][CC][4] state at the start of the group
   // raw u / delta / dout / z vectors of the tile, [tensor][item][thread]: written in P, read back in E by
@@ -166,7 +170,9 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   const int N = p.dstate, L = p.seqlen;
   const int b = blockIdx.y, c0 = blockIdx.x * kChan;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int chl = tid / NG * CC, g = tid % NG;  // first of this thread's CC channels
+  const int sc = tid / Cfg::kCThreads, tic = tid % Cfg::kCThreads;  // state chunk, thread within it
+  const int chl = tic / NG * CC, g = tic % NG;  // first of this thread's CC channels
+  const int n0 = (sc * NG + g) * 4;              // first of this thread's 4 states
   const int c = c0 + chl;
 
   float2 A2[CC][2], Gc[CC][2], dAacc[CC][2];
@@ -174,7 +180,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   for (int k = 0; k < CC; ++k) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int n = g * 4 + i;
+      const int n = n0 + i;
       reinterpret_cast<float*>(A2[k])[i] = (c + k < p.dim && n < N) ? p.A[(int64_t)(c + k) * N + n] * kLog2e : 0.f;
       reinterpret_cast<float*>(Gc[k])[i] = 0.f;
       reinterpret_cast<float*>(dAacc[k])[i] = 0.f;
@@ -185,7 +191,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   // belong to
   using CR = ChanReduce<NG>;
   const int red_idx = CR::prefix(lane) * CR::R;
-  const int red_n = g * 4 + (red_idx >> 2), red_j = red_idx & 3;
+  const int red_n = n0 + (red_idx >> 2), red_j = red_idx & 3;
   const int64_t red_off = ((int64_t)b * N + red_n) * L + red_j;
   const bool red_ok = red_n < N;
 
@@ -223,16 +229,16 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     for (int k = 0; k < CC; ++k) {
       float hv[4] = {0.f, 0.f, 0.f, 0.f};
       if (c + k < p.dim) {
-        const float* ck = p.checkpoints + (((int64_t)b * p.dim + c + k) * nchunks + tile) * N + g * 4;
+        const float* ck = p.checkpoints + (((int64_t)b * p.dim + c + k) * nchunks + tile) * N + n0;
         if ((N & 3) == 0) {
-          if (g * 4 < N) {
+          if (n0 < N) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(ck));
             hv[0] = v.x; hv[1] = v.y; hv[2] = v.z; hv[3] = v.w;
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (g * 4 + i < N) hv[i] = ck[i];
+            if (n0 + i < N) hv[i] = ck[i];
         }
       }
       ck4[k] = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -317,10 +323,11 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     // ---- M ----------------------------------------------------------------------------------------
     {
       const float* dtr = dts + chl * RS;
-      float* dur = dtus + chl * RS;
+      const float* dur = dtus + chl * RS;
       const float* gyr = gys + chl * RS;
-      float* yr = ys + chl * RS;
-      float* dar = das + chl * RS;
+      float* yr = ys + (sc * kChan + chl) * RS;
+      float* dar = das + (sc * kChan + chl) * RS;
+      float* sgr = NS > 1 ? sgs + (sc * kChan + chl) * RS : dtus + chl * RS;
       float* hb = hbs + tid * (4 * CC);
 
       float2 h[CC][2];
@@ -342,7 +349,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           dtv[k][0] = d4.x; dtv[k][1] = d4.y; dtv[k][2] = d4.z; dtv[k][3] = d4.w;
           duv[k][0] = x4.x; duv[k][1] = x4.y; duv[k][2] = x4.z; duv[k][3] = x4.w;
         }
-        const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
+        const int off = ((sc * NG + g) ^ ((s >> 1) & Cfg::kSwz)) << 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 Bv = lds128(Bs + (4 * s + j) * NP + off);
@@ -371,7 +378,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           duv[k][0] = x4.x; duv[k][1] = x4.y; duv[k][2] = x4.z; duv[k][3] = x4.w;
           gyv[k][0] = g4.x; gyv[k][1] = g4.y; gyv[k][2] = g4.z; gyv[k][3] = g4.w;
         }
-        const int off = (g ^ ((s >> 1) & Cfg::kSwz)) << 2;
+        const int off = ((sc * NG + g) ^ ((s >> 1) & Cfg::kSwz)) << 2;
         const float* Bt = Bs + 4 * s * NP + off;
         const float* Ct = Cs + 4 * s * NP + off;
 
@@ -454,7 +461,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
         }
 #pragma unroll
         for (int k = 0; k < CC; ++k) {
-          slice_reduce_store<NG>(sgb[k], g, dur + k * RS + 4 * s);
+          slice_reduce_store<NG>(sgb[k], g, sgr + k * RS + 4 * s);
           slice_reduce_store<NG>(dda[k], g, dar + k * RS + 4 * s);
         }
         {
@@ -498,9 +505,20 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
 #pragma unroll
         for (int i = 0; i < VE; i += 4) {
           const float4 q0 = lds128(dts + ich * RS + it + i);
-          const float4 q1 = lds128(dtus + ich * RS + it + i);
-          const float4 q2 = lds128(ys + ich * RS + it + i);
-          const float4 q3 = lds128(das + ich * RS + it + i);
+          float4 q1 = lds128((NS > 1 ? sgs : dtus) + ich * RS + it + i);
+          float4 q2 = kRecomputeY ? lds128(ys + ich * RS + it + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 q3 = lds128(das + ich * RS + it + i);
+#pragma unroll
+          for (int w = 1; w < NS; ++w) {  // the chunks' partial sums over their states
+            const float4 a1 = lds128(sgs + (w * kChan + ich) * RS + it + i);
+            const float4 a3 = lds128(das + (w * kChan + ich) * RS + it + i);
+            q1.x += a1.x; q1.y += a1.y; q1.z += a1.z; q1.w += a1.w;
+            q3.x += a3.x; q3.y += a3.y; q3.z += a3.z; q3.w += a3.w;
+            if constexpr (kRecomputeY) {
+              const float4 a2 = lds128(ys + (w * kChan + ich) * RS + it + i);
+              q2.x += a2.x; q2.y += a2.y; q2.z += a2.z; q2.w += a2.w;
+            }
+          }
           dtv[i] = q0.x; dtv[i + 1] = q0.y; dtv[i + 2] = q0.z; dtv[i + 3] = q0.w;
           sgv[i] = q1.x; sgv[i + 1] = q1.y; sgv[i + 2] = q1.z; sgv[i + 3] = q1.w;
           if constexpr (kRecomputeY) {
@@ -560,18 +578,18 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     if (c + k < p.dim) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (g * 4 + i < N)
-          atomicAdd(p.dA + (int64_t)(c + k) * N + g * 4 + i, reinterpret_cast<const float*>(dAacc[k])[i]);
+        if (n0 + i < N)
+          atomicAdd(p.dA + (int64_t)(c + k) * N + n0 + i, reinterpret_cast<const float*>(dAacc[k])[i]);
     }
   }
 }
 
-template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY>
+template <typename T, int NG, int CC, int kWarps, bool kVec, bool kRecomputeY, int NS>
 static int launch_scan_bwd_y(const mtts_scan_bwd_params& p, cudaStream_t stream) {
-  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec>;
+  using Cfg = ScanBwdCfg<T, NG, CC, kWarps, kVec, NS>;
   const int nchunks = (p.seqlen + MTTS_SCAN_CHUNK - 1) / MTTS_SCAN_CHUNK;
   const size_t smem = sizeof(float) * Cfg::smem_floats(kRecomputeY);
-  auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec, kRecomputeY>;
+  auto kern = scan_bwd_kernel<T, NG, CC, kWarps, kVec, kRecomputeY, NS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -static_cast<int>(e);
   const dim3 grid((p.dim + Cfg::kChan - 1) / Cfg::kChan, p.batch);
@@ -579,11 +597,11 @@ static int launch_scan_bwd_y(const mtts_scan_bwd_params& p, cudaStream_t stream)
   return launch_status();
 }
 
-template <typename T, int NG, int CC, int kWarps, bool kVec>
+template <typename T, int NG, int CC, int kWarps, bool kVec, int NS = 1>
 static int launch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
   // y is only needed for dz; with the forward's y_pre at hand the <C, h> recompute is skipped
-  if (p.z && !p.y_pre) return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, true>(p, stream);
-  return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, false>(p, stream);
+  if (p.z && !p.y_pre) return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, true, NS>(p, stream);
+  return launch_scan_bwd_y<T, NG, CC, kWarps, kVec, false, NS>(p, stream);
 }
 
 template <typename T, bool kVec>
@@ -591,14 +609,18 @@ static int dispatch_scan_bwd_n(const mtts_scan_bwd_params& p, cudaStream_t strea
   const int N = p.dstate;
   if (N <= 4) return launch_scan_bwd<T, 1, 1, 2, kVec>(p, stream);
   if (N <= 8) return launch_scan_bwd<T, 2, 1, 2, kVec>(p, stream);
-  return launch_scan_bwd<T, 4, 2, 1, kVec>(p, stream);
+  if (N <= 16) return launch_scan_bwd<T, 4, 2, 1, kVec>(p, stream);
+  // wide states: 16-state chunks in separate warps of one CTA, sharing its P / E phases and dt / dt*u / gy rows
+  // (C4 shape, bf16: N 32 9.8 ms, N 64 20.1 ms; the time-parallel kernel: 19.2 / 36.6 ms)
+  if (N <= 32) return launch_scan_bwd<T, 4, 2, 1, kVec, 2>(p, stream);
+  return launch_scan_bwd<T, 4, 2, 1, kVec, 4>(p, stream);
 }
 
 template <typename T>
 static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
-  // wide states (this kernel's slice butterflies stop paying beyond 4 slices), or too few channels: the
-  // time-parallel kernel
-  if (p.dstate > 16 || scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_bwd_wide(p, stream);
+  // very wide states or too few channels: the time-parallel kernel
+  static const int seq_max_n = getenv("MTTS_BWD_SEQ_MAX_N") ? atoi(getenv("MTTS_BWD_SEQ_MAX_N")) : 64;
+  if (p.dstate > seq_max_n || scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_bwd_wide(p, stream);
   const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&

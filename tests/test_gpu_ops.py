@@ -102,6 +102,8 @@ SCAN_CASES = [
     (1, 8, 200, 5, {"with_z": False}),        # odd dstate, no gate
     (2, 16, 128, 16, {"with_D": False, "with_bias": False}),
     (1, 4, 64, 16, {}),                       # fewer channels than one CTA group
+    (1, 20, 100, 24, {}),                     # backward: two 16-state warps, the second half empty
+    (2, 16, 96, 40, {"with_init": True}),     # backward: four 16-state warps, ragged
 ]
 
 
@@ -621,7 +623,7 @@ def _canaries_intact(buf, n, pad=4096):
 @pytest.mark.parametrize("impl", ["seq", "wide"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 24, 300, 16), (1, 16, 1, 16), (1, 20, 257, 16), (1, 8, 200, 5),
-                                   (2, 16, 64, 16), (1, 40, 96, 64)],
+                                   (2, 16, 64, 16), (1, 40, 96, 64), (1, 12, 33, 40)],
                          ids=lambda s: "b%dd%dt%dn%d" % s)
 def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatch):
     from mamba_tts_project_b200 import _lib
@@ -671,6 +673,22 @@ def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatc
         y_pre=P(g["ypre"][1]) if T % 2 == 0 else None,   # both dz routes: forward's y / recomputed y
         y_batch_stride=out.stride(0), y_dim_stride=out.stride(1)))
     torch.cuda.synchronize()
+    if T % 2 == 1:
+        # the two dz routes agree: repeat with the forward's y handed over
+        dz2 = torch.empty_like(dz)
+        scratch = {k: torch.zeros_like(g[k][1]) for k in ("dA", "dB", "dC", "dD", "ddb")}
+        du2, dd2 = torch.empty_like(du), torch.empty_like(dd)
+        _lib.call("mtts_selective_scan_bwd", _lib.ScanBwdParams(
+            **common, dout=P(dout), dout_batch_stride=dout.stride(0), dout_dim_stride=dout.stride(1),
+            checkpoints=P(chk), du=P(du2), du_batch_stride=du2.stride(0), du_dim_stride=du2.stride(1),
+            ddelta=P(dd2), ddelta_batch_stride=dd2.stride(0), ddelta_dim_stride=dd2.stride(1),
+            dz=P(dz2), dz_batch_stride=dz2.stride(0), dz_dim_stride=dz2.stride(1),
+            dA=P(scratch["dA"]), dB=P(scratch["dB"]), dC=P(scratch["dC"]), dD=P(scratch["dD"]),
+            ddelta_bias=P(scratch["ddb"]), y_pre=P(g["ypre"][1]),
+            y_batch_stride=out.stride(0), y_dim_stride=out.stride(1)))
+        torch.cuda.synchronize()
+        check("dz (recomputed y vs forward's y)", dz, dz2.float(), tol(dtype))
+        check("du (both routes)", du, du2.float(), 1e-6)
     for name, (buf, view) in g.items():
         assert _canaries_intact(buf, view.numel()), f"{name}: write outside the tensor"
         assert torch.isfinite(view.float()).all(), f"{name}: non-finite values"
