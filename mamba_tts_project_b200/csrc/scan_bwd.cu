@@ -619,8 +619,7 @@ static int dispatch_scan_bwd_n(const mtts_scan_bwd_params& p, cudaStream_t strea
 template <typename T>
 static int dispatch_scan_bwd(const mtts_scan_bwd_params& p, cudaStream_t stream) {
   // very wide states or too few channels: the time-parallel kernel
-  static const int seq_max_n = getenv("MTTS_BWD_SEQ_MAX_N") ? atoi(getenv("MTTS_BWD_SEQ_MAX_N")) : 64;
-  if (p.dstate > seq_max_n || scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_bwd_wide(p, stream);
+  if (p.dstate > 64 || scan_use_wide(p.batch, p.dim, p.seqlen)) return dispatch_scan_bwd_wide(p, stream);
   const bool vec = vec_ok<T>(p.u, p.u_batch_stride, p.u_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.delta, p.delta_batch_stride, p.delta_dim_stride, p.seqlen) &&
                    vec_ok<T>(p.B, p.B_batch_stride, p.B_state_stride, p.seqlen) &&

@@ -262,29 +262,30 @@ scan_fwd_kernel(const mtts_scan_fwd_params p, const int nchunks) {
       const float* dtr = dts + chl * RS;
       const float* dur = dtus + chl * RS;
       float* yr = ys + chl * RS;
-#pragma unroll(G * CC <= 8 ? 2 : 1)
-      for (int t4 = 0; t4 < TT; t4 += 4) {
-        // checkpoint: state at the start of every MTTS_SCAN_CHUNK timesteps (what the backward restarts from)
-        if (p.checkpoints && ((t0 + t4) % MTTS_SCAN_CHUNK) == 0 && t0 + t4 < L) {
+      // checkpoint: state at the start of every MTTS_SCAN_CHUNK timesteps (what the backward restarts from);
+      // tiles are exactly one chunk long
+      static_assert(TT == MTTS_SCAN_CHUNK, "one checkpoint per tile");
+      if (p.checkpoints) {
 #pragma unroll
-          for (int k = 0; k < CC; ++k) {
-            if (c + k < p.dim) {
-              float* ck = p.checkpoints +
-                          ((((int64_t)b * p.dim + c + k) * nchunks) + (t0 + t4) / MTTS_SCAN_CHUNK) * N + g * G;
-              if ((N & 3) == 0) {
+        for (int k = 0; k < CC; ++k) {
+          if (c + k < p.dim) {
+            float* ck = p.checkpoints + ((((int64_t)b * p.dim + c + k) * nchunks) + tile) * N + g * G;
+            if ((N & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < G; i += 4)
-                  if (g * G + i < N)
-                    *reinterpret_cast<float4*>(ck + i) =
-                        make_float4(h[k][i / 2].x, h[k][i / 2].y, h[k][i / 2 + 1].x, h[k][i / 2 + 1].y);
-              } else {
+              for (int i = 0; i < G; i += 4)
+                if (g * G + i < N)
+                  *reinterpret_cast<float4*>(ck + i) =
+                      make_float4(h[k][i / 2].x, h[k][i / 2].y, h[k][i / 2 + 1].x, h[k][i / 2 + 1].y);
+            } else {
 #pragma unroll
-                for (int i = 0; i < G; ++i)
-                  if (g * G + i < N) ck[i] = reinterpret_cast<const float*>(h[k])[i];
-              }
+              for (int i = 0; i < G; ++i)
+                if (g * G + i < N) ck[i] = reinterpret_cast<const float*>(h[k])[i];
             }
           }
         }
+      }
+#pragma unroll(G * CC <= 8 ? 2 : 1)
+      for (int t4 = 0; t4 < TT; t4 += 4) {
         float dtv[CC][4], duv[CC][4], yp[CC][4];
 #pragma unroll
         for (int k = 0; k < CC; ++k) {
