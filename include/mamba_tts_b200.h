@@ -317,6 +317,7 @@ int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* p, mtts_str
  * the logits of :254-256), with every counter resident on the device so a step is CUDA-graph replayable:
  *   embed:  x[b, :] = tok_embed[tok[b], :] + pos_embed[*pos, :]  (fp32);  then *step += 1
  *   greedy: tok[b] = argmax_v logits[b, v] (lowest index on ties); out[b, *step] = tok[b];  then *pos += 1
+ *           (rows that already produced eos_id get pad_id instead, see the struct)
  * tok (batch) int64 ids (caller guarantees 0 <= id < vocab rows of tok_embed); pos, step: device int64
  * scalars (step = column of `out` being generated, -1 before the first embed).  dim % 4 == 0.
  * ------------------------------------------------------------------------------------------- */
@@ -341,6 +342,12 @@ typedef struct {
   int64_t out_stride;
   const int64_t* step;
   int64_t* pos;       /* incremented after the argmax, or NULL */
+  /* end of sequence (optional): once a row has produced eos_id it is finished -- the eos itself is kept,
+   * every later token of that row is pad_id, and lengths[b] holds the number of tokens up to and
+   * including the eos.  lengths (batch) int64 must be initialised to -1 (= still running). */
+  int64_t eos_id;     /* < 0: no end-of-sequence handling */
+  int64_t pad_id;
+  int64_t* lengths;   /* required when eos_id >= 0 */
 } mtts_decode_greedy_params;
 int mtts_decode_greedy(const mtts_decode_greedy_params* p, mtts_stream_t stream);
 

@@ -123,7 +123,8 @@ DecodeEmbedParams = _struct("DecodeEmbedParams", """
     i:batch i:dim p:tok p:pos p:tok_embed p:pos_embed p:x p:step""")
 
 DecodeGreedyParams = _struct("DecodeGreedyParams", """
-    i:batch i:vocab i:io_dtype i:reserved p:logits p:tok p:out l:out_stride p:step p:pos""")
+    i:batch i:vocab i:io_dtype i:reserved p:logits p:tok p:out l:out_stride p:step p:pos
+    l:eos_id l:pad_id p:lengths""")
 
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,

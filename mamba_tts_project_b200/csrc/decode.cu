@@ -1149,8 +1149,13 @@ decode_greedy_kernel(const mtts_decode_greedy_params p) {
     for (int w = 1; w < 8; ++w)
       if (bv_s[w] > bv || (bv_s[w] == bv && bi_s[w] < bi)) { bv = bv_s[w]; bi = bi_s[w]; }
     if (bi == 0x7fffffff) bi = 0;  // all NaN / -inf row
-    p.tok[b] = bi;
-    if (p.out) p.out[(int64_t)b * p.out_stride + *p.step] = bi;
+    int64_t t = bi;
+    if (p.eos_id >= 0) {
+      if (p.lengths[b] >= 0) t = p.pad_id;                       // finished earlier
+      else if (t == p.eos_id) p.lengths[b] = (p.step ? *p.step : 0) + 1;  // finishes now, eos kept
+    }
+    p.tok[b] = t;
+    if (p.out) p.out[(int64_t)b * p.out_stride + *p.step] = t;
     if (b == 0 && p.pos) *p.pos += 1;
   }
 }
@@ -1258,6 +1263,7 @@ extern "C" int mtts_decode_embed(const mtts_decode_embed_params* p, mtts_stream_
 extern "C" int mtts_decode_greedy(const mtts_decode_greedy_params* p, mtts_stream_t stream) {
   if (!p || !p->logits || !p->tok) return MTTS_ERR_NULL;
   if (p->out && !p->step) return MTTS_ERR_NULL;
+  if (p->eos_id >= 0 && !p->lengths) return MTTS_ERR_NULL;
   if (p->batch < 0 || p->vocab < 1 || p->batch > 65535) return MTTS_ERR_SHAPE;
   if (p->batch == 0) return MTTS_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

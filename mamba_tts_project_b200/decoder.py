@@ -201,6 +201,22 @@ class GenerationContext:
             self.pos = decoder.pos_embed.weight.detach().float().contiguous()
 
 
+def flatten_codes(codes):
+    """(B, Q, T) codec ids -> the flattened (B, Q*T) order the decoder is trained on: all frames of quantizer 0,
+    then quantizer 1, ... (``train.py:181-182``: ``codec.permute(0, 2, 1).reshape(B, -1)``)."""
+    if codes.dim() != 3:
+        raise ValueError("codes must be (B, Q, T)")
+    return codes.reshape(codes.shape[0], -1)
+
+
+def unflatten_codes(tokens, num_quantizers):
+    """Inverse of ``flatten_codes``: (B, Q*T) generated ids -> (B, Q, T).  A length that is not a multiple of Q
+    (generation stopped inside the last quantizer) is an error rather than a silent truncation."""
+    if tokens.dim() != 2 or tokens.shape[1] % num_quantizers:
+        raise ValueError(f"tokens must be (B, Q*T) with Q = {num_quantizers}; got {tuple(tokens.shape)}")
+    return tokens.reshape(tokens.shape[0], num_quantizers, -1)
+
+
 class MambaTTSDecoder(nn.Module):
     def __init__(self, vocab_size_audio, d_model=512, n_layers=8, n_heads=8, d_ff=2048, d_style=256,
                  max_len=8192, num_quantizers=1, d_state=16, d_conv=4, expand=2):
@@ -217,6 +233,7 @@ class MambaTTSDecoder(nn.Module):
         self._gen_key = None
         self._gen_ctx = None
         self.last_generate_events = None
+        self.last_generate_lengths = None
 
     # ---- teacher-forced path (mamba_decoder.py:120-186) -----------------------------------------
     def forward(self, audio_tokens, text_hidden, z_style, text_mask=None, ref_hidden=None,
@@ -355,12 +372,19 @@ class MambaTTSDecoder(nn.Module):
     @torch.no_grad()
     def generate(self, first_token, n_steps, text_hidden, z_style, text_mask=None, ref_hidden=None,
                  ref_mask=None, start_index=0, temperature=0.0, use_cuda_graph=True, dtype=None,
-                 generator=None):
+                 generator=None, eos_id=None, pad_id=0, check_every=64):
         """Autoregressive loop around ``decode_step`` (greedy when temperature == 0).
 
         first_token (B, 1) int64.  Returns tokens (B, n_steps) int64 (the generated ids).  With
         ``use_cuda_graph`` one decode step is captured once and replayed: the token, the position
-        counter and the per-layer states live in static device buffers, nothing syncs the host."""
+        counter and the per-layer states live in static device buffers, nothing syncs the host.
+
+        ``eos_id``: a row that produces it is finished -- the eos is kept, every later position of the row is
+        ``pad_id`` (and pad is what the finished row feeds back, rows are independent); the loop stops early
+        once all rows are done, looked at every ``check_every`` steps (the only host sync).  The per-row token
+        counts (including the eos; ``n_steps`` for rows that never finished) are left in
+        ``self.last_generate_lengths``.  The ids are in the flattened (B, Q*T) codec order of ``train.py:181-182``;
+        ``unflatten_codes`` turns them into (B, Q, T)."""
         ctx = self.prepare_generation(text_hidden, z_style, text_mask, ref_hidden, ref_mask, dtype)
         B = first_token.shape[0]
         dev = first_token.device
@@ -378,31 +402,53 @@ class MambaTTSDecoder(nn.Module):
         xbuf = torch.empty(B, ctx.tok.shape[1], dtype=torch.float32, device=dev)
         if greedy:
             col.fill_(-1)  # decode_embed bumps it at the start of every step
+        lengths = torch.full((B,), -1, dtype=torch.long, device=dev) if eos_id is not None else None
+        if eos_id is not None:
+            out.fill_(pad_id)  # columns never reached after an early stop
 
         def one_step():
             if greedy:  # token plumbing as two library launches, counters stay on the device
                 ops.decode_embed(tok, pos, ctx.tok, ctx.pos, xbuf, step=col)
                 logits = self._step_core(ctx, xbuf, states)
-                ops.decode_greedy(logits, tok, out=out, step=col, pos=pos)
+                ops.decode_greedy(logits, tok, out=out, step=col, pos=pos, eos_id=eos_id, pad_id=pad_id,
+                                  lengths=lengths)
                 return
             x = (ctx.tok.index_select(0, tok) + ctx.pos.index_select(0, pos)).float()
             logits = self._step_core(ctx, x, states)
             probs = torch.softmax(logits.float() / temperature, dim=-1)
             nxt = torch.multinomial(probs, 1, generator=generator)[:, 0]
+            if eos_id is not None:
+                done = lengths >= 0
+                lengths.copy_(torch.where(~done & (nxt == eos_id), col + 1, lengths))
+                nxt = torch.where(done, torch.full_like(nxt, pad_id), nxt)
             tok.copy_(nxt)
             out.index_copy_(1, col, nxt[:, None])
             pos.add_(1)
             col.add_(1)
 
+        def all_done(i):  # one host sync every check_every steps, only when an eos is in play
+            return eos_id is not None and (i + 1) % check_every == 0 and bool((lengths >= 0).all())
+
+        def finish(n_done):
+            if lengths is not None:
+                self.last_generate_lengths = torch.where(lengths >= 0, lengths, torch.full_like(lengths, n_done))
+            else:
+                self.last_generate_lengths = None
+            return out
+
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         if not use_cuda_graph:
             ev0.record()
-            for _ in range(n_steps):
+            n_done = n_steps
+            for i in range(n_steps):
                 one_step()
+                if all_done(i):
+                    n_done = i + 1
+                    break
             ev1.record()
-            self.last_generate_events = (ev0, ev1, n_steps)
-            return out
+            self.last_generate_events = (ev0, ev1, n_done)
+            return finish(n_done)
 
         # warm up on a side stream (cuBLAS workspaces, lazy module loads), then restore the state
         snap = [(c.clone(), s.clone()) for c, s in states]
@@ -417,13 +463,20 @@ class MambaTTSDecoder(nn.Module):
         tok.copy_(first_token[:, 0])
         pos.fill_(start_index)
         col.fill_(-1 if greedy else 0)
+        if lengths is not None:
+            lengths.fill_(-1)
+            out.fill_(pad_id)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             one_step()
         # capture does not execute: state is still the initial one
         ev0.record()
-        for _ in range(n_steps):
+        n_done = n_steps
+        for i in range(n_steps):
             graph.replay()
+            if all_done(i):
+                n_done = i + 1
+                break
         ev1.record()
-        self.last_generate_events = (ev0, ev1, n_steps)  # steady-state loop only (bench.py)
-        return out
+        self.last_generate_events = (ev0, ev1, n_done)  # steady-state loop only (bench.py)
+        return finish(n_done)

@@ -588,9 +588,11 @@ def decode_embed(tok, pos, tok_embed, pos_embed, x, step=None):
     return x
 
 
-def decode_greedy(logits, tok, out=None, step=None, pos=None):
+def decode_greedy(logits, tok, out=None, step=None, pos=None, eos_id=None, pad_id=0, lengths=None):
     """tok[b] = argmax logits[b] (lowest index on ties), out[b, step] = tok[b]; then pos += 1
-    (``mtts_decode_greedy``).  logits (batch, vocab) fp32 / bf16; tok (batch), out (batch, n) int64."""
+    (``mtts_decode_greedy``).  logits (batch, vocab) fp32 / bf16; tok (batch), out (batch, n) int64.
+    With ``eos_id``: rows that produced it earlier get ``pad_id``; ``lengths`` (batch) int64, -1 while a
+    row is running, receives the token count up to and including the eos."""
     _lib.require_cuda(logits, tok, out, step, pos)
     if not logits.is_contiguous() or logits.dim() != 2 or tok.shape != (logits.shape[0],):
         raise RuntimeError("logits must be contiguous (batch, vocab), tok (batch)")
@@ -598,9 +600,14 @@ def decode_greedy(logits, tok, out=None, step=None, pos=None):
         raise RuntimeError("tok / out must be int64, out unit-stride along steps")
     if out is not None and step is None:
         raise RuntimeError("out needs the step counter")
+    if eos_id is not None and (lengths is None or lengths.dtype != torch.long or lengths.shape != tok.shape):
+        raise RuntimeError("eos_id needs lengths (batch) int64")
+    _lib.require_cuda(lengths)
     p = _lib.DecodeGreedyParams(batch=logits.shape[0], vocab=logits.shape[1], io_dtype=_lib.io_dtype(logits),
                                 reserved=0, logits=ptr(logits), tok=ptr(tok), out=ptr(out),
-                                out_stride=0 if out is None else out.stride(0), step=ptr(step), pos=ptr(pos))
+                                out_stride=0 if out is None else out.stride(0), step=ptr(step), pos=ptr(pos),
+                                eos_id=-1 if eos_id is None else int(eos_id), pad_id=int(pad_id),
+                                lengths=ptr(lengths))
     _lib.call("mtts_decode_greedy", p)
     return tok
 

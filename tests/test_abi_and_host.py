@@ -130,3 +130,15 @@ def test_caller_contract_helpers_cpu():
     tgt[0, :3] = 0
     want = torch.nn.functional.cross_entropy(logits.view(14, 16), tgt.view(14), ignore_index=0)
     assert torch.allclose(mt.codec_ce_loss(logits, tgt), want)
+
+
+def test_flatten_unflatten_codes():
+    from mamba_tts_project_b200 import flatten_codes, unflatten_codes
+    codes = torch.arange(2 * 5 * 7).reshape(2, 5, 7)
+    flat = flatten_codes(codes)
+    assert flat.shape == (2, 35) and torch.equal(flat[0, :7], codes[0, 0]) and torch.equal(flat[1, 7:14], codes[1, 1])
+    assert torch.equal(unflatten_codes(flat, 5), codes)
+    # train.py:181-182 builds the same order from the codec's (B, T, Q) output
+    assert torch.equal(codes.permute(0, 2, 1).permute(0, 2, 1).reshape(2, -1), flat)
+    with pytest.raises(ValueError):
+        unflatten_codes(flat[:, :34], 5)

@@ -267,6 +267,39 @@ def test_decoder_d512_decode_vs_oracle(fused, monkeypatch):
         check("bf16 step logits", torch.cat(got, 1), ref_lg, 4e-2)
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_generate_eos_padding_and_early_stop(graph):
+    """generate(eos_id=...): the eos is kept, later positions of that row are pad (and pad is fed back: rows are
+    independent, so the other row still reproduces the oracle's greedy ids), lengths are reported, and the
+    loop stops at the first check after every row has finished."""
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    g = load_golden("oracle_decoder_small.pt")
+    dec = MambaTTSDecoder(**g["config"]).cuda().eval()
+    dec.load_state_dict(g["state_dict"])
+    c = lambda k: g[k].cuda()
+    ids = g["greedy_ids"]                       # (2, 24) oracle greedy ids
+    eos = int(ids[0, 6])                        # row 0 finishes at step 6 (or earlier if the id repeats)
+    first0 = int((ids[0] == eos).nonzero()[0])
+    hits1 = (ids[1] == eos).nonzero()
+    first1 = int(hits1[0]) if len(hits1) else None
+    kw = dict(text_mask=c("text_mask"), ref_hidden=c("ref_hidden"), use_cuda_graph=graph)
+    out = dec.generate(torch.ones(2, 1, dtype=torch.long, device="cuda"), 24, c("text_hidden"), c("z_style"),
+                       eos_id=eos, pad_id=0, check_every=1000, **kw).cpu()
+    assert torch.equal(out[0, :first0 + 1], ids[0, :first0 + 1]) and bool((out[0, first0 + 1:] == 0).all())
+    if first1 is None:
+        assert torch.equal(out[1], ids[1])
+    else:
+        assert torch.equal(out[1, :first1 + 1], ids[1, :first1 + 1]) and bool((out[1, first1 + 1:] == 0).all())
+    want_len = [first0 + 1, 24 if first1 is None else first1 + 1]
+    assert dec.last_generate_lengths.cpu().tolist() == want_len
+    # early stop: one row only, checked every 4 steps -> stops at the first multiple of 4 past the eos
+    out1 = dec.generate(torch.ones(1, 1, dtype=torch.long, device="cuda"), 24, c("text_hidden")[:1], c("z_style")[:1],
+                        text_mask=c("text_mask")[:1], ref_hidden=c("ref_hidden")[:1], use_cuda_graph=graph,
+                        eos_id=eos, pad_id=0, check_every=4).cpu()
+    assert dec.last_generate_events[2] == ((first0 + 1 + 3) // 4) * 4
+    assert torch.equal(out1[0, :first0 + 1], ids[0, :first0 + 1]) and bool((out1[0, first0 + 1:] == 0).all())
+
+
 def test_decoder_multi_quantizer_tokens():
     cfg = dict(vocab_size_audio=32, d_model=64, n_layers=1, n_heads=4, d_ff=64, d_style=16,
                max_len=64, num_quantizers=3)

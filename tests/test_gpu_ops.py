@@ -429,6 +429,17 @@ def test_decode_embed_and_greedy_vs_torch(dtype):
         decode_greedy(logits, tok, out=out, step=col, pos=pos)
         assert torch.equal(tok, ref) and torch.equal(out[:, step], ref) and int(pos) == 6 + step
     assert bool((out[:, 3:] == -7).all())
+    # end of sequence: eos kept, pad afterwards, lengths recorded once
+    lengths = torch.full((B,), -1, dtype=torch.long, device="cuda")
+    col.fill_(0)
+    for step, hot in enumerate((5, 9, 5)):
+        logits = torch.zeros(B, V, device="cuda").to(dtype)
+        logits[:, 3] = 1.0
+        logits[2, hot] = 9.0                      # row 2 says 5, 9, 5; eos = 9
+        decode_greedy(logits, tok, out=out, step=col, eos_id=9, pad_id=1, lengths=lengths)
+        col.add_(1)
+    assert out[2, :3].tolist() == [5, 9, 1] and int(lengths[2]) == 2
+    assert out[0, :3].tolist() == [3, 3, 3] and int(lengths[0]) == -1
 
 
 def test_cross_attn_block_decode_unsupported_shapes_raise():
