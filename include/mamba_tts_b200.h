@@ -401,6 +401,39 @@ typedef struct {
 int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * length_regulate_fwd / length_regulate_bwd -- LengthRegulator.forward of the style pipeline next to the
+ * decoder (style_cross_attention.py:144-198): phoneme rows repeated by their durations.
+ *   dur[b, t] = max(round_half_even(durations[b, t]), 0);  output_lengths[b] = sum_t dur[b, t]
+ *   expanded[b, f, :] = hidden[b, t(f), :] with t(f) the phoneme whose frame range contains f, for
+ *   f < min(output_lengths[b], max_len); zeros beyond.  Every element of expanded is written.
+ *   frame_index (batch, max_len) int32, optional: t(f), -1 for padding.
+ * hidden (batch, t_text, dim), expanded (batch, max_len, dim) contiguous in the io dtype; durations fp32.
+ * Backward: dhidden[b, t, :] = sum over the frames of phoneme t (inside max_len) of dexpanded[b, f, :];
+ * every element of dhidden is written.  t_text <= 8192.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, t_text, dim, max_len;
+  int32_t io_dtype;
+  int32_t reserved;
+  const void* hidden;
+  const float* durations;
+  void* expanded;
+  int64_t* output_lengths; /* (batch) or NULL */
+  int32_t* frame_index;    /* (batch, max_len) or NULL */
+} mtts_length_regulate_fwd_params;
+int mtts_length_regulate_fwd(const mtts_length_regulate_fwd_params* p, mtts_stream_t stream);
+
+typedef struct {
+  int32_t batch, t_text, dim, max_len;
+  int32_t io_dtype;
+  int32_t reserved;
+  const float* durations;
+  const void* dexpanded;
+  void* dhidden;
+} mtts_length_regulate_bwd_params;
+int mtts_length_regulate_bwd(const mtts_length_regulate_bwd_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * skinny_linear -- decode_step's projections for m <= 64 rows in one launch:
  *     out = act( A @ W^T + bias ),  A = a                                   (ln_mode == 0)
  *                                   A = FiLM(LN(x + delta))                 (ln_mode == 1)

@@ -126,11 +126,19 @@ DecodeGreedyParams = _struct("DecodeGreedyParams", """
     i:batch i:vocab i:io_dtype i:reserved p:logits p:tok p:out l:out_stride p:step p:pos
     l:eos_id l:pad_id p:lengths""")
 
+LengthRegulateFwdParams = _struct("LengthRegulateFwdParams", """
+    i:batch i:t_text i:dim i:max_len i:io_dtype i:reserved
+    p:hidden p:durations p:expanded p:output_lengths p:frame_index""")
+
+LengthRegulateBwdParams = _struct("LengthRegulateBwdParams", """
+    i:batch i:t_text i:dim i:max_len i:io_dtype i:reserved p:durations p:dexpanded p:dhidden""")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
-                 GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams]
+                 GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
+                 LengthRegulateFwdParams, LengthRegulateBwdParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -149,6 +157,8 @@ ENTRY_POINTS = {
     "mtts_cross_attn_block_decode": CrossAttnBlockParams,
     "mtts_decode_embed": DecodeEmbedParams,
     "mtts_decode_greedy": DecodeGreedyParams,
+    "mtts_length_regulate_fwd": LengthRegulateFwdParams,
+    "mtts_length_regulate_bwd": LengthRegulateBwdParams,
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,

@@ -40,6 +40,8 @@ extern "C" int mtts_sizeof_params(int which) {
     case 13: return (int)sizeof(mtts_cross_attn_block_params);
     case 14: return (int)sizeof(mtts_decode_embed_params);
     case 15: return (int)sizeof(mtts_decode_greedy_params);
+    case 16: return (int)sizeof(mtts_length_regulate_fwd_params);
+    case 17: return (int)sizeof(mtts_length_regulate_bwd_params);
     default: return -1;
   }
 }

@@ -23,7 +23,7 @@ from ._lib import ptr
 __all__ = ["selective_scan_fn", "selective_state_update", "causal_conv1d_fn",
            "causal_conv1d_update", "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode",
            "add_layernorm", "skinny_linear", "gemm_bf16", "bias_gelu", "colsum", "linear",
-           "cross_attn_block_decode", "cross_attn_block_decode_supported", "decode_embed", "decode_greedy"]
+           "cross_attn_block_decode", "cross_attn_block_decode_supported", "decode_embed", "decode_greedy", "length_regulate"]
 
 
 def _unit_last_stride(t):
@@ -610,6 +610,53 @@ def decode_greedy(logits, tok, out=None, step=None, pos=None, eos_id=None, pad_i
                                 lengths=ptr(lengths))
     _lib.call("mtts_decode_greedy", p)
     return tok
+
+
+class _LengthRegulateFn(torch.autograd.Function):
+    """``mtts_length_regulate_fwd / _bwd``: frame-level expansion of phoneme rows by their durations."""
+
+    @staticmethod
+    def forward(ctx, hidden, durations, max_len):
+        _lib.require_cuda(hidden, durations)
+        if hidden.dim() != 3 or durations.shape != hidden.shape[:2]:
+            raise RuntimeError("hidden must be (B, T_text, D) and durations (B, T_text)")
+        B, T, D = hidden.shape
+        h = hidden.contiguous()
+        dur = durations.detach().float().contiguous()
+        expanded = torch.empty(B, max_len, D, dtype=h.dtype, device=h.device)
+        lengths = torch.empty(B, dtype=torch.long, device=h.device)
+        if B > 0 and max_len == 0:  # nothing to expand, but the lengths are still defined
+            lengths.copy_(torch.clamp(torch.round(dur), min=0).long().sum(1))
+        p = _lib.LengthRegulateFwdParams(batch=B, t_text=T, dim=D, max_len=max_len, io_dtype=_lib.io_dtype(h),
+                                         reserved=0, hidden=ptr(h), durations=ptr(dur), expanded=ptr(expanded),
+                                         output_lengths=ptr(lengths), frame_index=None)
+        _lib.call("mtts_length_regulate_fwd", p)
+        ctx.save_for_backward(dur)
+        ctx.meta = (B, T, D, max_len, hidden.dtype)
+        ctx.mark_non_differentiable(lengths)
+        return expanded, lengths
+
+    @staticmethod
+    def backward(ctx, dexp, _dlen):
+        (dur,) = ctx.saved_tensors
+        B, T, D, max_len, dt = ctx.meta
+        g = dexp.to(dt).contiguous()
+        dh = torch.empty(B, T, D, dtype=dt, device=g.device)
+        p = _lib.LengthRegulateBwdParams(batch=B, t_text=T, dim=D, max_len=max_len, io_dtype=_lib.io_dtype(g),
+                                         reserved=0, durations=ptr(dur), dexpanded=ptr(g), dhidden=ptr(dh))
+        _lib.call("mtts_length_regulate_bwd", p)
+        return dh, None, None
+
+
+def length_regulate(hidden, durations, max_len=None):
+    """``LengthRegulator.forward`` (``style_cross_attention.py:155-198``): (expanded (B, max_len, D),
+    output_lengths (B,) int64).  ``max_len=None`` takes the longest row of the batch, which -- exactly as in
+    the reference (``:178-179``) -- costs one host sync; pass it to stay asynchronous."""
+    if max_len is None:
+        _lib.require_cuda(hidden, durations)
+        dur = torch.clamp(torch.round(durations.detach().float()), min=0).long()
+        max_len = int(dur.sum(dim=1).max().item()) if dur.shape[0] > 0 else 0
+    return _LengthRegulateFn.apply(hidden, durations, int(max_len))
 
 
 class _AddLayerNormFn(torch.autograd.Function):

@@ -442,6 +442,50 @@ def test_decode_embed_and_greedy_vs_torch(dtype):
     assert out[0, :3].tolist() == [3, 3, 3] and int(lengths[0]) == -1
 
 
+@pytest.mark.parametrize("name", ["small", "truncated", "padded", "zeros"])
+def test_length_regulator_matches_reference_vectors(name):
+    """Bit-exact against outputs of the reference's own LengthRegulator (style_cross_attention.py:144-198),
+    generated by oracle/make_golden_length_regulator.py."""
+    from mamba_tts_project_b200 import LengthRegulator
+    g = load_golden(f"ref_length_regulator_{name}.pt")
+    exp, lens = LengthRegulator()(g["hidden"].cuda(), g["durations"].cuda(), max_len=g["max_len"])
+    assert torch.equal(exp.cpu(), g["expanded"]) and torch.equal(lens.cpu(), g["output_lengths"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(4, 37, 512, None), (2, 300, 256, 700), (3, 5, 20, None), (1, 1, 8, 3), (2, 0, 16, 5)],
+                         ids=["d512", "long_truncated", "unaligned_dim", "one_phoneme", "no_phonemes"])
+def test_length_regulator_fwd_bwd_vs_oracle(shape, dtype):
+    from mamba_tts_project_b200.ops import length_regulate
+    from oracle.length_regulator_ref import length_regulator_ref
+    B, T, D, max_len = shape
+    gen = torch.Generator().manual_seed(B * 100 + T)
+    hidden = torch.randn(B, T, D, generator=gen).to(dtype)
+    durations = torch.rand(B, T, generator=gen) * 5.0
+    if T > 2:
+        durations[:, 1] = 0.2   # -> 0 frames
+    hr = hidden.detach().float().clone().requires_grad_()
+    ref, ref_len = length_regulator_ref(hr, durations, max_len)
+    hg = hidden.detach().cuda().requires_grad_()
+    out, lens = length_regulate(hg, durations.cuda(), max_len=max_len)
+    assert out.dtype == dtype and out.shape == ref.shape
+    assert torch.equal(out.float().cpu(), ref.detach()) and torch.equal(lens.cpu(), ref_len)   # a gather: exact
+    if ref.numel() == 0 or T == 0:
+        return
+    dout = torch.randn(ref.shape, generator=gen).to(dtype)
+    ref.backward(dout.float())
+    out.backward(dout.cuda())
+    check("d hidden", hg.grad, hr.grad, 1e-6 if dtype == torch.float32 else 1e-2)
+
+
+def test_length_regulator_errors():
+    from mamba_tts_project_b200.ops import length_regulate
+    with pytest.raises(RuntimeError):   # CUDA only, no CPU path
+        length_regulate(torch.randn(1, 2, 4), torch.ones(1, 2))
+    with pytest.raises(RuntimeError):
+        length_regulate(torch.randn(1, 2, 4, device="cuda"), torch.ones(1, 3, device="cuda"))
+
+
 def test_cross_attn_block_decode_unsupported_shapes_raise():
     from mamba_tts_project_b200 import cross_attn_block_decode
     from mamba_tts_project_b200.ops import cross_attn_block_decode_supported

@@ -142,3 +142,14 @@ def test_decoder_three_dim_tokens_and_errors():
     assert out.shape == (2, 15, 32)
     with pytest.raises(ValueError):
         dec(torch.zeros(2, dtype=torch.long), torch.randn(2, 4, 32), torch.randn(2, 16))
+
+
+# ---- LengthRegulator: the oracle against vectors produced by the reference class itself ----------
+@pytest.mark.parametrize("name", ["small", "truncated", "padded", "zeros"])
+def test_length_regulator_oracle_matches_reference_vectors(name):
+    from oracle.length_regulator_ref import length_regulator_ref
+    g = load_golden(f"ref_length_regulator_{name}.pt")
+    exp, lens = length_regulator_ref(g["hidden"], g["durations"], g["max_len"])
+    assert torch.equal(exp, g["expanded"]) and torch.equal(lens, g["output_lengths"])
+    if name == "small":  # half-way durations round to even: 2.5 -> 2, 3.5 -> 4 (torch.round)
+        assert torch.equal(exp[0, :2], g["hidden"][0, 0].expand(2, -1)) and torch.equal(exp[0, 2], g["hidden"][0, 1])
