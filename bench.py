@@ -211,7 +211,20 @@ def extra_decode(cfg, steps=512):
         dtm = time.perf_counter() - t0
         e0, e1, ns = model.last_generate_events
         loop_ms = e0.elapsed_time(e1) / ns
+        # algorithmic HBM bytes of one step: per layer the conv / SSM states read + written, the
+        # cached K and V read once, every weight read once; plus the head
+        e = 2 if dt == torch.bfloat16 else 4
+        D, L = cfg["d_model"], cfg["n_layers"]
+        Di, N, W = 2 * D, cfg["d_state"], 4
+        t_kv = cfg["t_text"]
+        layer_params = sum(p.numel() for p in model.layers[0].parameters())
+        step_bytes = L * (2 * B * Di * N * 4 + 2 * B * Di * W * e + 2 * B * t_kv * D * e + e * layer_params) \
+            + e * (cfg["vocab"] * D)
+        peak, _ = measured_peaks()
         res[name] = {"tokens_per_s": round(B * steps / dtm, 1), "ms_per_step": round(dtm / steps * 1e3, 4),
+                     "algorithmic_bytes_per_step": step_bytes,
+                     "steady_state_GBs": round(step_bytes / loop_ms / 1e6, 1),
+                     "steady_state_frac_hbm": round(step_bytes / loop_ms / 1e6 / peak, 4),
                      "steps": steps, "batch": B,
                      "includes": "whole generate(): K/V + FiLM precompute, warm-up step, graph capture, replay",
                      "steady_state_ms_per_step": round(loop_ms, 4),

@@ -138,10 +138,10 @@ struct ScanBwdCfg {
   static constexpr int kIt = (kItems + kThreads - 1) / kThreads;
   static constexpr int kBCItems = NG * NS * kVecPerRow;  // (4-row chunk, 16-byte vector) per tensor
   // dt, dtu (-> sGB when NS == 1), gy rows; per state chunk: ddtA (, y) (, sGB when NS > 1) rows; B, C tiles;
-  // group-start states; raw u / delta / dout / z slots
+  // group-start states; raw u / delta / dout / z slots + two tiles of the forward's y
   static constexpr size_t smem_floats(bool recompute_y) {
     return (3 + NS * ((recompute_y ? 2 : 1) + (NS > 1 ? 1 : 0))) * (size_t)kChan * RS + 2 * (size_t)kTT * NP +
-           7 * 4 * CC * (size_t)kThreads + 4 * 4 * kIt * (size_t)kThreads;
+           7 * 4 * CC * (size_t)kThreads + 6 * 4 * kIt * (size_t)kThreads;
   }
 };
 
@@ -210,8 +210,28 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
   // one tile ahead, during the previous tile's E phase, so they are never live across M.
   uint4 ur[kIt], dr[kIt], gr[kIt], zr[kIt];
   float4 ck4[CC];
+  // the forward's y of a tile (for dz) goes global -> shared by cp.async into a slot of its own parity: it is
+  // requested a whole tile before E reads it and never occupies a register
+  const T* yb = (!kRecomputeY && zb && p.y_pre) ? reinterpret_cast<const T*>(p.y_pre) + (int64_t)b * p.y_batch_stride
+                                                 : nullptr;
   auto fetch_tile = [&](int tile) {
     const int t0 = tile * kTT;
+    if (yb) {
+#pragma unroll
+      for (int k = 0; k < kIt; ++k) {
+        const int idx = tid + k * kThreads;
+        const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
+        const int cc = c0 + ich;
+        uint4* slot = raws + ((4 + (tile & 1)) * kIt + k) * kThreads;
+        if (idx < Cfg::kItems && cc < p.dim && t0 + it < L) {
+          if constexpr (kVec) cp_async16(slot, yb + (int64_t)cc * p.y_dim_stride + t0 + it);
+          else *slot = load_raw<T, false>(yb + (int64_t)cc * p.y_dim_stride, t0 + it, L);
+        } else {
+          *slot = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      cp_async_commit();
+    }
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
       const int idx = tid + k * kThreads;
@@ -475,18 +495,8 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     __syncthreads();
 
     // ---- E ----------------------------------------------------------------------------------------
-    // y_pre of this tile and the next tile's raw inputs / checkpoints are requested now
-    uint4 ey[kIt];
-    const T* yb = p.y_pre ? reinterpret_cast<const T*>(p.y_pre) + (int64_t)b * p.y_batch_stride : nullptr;
-#pragma unroll
-    for (int k = 0; k < kIt; ++k) {
-      const int idx = tid + k * kThreads;
-      const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
-      const int cc = c0 + ich;
-      ey[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (!kRecomputeY && zb && yb && idx < Cfg::kItems && cc < p.dim)
-        ey[k] = load_raw<T, kVec>(yb + (int64_t)cc * p.y_dim_stride, t0 + it, L);
-    }
+    // the next tile's raw inputs / checkpoints / y are requested now (this tile's y sits in the other slot)
+    cp_async_wait_all();
     if (tile > 0) fetch_tile(tile - 1);
 #pragma unroll
     for (int k = 0; k < kIt; ++k) {
@@ -526,7 +536,12 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           }
           dav[i] = q3.x; dav[i + 1] = q3.y; dav[i + 2] = q3.z; dav[i + 3] = q3.w;
         }
-        if constexpr (!kRecomputeY) Io<T>::unpack(ey[k], yv);  // the forward's y already holds D u
+        if constexpr (!kRecomputeY) {  // the forward's y already holds D u
+          if (yb) Io<T>::unpack(raws[((4 + (tile & 1)) * kIt + k) * kThreads], yv);
+          else
+#pragma unroll
+            for (int i = 0; i < VE; ++i) yv[i] = 0.f;
+        }
         float o_du[VE], o_dd[VE], o_dz[VE];
 #pragma unroll
         for (int i = 0; i < VE; ++i) {

@@ -54,6 +54,14 @@ __device__ __forceinline__ float2 shfl_down2(float2 v, int d) {
   return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
 }
 
+// ---- cp.async (LDGSTS) staging into thread-private shared slots ----------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- pair-interleaved tile: two dstate rows (2p, 2p+1) share one smem row ---------------------------
 // element (n, t) lives at  (n/2)*kRow + (t/kItems)*kSeg + (t%kItems)*2 + (n&1):  a lane reads its
 // kItems timesteps of BOTH rows as kItems float2 with LDS.128; kSeg = 2*kItems + 4 keeps the eight

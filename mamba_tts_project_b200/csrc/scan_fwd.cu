@@ -57,14 +57,6 @@ __device__ __forceinline__ void store_raw(T* __restrict__ row, int t, int len, c
   }
 }
 
-// ---- cp.async (LDGSTS) staging into thread-private shared slots ----------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // 16 bytes of row[t ..) into *slot: asynchronous when the row is vector-aligned, zeros when absent
 template <typename T, bool kVec>
 __device__ __forceinline__ void stage_raw(uint4* slot, const T* __restrict__ row, int t, int len, bool ok) {
