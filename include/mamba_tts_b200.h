@@ -251,6 +251,13 @@ typedef struct {
   const float* D;       /* (dim) */
   void* y;              /* (batch, dim) */
   int64_t y_batch_stride;
+  /* Optional L2 prefetch for the kernels that follow in the step: prefetch_bytes bytes per batch element
+   * starting at prefetch_a + b * prefetch_bytes (and likewise prefetch_b) are pulled from HBM into L2 once the
+   * kernel's own loads are done -- the decoder passes the layer's cached K and V, which the cross-attention
+   * two launches later then finds in L2 (this kernel itself moves 10 MB and leaves HBM idle).  NULL = none. */
+  const void* prefetch_a;
+  const void* prefetch_b;
+  int64_t prefetch_bytes;
 } mtts_decode_step_params;
 int mtts_mamba_decode_step(const mtts_decode_step_params* p, mtts_stream_t stream);
 

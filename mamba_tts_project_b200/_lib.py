@@ -90,7 +90,8 @@ StateUpdateParams = _struct("StateUpdateParams", """
 DecodeStepParams = _struct("DecodeStepParams", """
     i:batch i:dim i:dstate i:dt_rank i:width i:io_dtype
     p:xz l:xz_batch_stride p:conv_state p:ssm_state p:conv_weight p:conv_bias
-    p:x_proj_w p:dt_proj_w p:dt_bias p:A p:D p:y l:y_batch_stride""")
+    p:x_proj_w p:dt_proj_w p:dt_bias p:A p:D p:y l:y_batch_stride
+    p:prefetch_a p:prefetch_b l:prefetch_bytes""")
 
 CrossAttnDecodeParams = _struct("CrossAttnDecodeParams", """
     i:batch i:heads i:head_dim i:t_kv i:io_dtype

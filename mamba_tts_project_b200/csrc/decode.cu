@@ -384,6 +384,17 @@ __global__ void __launch_bounds__(kStepFastThreads) decode_step_fast_kernel(cons
     y *= silu_f(zg[c]);
     reinterpret_cast<T*>(p.y)[(int64_t)b * p.y_batch_stride + d] = Io<T>::from_f(y);
   }
+  // HBM is idle from here to the cross-attention two launches later: pull this batch element's cached K / V
+  // into L2 (one request per 128-byte line, spread over the cluster's threads)
+  if (p.prefetch_a) {
+    const char* pa = reinterpret_cast<const char*>(p.prefetch_a) + (int64_t)b * p.prefetch_bytes;
+    const char* pb = reinterpret_cast<const char*>(p.prefetch_b) + (int64_t)b * p.prefetch_bytes;
+    for (int64_t off = (int64_t)(rank * kStepFastThreads + tid) * 128; off < p.prefetch_bytes;
+         off += (int64_t)S * kStepFastThreads * 128) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+    }
+  }
   // no CTA may exit while a peer can still read its `part`
   if constexpr (S > 1) cg::this_cluster().sync();
 }

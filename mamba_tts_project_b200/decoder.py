@@ -197,6 +197,8 @@ class GenerationContext:
             self.fused_attention = int(os.environ.get("MTTS_FUSED_ATTENTION", "1")) \
                 if ops.cross_attn_block_decode_supported(dtype, memory.shape[2], self.layers[0].heads,
                                                          memory.shape[1]) else 0
+            # the step kernel pulls the layer's K / V into L2 for the attention that follows (MTTS_PREFETCH_KV=0: off)
+            self.prefetch_kv = os.environ.get("MTTS_PREFETCH_KV", "1") != "0"
             self.tok = decoder.token_embed.weight.detach().float().contiguous()
             self.pos = decoder.pos_embed.weight.detach().float().contiguous()
 
@@ -295,7 +297,8 @@ class MambaTTSDecoder(nn.Module):
             xz = F.linear(h, lw.mamba["in_proj"], lw.mamba["in_bias"])
             y = ops.mamba_decode_step(xz, conv_state, ssm_state, lw.mamba["conv_w"],
                                       lw.mamba["conv_b"], lw.mamba["x_proj"], lw.mamba["dt_proj"],
-                                      lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"])
+                                      lw.mamba["dt_bias"], lw.mamba["A"], lw.mamba["D"],
+                                      prefetch=(lw.k, lw.v) if ctx.prefetch_kv else None)
             m = F.linear(y, lw.mamba["out_proj"], lw.mamba["out_bias"])
             if ctx.fused_attention == 2:
                 # residual add + LN + q projection + attention + out projection + residual add + LN + FiLM:

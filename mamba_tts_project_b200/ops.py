@@ -470,8 +470,10 @@ def mamba_block_fn(h, in_proj_weight, conv_weight, conv_bias, x_proj_weight, dt_
 # decode-step kernels (inference only)
 # ------------------------------------------------------------------------------------------------
 def mamba_decode_step(xz, conv_state, ssm_state, conv_weight, conv_bias, x_proj_w, dt_proj_w,
-                      dt_bias, A, D, out=None):
+                      dt_bias, A, D, out=None, prefetch=None):
     """The inner part of ``Mamba.step`` in one launch; both states updated IN PLACE.
+    ``prefetch`` = (a, b): two contiguous (batch, ...) tensors of equal size that the kernel pulls into L2
+    after its own loads (the decoder passes the layer's cached K / V for the attention that follows).
     xz (batch, 2*dim); conv_state (batch, dim, width) same dtype; ssm_state (batch, dim, dstate)
     fp32; conv_weight (dim, width) / conv_bias / dt_bias / A / D fp32; x_proj_w (R + 2N, dim) and
     dt_proj_w (dim, R) in xz's dtype.  Returns y (batch, dim)."""
@@ -499,6 +501,14 @@ def mamba_decode_step(xz, conv_state, ssm_state, conv_weight, conv_bias, x_proj_
         ssm_state=ptr(ssm_state), conv_weight=ptr(conv_weight), conv_bias=ptr(conv_bias),
         x_proj_w=ptr(x_proj_w), dt_proj_w=ptr(dt_proj_w), dt_bias=ptr(dt_bias), A=ptr(A), D=ptr(D),
         y=ptr(y), y_batch_stride=y.stride(0))
+    if prefetch is not None:
+        pa, pb = prefetch
+        _lib.require_cuda(pa, pb)
+        if not (pa.is_contiguous() and pb.is_contiguous()) or pa.shape[0] != batch or pb.shape[0] != batch \
+                or pa.numel() * pa.element_size() != pb.numel() * pb.element_size():
+            raise RuntimeError("prefetch tensors must be contiguous (batch, ...) of equal byte size")
+        p.prefetch_a, p.prefetch_b = ptr(pa), ptr(pb)
+        p.prefetch_bytes = pa.numel() * pa.element_size() // batch
     _lib.call("mtts_mamba_decode_step", p)
     return y
 
