@@ -329,6 +329,29 @@ __global__ void __launch_bounds__(kStepFastThreads) decode_step_fast_kernel(cons
     Dv[c] = p.D[d];
   }
 
+  // The kernel's own loads are all in flight now and HBM is idle from here to the cross-attention two launches
+  // later: pull this batch element's cached K / V into L2.  Requested here rather than at the end, because a
+  // kernel does not retire before its prefetches have landed -- this way they overlap the exchange, the state
+  // update and the stores.
+  if (p.prefetch_a) {
+    const char* pa = reinterpret_cast<const char*>(p.prefetch_a) + (int64_t)b * p.prefetch_bytes;
+    const char* pb = reinterpret_cast<const char*>(p.prefetch_b) + (int64_t)b * p.prefetch_bytes;
+    constexpr int kChunk = 16384;  // bytes per bulk request
+    if (p.prefetch_bytes % (S * kChunk) == 0 && ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 15) == 0) {
+      // TMA bulk prefetch: a handful of requests per CTA instead of one LSU request per line
+      const int per_cta = (int)(p.prefetch_bytes / S), nchunk = per_cta / kChunk;
+      if (tid < 2 * nchunk) {
+        const char* src = (tid < nchunk ? pa : pb) + (int64_t)rank * per_cta + (int64_t)(tid % nchunk) * kChunk;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kChunk) : "memory");
+      }
+    } else {
+      for (int64_t off = (int64_t)(rank * kStepFastThreads + tid) * 128; off < p.prefetch_bytes;
+           off += (int64_t)S * kStepFastThreads * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+      }
+    }
+  }
   // all-gather-reduce the partials (over the cluster through DSMEM when S > 1)
   if constexpr (S > 1) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -383,17 +406,6 @@ __global__ void __launch_bounds__(kStepFastThreads) decode_step_fast_kernel(cons
     }
     y *= silu_f(zg[c]);
     reinterpret_cast<T*>(p.y)[(int64_t)b * p.y_batch_stride + d] = Io<T>::from_f(y);
-  }
-  // HBM is idle from here to the cross-attention two launches later: pull this batch element's cached K / V
-  // into L2 (one request per 128-byte line, spread over the cluster's threads)
-  if (p.prefetch_a) {
-    const char* pa = reinterpret_cast<const char*>(p.prefetch_a) + (int64_t)b * p.prefetch_bytes;
-    const char* pb = reinterpret_cast<const char*>(p.prefetch_b) + (int64_t)b * p.prefetch_bytes;
-    for (int64_t off = (int64_t)(rank * kStepFastThreads + tid) * 128; off < p.prefetch_bytes;
-         off += (int64_t)S * kStepFastThreads * 128) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + off));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
-    }
   }
   // no CTA may exit while a peer can still read its `part`
   if constexpr (S > 1) cg::this_cluster().sync();
