@@ -285,7 +285,8 @@ int mtts_cross_attn_decode(const mtts_cross_attn_decode_params* p, mtts_stream_t
  * cross_attn_decode + out_proj Linear + add_layernorm):
  *   x1 = x + delta;  hq = LN(x1; lnq);  q = wq hq + bq;  a = softmax(q k^T / sqrt(head_dim) + mask) v;
  *   o = wo a + bo;   x_out = x1 + o;    out = film_gamma * LN(x_out; lno) + film_beta
- *   x, x_out (batch, d) fp32 residual stream (x_out may alias x); delta (batch, d) io dtype or NULL;
+ *   x, x_out (batch, d) fp32 residual stream (x_out may alias x only when wo is given: the cluster
+ *   synchronises before the write; the front-half variant's CTAs are independent); delta (batch, d) io dtype or NULL;
  *   wq, wo (d, d) row-major [out][in] and bq, bo (d) in the io dtype (nn.MultiheadAttention's
  *   in_proj_weight[0:d] / out_proj); k, v (batch, t_kv, d); mask as in cross_attn_decode;
  *   LN weights / biases and film_gamma / film_beta (batch, d) fp32 (FiLM optional); out (batch, d) io dtype.

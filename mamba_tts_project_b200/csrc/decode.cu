@@ -1254,6 +1254,8 @@ extern "C" int mtts_cross_attn_block_decode(const mtts_cross_attn_block_params* 
   if (!p || !p->x || !p->lnq_weight || !p->lnq_bias || !p->wq || !p->bq || !p->k || !p->v || !p->out)
     return MTTS_ERR_NULL;
   if (p->wo && (!p->bo || !p->lno_weight || !p->lno_bias)) return MTTS_ERR_NULL;
+  // front half: the head CTAs of a batch element are independent and each reads the whole row of x
+  if (!p->wo && p->x_out == p->x) return MTTS_ERR_UNSUPPORTED;
   if ((p->film_gamma == nullptr) != (p->film_beta == nullptr)) return MTTS_ERR_NULL;
   if (p->batch < 0 || p->t_kv < 1 || p->batch > 65535) return MTTS_ERR_SHAPE;
   // one instantiation per supported decoder shape: 8 heads x 64 features, cached rows

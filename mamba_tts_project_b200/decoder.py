@@ -303,11 +303,12 @@ class MambaTTSDecoder(nn.Module):
             if ctx.fused_attention == 2:
                 # residual add + LN + q projection + attention + out projection + residual add + LN + FiLM:
                 # one cluster launch instead of five
-                h = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads, lw.wo,
-                                                lw.bo, lw.ln3, mask=ctx.mask, gamma=lw.gamma, beta=lw.beta)
+                x, h = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads, lw.wo,
+                                                   lw.bo, lw.ln3, mask=ctx.mask, gamma=lw.gamma, beta=lw.beta)
             elif ctx.fused_attention == 1:
                 # residual add + LN + q projection + attention in one launch of independent (batch, head) CTAs
-                a = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads, mask=ctx.mask)
+                x, a = ops.cross_attn_block_decode(x, m, lw.ln2, lw.wq, lw.bq, lw.k, lw.v, lw.heads,
+                                                   mask=ctx.mask)
                 o = F.linear(a, lw.wo, lw.bo)
                 x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
                                          beta=lw.beta, out_dtype=dt, inplace=True)

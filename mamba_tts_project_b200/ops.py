@@ -543,11 +543,15 @@ def cross_attn_block_decode_supported(dtype, d_model, heads, t_kv):
 def cross_attn_block_decode(x, delta, lnq, wq, bq, k, v, heads, wo=None, bo=None, lno=None, mask=None,
                             gamma=None, beta=None, out=None):
     """One launch for the cross-attention branch of a decode step (``mtts_cross_attn_block_decode``):
-    x (batch, d) fp32 residual stream, updated IN PLACE to x + delta + o; delta (batch, d) or None;
+    x (batch, d) fp32 residual stream; delta (batch, d) or None;
     lnq / lno = (weight, bias, eps) of the LayerNorms before the attention / before the FFN; wq, bq, wo,
     bo in the io dtype; k, v (batch, t_kv, d); gamma, beta (batch, d) fp32 FiLM or None.
-    Returns FiLM(LN(x_new; lno)) (batch, d) in the io dtype.  With wo=None only the front half runs:
-    x <- x + delta and the attention output (before the out projection) is returned."""
+    Returns ``(x_new, out)``.  Whole branch (wo given): x_new = x + delta + o, written IN PLACE into x (the
+    8 head CTAs of a batch element are one cluster and synchronise before the write), out =
+    FiLM(LN(x_new; lno)) (batch, d) in the io dtype.  Front half only (wo=None): x_new = x + delta in a NEW
+    tensor -- the head CTAs of a batch element are independent there and all of them read the whole row of x,
+    so the row must not be overwritten by the launch -- and out = the attention output before the out
+    projection."""
     _lib.require_cuda(x, delta, wq, bq, k, v, wo, bo, mask, gamma, beta)
     batch, dm = x.shape
     if x.dtype != torch.float32 or not x.is_contiguous():
@@ -568,15 +572,16 @@ def cross_attn_block_decode(x, delta, lnq, wq, bq, k, v, heads, wo=None, bo=None
     if mask is not None:
         m8 = mask.to(torch.uint8).contiguous() if mask.dtype != torch.uint8 else mask.contiguous()
     o = out if out is not None else torch.empty(batch, dm, device=x.device, dtype=dt)
+    x_new = torch.empty_like(x) if front_only else x
     p = _lib.CrossAttnBlockParams(
         batch=batch, heads=heads, head_dim=dm // heads, t_kv=k.shape[1], io_dtype=_lib.io_dtype(k),
-        eps_q=lnq[2], eps_o=0.0 if front_only else lno[2], x=ptr(x), delta=ptr(delta), x_out=ptr(x),
+        eps_q=lnq[2], eps_o=0.0 if front_only else lno[2], x=ptr(x), delta=ptr(delta), x_out=ptr(x_new),
         lnq_weight=ptr(lnq[0]), lnq_bias=ptr(lnq[1]), wq=ptr(wq), bq=ptr(bq), k=ptr(k), v=ptr(v),
         mask=ptr(m8), wo=ptr(wo), bo=ptr(bo), lno_weight=None if front_only else ptr(lno[0]),
         lno_bias=None if front_only else ptr(lno[1]),
         film_gamma=ptr(gamma), film_beta=ptr(beta), out=ptr(o))
     _lib.call("mtts_cross_attn_block_decode", p)
-    return o
+    return x_new, o
 
 
 def decode_embed(tok, pos, tok_embed, pos_embed, x, step=None):

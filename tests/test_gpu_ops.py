@@ -397,12 +397,22 @@ def test_cross_attn_block_decode_vs_torch(case, dtype):
     xg = x.cuda()
     for with_delta in (True, False):
         xg = x.cuda() if with_delta else x1.cuda()
-        out = cross_attn_block_decode(xg, dev(delta) if with_delta else None,
-                                      (dev(lnq[0]), dev(lnq[1]), lnq[2]), dev(wq), dev(bq), dev(k), dev(v), heads,
-                                      dev(wo), dev(bo), (dev(lno[0]), dev(lno[1]), lno[2]), mask=dev(mask),
-                                      gamma=dev(gamma), beta=dev(beta))
-        check("x_out", xg, x2, tol(dtype))
+        xn, out = cross_attn_block_decode(xg, dev(delta) if with_delta else None,
+                                          (dev(lnq[0]), dev(lnq[1]), lnq[2]), dev(wq), dev(bq), dev(k), dev(v), heads,
+                                          dev(wo), dev(bo), (dev(lno[0]), dev(lno[1]), lno[2]), mask=dev(mask),
+                                          gamma=dev(gamma), beta=dev(beta))
+        assert xn.data_ptr() == xg.data_ptr()     # whole branch: in place (cluster-synchronised)
+        check("x_out", xn, x2, tol(dtype))
         check("out", out, ref, tol(dtype))
+        # front half only: x + delta in a new tensor (x untouched), attention output before the out projection
+        xg = x.cuda() if with_delta else x1.cuda()
+        keep = xg.clone()
+        xn, att = cross_attn_block_decode(xg, dev(delta) if with_delta else None,
+                                          (dev(lnq[0]), dev(lnq[1]), lnq[2]), dev(wq), dev(bq), dev(k), dev(v), heads,
+                                          mask=dev(mask))
+        assert xn.data_ptr() != xg.data_ptr() and torch.equal(xg, keep)
+        check("front x_out", xn, x1, 1e-6)
+        check("front attention", att, a, tol(dtype))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
@@ -484,6 +494,30 @@ def test_length_regulator_errors():
         length_regulate(torch.randn(1, 2, 4), torch.ones(1, 2))
     with pytest.raises(RuntimeError):
         length_regulate(torch.randn(1, 2, 4, device="cuda"), torch.ones(1, 3, device="cuda"))
+
+
+def test_cross_attn_block_decode_front_half_many_waves():
+    """More batch elements than one wave of CTAs holds (4 CTAs/SM x 148 SMs = 74 batch elements): head CTAs of
+    one batch element start in different waves, so the launch must not write into the row it reads."""
+    from mamba_tts_project_b200 import cross_attn_block_decode
+    import torch.nn.functional as F
+    batch, Tk, dm, heads, dt = 300, 64, 512, 8, torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *sh: torch.randn(*sh, generator=g)
+    x, delta = rn(batch, dm).cuda(), rn(batch, dm).to(dt).cuda()
+    ln = (torch.ones(dm).cuda(), torch.zeros(dm).cuda(), 1e-5)
+    wq, bq = (rn(dm, dm) * dm ** -0.5).to(dt).cuda(), torch.zeros(dm).to(dt).cuda()
+    k, v = rn(batch, Tk, dm).to(dt).cuda(), rn(batch, Tk, dm).to(dt).cuda()
+    xn, att = cross_attn_block_decode(x, delta, ln, wq, bq, k, v, heads)
+    x1 = x + delta.float()
+    check("x_out", xn, x1, 1e-6)
+    # the same rows one batch element at a time must give the same attention output bit for bit
+    xn1, att1 = cross_attn_block_decode(x[:8].contiguous(), delta[:8].contiguous(), ln, wq, bq, k[:8].contiguous(),
+                                        v[:8].contiguous(), heads)
+    assert torch.equal(att[:8], att1) and torch.equal(xn[:8], xn1)
+    xn2, att2 = cross_attn_block_decode(x[-8:].contiguous(), delta[-8:].contiguous(), ln, wq, bq,
+                                        k[-8:].contiguous(), v[-8:].contiguous(), heads)
+    assert torch.equal(att[-8:], att2)
 
 
 def test_cross_attn_block_decode_unsupported_shapes_raise():
