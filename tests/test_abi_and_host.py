@@ -142,3 +142,66 @@ def test_flatten_unflatten_codes():
     assert torch.equal(codes.permute(0, 2, 1).permute(0, 2, 1).reshape(2, -1), flat)
     with pytest.raises(ValueError):
         unflatten_codes(flat[:, :34], 5)
+
+
+def _write_reference_style(tmp_path, parallel):
+    """Files exactly as the reference's two writers leave them (preprocess.py:272-305 pickles numpy arrays and
+    lists through torch.save; preprocess_parallel.py:307-329 stores tensors)."""
+    import json
+    import numpy as np
+    tdir = tmp_path / "tensors"
+    tdir.mkdir()
+    g = torch.Generator().manual_seed(3)
+    meta, truth = [], {}
+    for i, (name, T, Tt) in enumerate((("spk1/utt 01", 7, 5), ("spk2/utt_02", 4, 9), ("spk3/no audio", 0, 3))):
+        safe = name.replace("/", "_").replace(" ", "_")
+        ph = torch.randint(1, 80, (Tt,), generator=g).tolist()
+        style = torch.randn(16, generator=g).numpy()
+        codec = torch.randint(1, 1024, (1, T, 5), generator=g).numpy() if T else None
+        spk = torch.randn(1, 8, generator=g).numpy()
+        if parallel:
+            torch.save(torch.tensor(ph, dtype=torch.long), tdir / f"{safe}_phonemes.pt")
+            torch.save(torch.from_numpy(style), tdir / f"{safe}_style.pt")
+            if codec is not None:
+                torch.save(torch.from_numpy(codec), tdir / f"{safe}_codec.pt")
+        else:
+            torch.save(ph, tdir / f"{safe}_phonemes.pt")
+            torch.save(style, tdir / f"{safe}_style.pt")
+            if codec is not None:
+                torch.save(codec, tdir / f"{safe}_codec.pt")
+                torch.save(spk, tdir / f"{safe}_spk_emb.pt")
+        meta.append({"item_name": name, "text": "t", "phonemes": [], "phoneme_str": "", "ph2word": [],
+                     "style_prompt": "calm"})
+        truth[name] = (ph, style, codec)
+    with open(tmp_path / "metadata.json", "w") as f:
+        json.dump(meta, f, indent=2)
+    return truth
+
+
+@pytest.mark.parametrize("parallel", [False, True], ids=["sequential_writer", "parallel_writer"])
+def test_preprocessed_reader_and_collate(tmp_path, parallel):
+    from mamba_tts_project_b200.data import PreprocessedItems, collate_codec_batch
+    truth = _write_reference_style(tmp_path, parallel)
+    ds = PreprocessedItems(str(tmp_path))
+    assert len(ds) == 2                                   # the utterance without a codec file is dropped
+    assert len(PreprocessedItems(str(tmp_path), require_codec=False)) == 3
+    items = [ds[0], ds[1]]
+    for it in items:
+        ph, style, codec = truth[it["item_name"]]
+        assert it["phoneme_ids"].tolist() == ph and it["codec"].shape == (codec.shape[1], 5)
+        assert torch.equal(it["codec"], torch.from_numpy(codec)[0].long())
+        assert torch.allclose(it["style"], torch.from_numpy(style))
+        assert (it["spk_emb"] is None) == parallel
+    batch = collate_codec_batch(items)
+    # train.py:181-185 on the zero-padded (B, T, C) codec batch
+    codec = torch.zeros(2, 7, 5, dtype=torch.long)
+    codec[0] = items[0]["codec"]
+    codec[1, :4] = items[1]["codec"]
+    want_3d = codec.permute(0, 2, 1)
+    assert torch.equal(batch["audio_tokens_3d"], want_3d)
+    assert torch.equal(batch["audio_tokens"], want_3d.reshape(2, -1))
+    assert torch.equal(batch["codec_pad_mask"], (want_3d == 0).reshape(2, -1))
+    assert batch["codec_lengths"].tolist() == [7, 4]
+    assert batch["phoneme_ids"].shape == (2, 9) and batch["text_mask"].sum(1).tolist() == [5, 9]
+    assert torch.equal(mt.unflatten_codes(batch["audio_tokens"], 5), want_3d)
+    assert batch["style"].shape == (2, 16) and (batch["spk_emb"] is None) == parallel
