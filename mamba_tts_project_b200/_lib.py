@@ -218,10 +218,23 @@ def ptr(t):
 
 
 def require_cuda(*tensors):
+    """Every operand is a CUDA tensor on ONE device, and that device is the current one: ``call`` enqueues
+    on the current device's current stream, so operands living elsewhere would be a fault (or a silent peer
+    access with the wrong stream ordering).  Wrap calls for another GPU in ``torch.cuda.device(...)``."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("mamba_tts_project_b200 ops are CUDA-only (sm_100a); got a "
                                f"{t.device} tensor.  There is no CPU path.")
+        if dev is None:
+            dev = t.device
+            if dev.index != torch.cuda.current_device():
+                raise RuntimeError(f"operands live on {dev} but the current device is "
+                                   f"cuda:{torch.cuda.current_device()}; use torch.cuda.device({dev.index})")
+        elif t.device != dev:
+            raise RuntimeError(f"operands on different devices: {dev} and {t.device}")
 
 
 def call(name: str, params) -> None:

@@ -22,9 +22,25 @@ def _safe_name(item_name: str) -> str:
     return item_name.replace("/", "_").replace(" ", "_")   # preprocess.py:275 / preprocess_parallel.py:309
 
 
-def _load(path):
-    # the sequential writer pickles numpy arrays and Python lists through torch.save (preprocess.py:278-289)
-    obj = torch.load(path, map_location="cpu", weights_only=False)
+def _numpy_safe_globals():
+    """The globals a pickled ``numpy.ndarray`` needs (what the sequential writer stores through
+    ``torch.save``, ``preprocess.py:278-289``) -- allow-listed so ``weights_only=True`` can read them."""
+    core = getattr(np, "_core", None) or np.core
+    out = [core.multiarray._reconstruct, np.ndarray, np.dtype]
+    out += [type(np.dtype(t)) for t in (np.int16, np.int32, np.int64, np.uint8, np.float16, np.float32,
+                                        np.float64, np.bool_)]
+    return out
+
+
+def _load(path, allow_pickle: bool = False):
+    """One ``tensors/*.pt`` file -> tensor.  Loaded with ``weights_only=True`` (tensors, lists and -- through
+    an explicit allow-list -- numpy arrays): a dataset directory is untrusted input and must not be able to
+    run code.  ``allow_pickle=True`` is the explicit opt-in for files that need the full unpickler."""
+    if allow_pickle:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+    else:
+        with torch.serialization.safe_globals(_numpy_safe_globals()):
+            obj = torch.load(path, map_location="cpu", weights_only=True)
     if isinstance(obj, np.ndarray):
         obj = torch.from_numpy(obj)
     elif isinstance(obj, (list, tuple)):
@@ -39,9 +55,11 @@ class PreprocessedItems(torch.utils.data.Dataset):
 
     Item = dict(item_name, codec (T, Q) int64, phoneme_ids (T_text,) int64, style (d_style,) float32,
     spk_emb (d_spk,) float32 or None, meta = the utterance's metadata.json record).  Utterances whose codec file
-    is missing (the writers skip it when the audio was not found) are dropped unless ``require_codec=False``."""
+    is missing (the writers skip it when the audio was not found) are dropped unless ``require_codec=False``.
+    Files are read without the general unpickler unless ``allow_pickle=True`` (see ``_load``)."""
 
-    def __init__(self, output_dir: str, require_codec: bool = True):
+    def __init__(self, output_dir: str, require_codec: bool = True, allow_pickle: bool = False):
+        self.allow_pickle = allow_pickle
         self.tensors_dir = os.path.join(output_dir, "tensors")
         with open(os.path.join(output_dir, "metadata.json")) as f:
             meta = json.load(f)
@@ -63,15 +81,15 @@ class PreprocessedItems(torch.utils.data.Dataset):
         path = lambda kind: os.path.join(self.tensors_dir, f"{name}_{kind}.pt")
         codec = None
         if os.path.exists(path("codec")):
-            codec = _load(path("codec")).long()
+            codec = _load(path("codec"), self.allow_pickle).long()
             if codec.dim() == 3 and codec.shape[0] == 1:      # FACodecEncoder.encode of one file: (1, T, Q)
                 codec = codec[0]
             if codec.dim() != 2:
                 raise ValueError(f"{path('codec')}: expected (T, Q) or (1, T, Q), got {tuple(codec.shape)}")
-        spk = _load(path("spk_emb")).float().reshape(-1) if os.path.exists(path("spk_emb")) else None
+        spk = _load(path("spk_emb"), self.allow_pickle).float().reshape(-1) if os.path.exists(path("spk_emb")) else None
         return {"item_name": rec["item_name"], "codec": codec,
-                "phoneme_ids": _load(path("phonemes")).long().reshape(-1),
-                "style": _load(path("style")).float().reshape(-1), "spk_emb": spk, "meta": rec}
+                "phoneme_ids": _load(path("phonemes"), self.allow_pickle).long().reshape(-1),
+                "style": _load(path("style"), self.allow_pickle).float().reshape(-1), "spk_emb": spk, "meta": rec}
 
 
 def collate_codec_batch(items, pad_id: int = 0):

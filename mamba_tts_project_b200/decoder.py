@@ -276,12 +276,19 @@ class MambaTTSDecoder(nn.Module):
         return [l.mamba.allocate_inference_cache(batch, dtype=dtype) for l in self.layers]
 
     def _context_for(self, text_hidden, z_style, text_mask, ref_hidden, ref_mask):
-        key = tuple(None if t is None else (t.data_ptr(), tuple(t.shape), t._version, t.dtype)
-                    for t in (text_hidden, z_style, text_mask, ref_hidden, ref_mask))
-        key += tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._gen_key != key:
+        """The cached ``GenerationContext`` of ``decode_step``: valid only for the very same input TENSORS
+        (identity, not address: the entry keeps strong references to them, so the allocator cannot hand
+        their storage to the next utterance while the entry lives) at the same ``_version``, and for
+        unchanged parameters."""
+        inputs = (text_hidden, z_style, text_mask, ref_hidden, ref_mask)
+        versions = tuple(None if t is None else t._version for t in inputs)
+        pkey = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        hit = (self._gen_key is not None
+               and all(a is b for a, b in zip(self._gen_key[0], inputs))
+               and self._gen_key[1] == versions and self._gen_key[2] == pkey)
+        if not hit:
             self._gen_ctx = self.prepare_generation(text_hidden, z_style, text_mask, ref_hidden, ref_mask)
-            self._gen_key = key
+            self._gen_key = (inputs, versions, pkey)
         return self._gen_ctx
 
     def _step_core(self, ctx: GenerationContext, x, states):

@@ -172,6 +172,8 @@ class _SelectiveScanFn(torch.autograd.Function):
             raise RuntimeError(f"selective_scan only supports state dimension <= {_lib.MAX_DSTATE}")
         io = u.dtype
         ctx.dtypes = tuple(None if t is None else t.dtype for t in (delta, A, B, C, D, z, delta_bias))
+        # from the ORIGINAL arguments: the .to()/.contiguous() copies below do not require grad
+        needs_grad = any(ctx.needs_input_grad[:8])
         u = _unit_last_stride(u)
         delta = _unit_last_stride(delta.to(io))
         Bm = _unit_last_stride(B.to(io))
@@ -182,8 +184,6 @@ class _SelectiveScanFn(torch.autograd.Function):
         if h0 is not None and h0.shape != (batch, dim, N):
             raise RuntimeError("initial_state must be (batch, dim, dstate)")
 
-        needs_grad = any(t is not None and t.requires_grad
-                         for t in (u, delta, A, B, C, D, z, delta_bias))
         out = torch.empty((batch, dim, L), dtype=io, device=u.device)
         last = torch.empty((batch, dim, N), dtype=torch.float32, device=u.device) \
             if return_last_state else None
@@ -704,8 +704,7 @@ class _AddLayerNormFn(torch.autograd.Function):
                 d2 = d2.contiguous()
         w32, b32, g32, be32 = _f32c(weight), _f32c(bias), _f32c(gamma), _f32c(beta)
         db32 = _f32c(delta_bias)
-        need = any(t is not None and t.requires_grad
-                   for t in (x, delta, weight, bias, gamma, beta, delta_bias))
+        need = any(ctx.needs_input_grad)
         out = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
         if d2 is None:
             x_out = x2

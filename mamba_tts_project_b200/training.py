@@ -97,11 +97,12 @@ class GraphedForwardBackward:
         loss = step(tokens, text, z, targets)      # host (pinned) or device tensors; returns a 0-d tensor
 
     After a call every ``p.grad`` holds this step's gradient (in the graph's memory pool: consume it --
-    optimizer, clipping, all-reduce -- before the next call).  Data parallel: call
+    optimizer, clipping, all-reduce -- before the next call).  ``pad_id`` (default 0, the codec padding id of
+    ``codec_ce_loss``, ``train.py:31-42``) is the ``ignore_index`` of the loss; ``None`` averages over every token.  Data parallel: call
     ``GradAllReducer.finish()`` after it (the all-reduce then runs after the backward, not under it)."""
 
     def __init__(self, decoder, tokens, text_hidden, z_style, targets=None, amp_dtype=torch.bfloat16,
-                 pad_id=None, warmup=3):
+                 pad_id=0, warmup=3):
         self.decoder, self.amp_dtype, self.pad_id = decoder, amp_dtype, pad_id
         dev = next(decoder.parameters()).device
         targets = tokens if targets is None else targets

@@ -373,3 +373,26 @@ def test_graphed_forward_backward_matches_eager():
         for p in dec.parameters():                        # what a DP reducer does after its all-reduce
             p.grad = torch.zeros_like(p)
     assert step.library_launches > 0
+
+
+def test_decode_step_context_not_reused_across_same_shape_utterances():
+    """decode_step called from a helper with a NEW utterance of the same shapes each time: the tensors of the
+    first call are freed, the caching allocator hands their addresses to the second -- the cached K/V and FiLM
+    terms of the first utterance must not be reused (identity-keyed context cache)."""
+    cfg = dict(vocab_size_audio=64, d_model=64, n_layers=2, n_heads=4, d_ff=128, d_style=16, max_len=64)
+    ref, dec = _make_pair(cfg, seed=21)
+
+    def utterance(seed):
+        g = torch.Generator().manual_seed(seed)
+        return torch.randn(2, 9, 64, generator=g), torch.randn(2, 16, generator=g)
+
+    def first_step(seed):          # tensors die with the frame: same-shape allocations reuse their addresses
+        text, z = utterance(seed)
+        lg, _ = dec.decode_step(torch.ones(2, 1, dtype=torch.long, device="cuda"), text.cuda(), z.cuda(), None, 0)
+        return lg
+
+    with torch.no_grad():
+        for seed in (1, 2, 3):
+            text, z = utterance(seed)
+            want, _ = ref.decode_step(torch.ones(2, 1, dtype=torch.long), text, z, None, 0)
+            check(f"utterance {seed}", first_step(seed), want, FP32_TOL)

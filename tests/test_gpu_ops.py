@@ -810,3 +810,21 @@ def test_selective_scan_per_timestep_outputs_are_deterministic():
     for r in runs[1:]:
         for name, a, b in zip(("out", "du", "ddelta", "dz"), runs[0], r):
             assert torch.equal(a, b), f"{name} differs between runs"
+
+
+def test_scan_grad_only_noncontiguous_u_requires_grad():
+    """Only u requires grad and it is a transposed (non-contiguous) view: forward must still allocate the
+    checkpoints (decided from the original arguments, not from the contiguous copy it makes)."""
+    from mamba_tts_project_b200 import ops
+    torch.manual_seed(0)
+    B, D, L, N = 2, 24, 40, 16
+    u_t = torch.randn(B, L, D, device="cuda", requires_grad=True)     # (B, L, D): u = u_t^T is strided
+    delta = 0.5 * torch.rand(B, D, L, device="cuda")
+    A = -0.5 * torch.rand(D, N, device="cuda")
+    Bm, Cm = torch.randn(B, N, L, device="cuda"), torch.randn(B, N, L, device="cuda")
+    out = ops.selective_scan_fn(u_t.transpose(1, 2), delta, A, Bm, Cm, delta_softplus=True)
+    (g,) = torch.autograd.grad(out.sum(), u_t)
+    u_ref = u_t.detach().cpu().transpose(1, 2).contiguous().requires_grad_()
+    out_ref = selective_scan_ref(u_ref, delta.cpu(), A.cpu(), Bm.cpu(), Cm.cpu(), delta_softplus=True)
+    (g_ref,) = torch.autograd.grad(out_ref.sum(), u_ref)
+    assert rel_err(g.transpose(1, 2), g_ref) < 1e-4
