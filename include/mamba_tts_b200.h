@@ -494,6 +494,62 @@ typedef struct {
 int mtts_gemm_bf16(const mtts_gemm_bf16_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * gemm -- every dense contraction of the teacher-forced path on the tcgen05 tensor cores (bf16 operands,
+ * fp32 accumulation in tensor memory), forward and backward:
+ *     C[bo][bi][m, n] = epilogue( sum_k A[bo][bi][m, k] * B[bo][bi][n, k] )
+ * Reference sites: Mamba in/x/dt/out projections (mamba_decoder.py:29,61 -> mamba_ssm nn.Linear /
+ * mamba_inner_fn), nn.MultiheadAttention (:32-36,72-77: packed q / kv projections, QK^T, softmax, PV, out
+ * projection), FFN (:39-43,88), head (:118,185) and their autograd backward (train.py:231).
+ * Replaces cuBLASLt GEMMs, cuDNN SDPA and aten::gelu / softmax.
+ *
+ * Operand storage, element strides (lda / ldb and every batch stride multiples of 8, bases 16-byte aligned):
+ *   a_major = 0 (K-major):  A[m, k] at a + m * lda + k          (nn.Linear weights, token-major activations)
+ *   a_major = 1 (M-major):  A[m, k] at a + k * lda + m          (channel-major activations, transposes)
+ *   likewise b_major / ldb for B[n, k].  Batch offsets: bo * x_bo_stride + bi * x_bi_stride; a stride of 0
+ *   shares the operand across that batch dimension (weights).  batch_inner exists for (batch, head) views.
+ * k_batches > 1 (weight gradients): the contraction also runs over kb in [0, k_batches), A and B advancing by
+ *   their bo strides; batch_outer must be 1.  split_k > 1 (or -1 = automatic) splits the contraction across
+ *   CTAs, which add into the fp32 output with vector REDs (the library zeroes it first unless accumulate).
+ * Output: C row-major [m, n], leading dimension ldc, batch strides c_bo_stride / c_bi_stride; out_dtype
+ *   MTTS_BF16 or MTTS_F32 (MTTS_EPI_STORE only).  accumulate != 0: C += result.
+ * Epilogues:
+ *   MTTS_EPI_STORE     C = acc + bias_n[n] + bias_m[m]                      (either bias may be NULL)
+ *   MTTS_EPI_GELU      aux = pre = acc + bias_n (bf16, optional);  C = gelu(pre)        exact-erf GELU
+ *   MTTS_EPI_GELU_BWD  C = acc * gelu'(aux)                                 aux = the forward's pre (bf16)
+ *   MTTS_EPI_SOFTMAX   C = softmax_n(scale * acc + key mask)                n <= 256; mask (batch_outer, n)
+ *                      uint8, 1 = attend, NULL = all; a fully masked row gives zeros
+ *   MTTS_EPI_DSOFTMAX  C = scale * P o (acc - sum_n P o acc)                aux = P (bf16), n <= 256
+ * aux is addressed like C with ld_aux / aux_bo_stride / aux_bi_stride.
+ * ------------------------------------------------------------------------------------------- */
+enum { MTTS_GEMM_SINGLE_CTA = 1 };
+enum { MTTS_EPI_STORE = 0, MTTS_EPI_GELU = 1, MTTS_EPI_GELU_BWD = 2, MTTS_EPI_SOFTMAX = 3, MTTS_EPI_DSOFTMAX = 4 };
+typedef struct {
+  int32_t m, n, k;
+  int32_t batch_outer, batch_inner;
+  int32_t k_batches;
+  int32_t a_major, b_major;
+  int32_t out_dtype;
+  int32_t epilogue;
+  int32_t accumulate;
+  int32_t split_k;
+  const void* a;
+  int64_t lda, a_bo_stride, a_bi_stride;
+  const void* b;
+  int64_t ldb, b_bo_stride, b_bi_stride;
+  void* out;
+  int64_t ldc, c_bo_stride, c_bi_stride;
+  const float* bias_n;
+  const float* bias_m;
+  void* aux;
+  int64_t ld_aux, aux_bo_stride, aux_bi_stride;
+  const uint8_t* mask;
+  int64_t mask_bo_stride;
+  float scale;
+  int32_t flags;         /* MTTS_GEMM_SINGLE_CTA: never pair CTAs (cta_group::1 tiles of 128 rows; measurements) */
+} mtts_gemm_params;
+int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FFN / projection glue (mamba_decoder.py:39-43,86-88: Linear -> GELU -> Linear, and the bias gradients
  * of every biased Linear on the path).  Row-major (rows, cols) tensors of the io dtype with leading
  * dimension ld (elements); cols, ld multiples of the 16-byte vector (8 bf16 / 4 fp32).
@@ -516,6 +572,89 @@ typedef struct {
 int mtts_bias_gelu_fwd(const mtts_bias_gelu_params* p, mtts_stream_t stream);
 int mtts_bias_gelu_bwd(const mtts_bias_gelu_params* p, mtts_stream_t stream);
 int mtts_colsum(const mtts_bias_gelu_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The caller's side of the training step (train.py:31-42,115-131,152-159,230-235).
+ *
+ * embed_sum_fwd: x[b, l, :] = token_embed[tokens[b, l]] + pos_embed[pos_ids[l]] (+ quant_embed[quant_ids[l]])
+ *   -- mamba_decoder.py:167-171 (teacher-forced embedding sum) and train.py:115-131 (`embed_codec_tokens`).
+ *   tokens (batch, seqlen) int64; pos_ids, quant_ids (seqlen) int64 (quant_ids NULL: no quantizer term);
+ *   tables fp32 row-major (rows, dim); x (batch, seqlen, dim) fp32; dim % 4 == 0.
+ * embed_sum_bwd: the same struct with x = d loss / d x and the three table pointers = their (pre-zeroed or
+ *   accumulating) fp32 gradients; a NULL table pointer skips that gradient.  Replaces three aten::embedding /
+ *   embedding_dense_backward launches and two adds.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, seqlen, dim;
+  int32_t reserved;
+  const int64_t* tokens;
+  const int64_t* pos_ids;
+  const int64_t* quant_ids;
+  float* token_embed;
+  float* pos_embed;
+  float* quant_embed;
+  float* x;
+} mtts_embed_sum_params;
+int mtts_embed_sum_fwd(const mtts_embed_sum_params* p, mtts_stream_t stream);
+int mtts_embed_sum_bwd(const mtts_embed_sum_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ce_loss -- F.cross_entropy(logits, targets, ignore_index) of train.py:31-42 in one pass:
+ *   loss_sum += sum over rows with targets != ignore_index of (logsumexp(logits[r]) - logits[r, target])
+ *   dlogits[r, :] = grad_scale / n_valid * (softmax(logits[r]) - onehot(target))   (zeros for ignored rows)
+ * logits (rows, vocab) io dtype, leading dimension ld; targets (rows) int64; n_valid: device pointer to the
+ * number of non-ignored targets (of the GLOBAL batch under data parallelism); loss_sum fp32 device scalar,
+ * ACCUMULATED (zero it first; the mean loss is loss_sum / n_valid); row_loss (rows) fp32 optional; dlogits NULL
+ * skips the gradient.  vocab, ld multiples of the 16-byte vector.  Replaces aten log_softmax + nll_loss forward
+ * and backward and the fp32 copy of the logits.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t rows;
+  int32_t vocab;
+  int32_t io_dtype;
+  int64_t ld;
+  int64_t ignore_index;
+  const void* logits;
+  const int64_t* targets;
+  const float* n_valid;
+  float grad_scale;
+  int32_t reserved;
+  float* loss_sum;
+  float* row_loss;
+  void* dlogits;
+} mtts_ce_loss_params;
+int mtts_ce_loss(const mtts_ce_loss_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * grad_sumsq + adam_step -- torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step()
+ * (train.py:152-159,233-234) over a DEVICE-resident table of fp32 tensors:
+ *   grad_sumsq:  *grad_sumsq = sum over all tensors of sum(grad^2)           (zeroed by the call)
+ *   adam_step:   g = grad * min(1, max_norm / (sqrt(*grad_sumsq) + 1e-6))    (max_norm <= 0: no clipping)
+ *                exp_avg = beta1 exp_avg + (1 - beta1) g;  exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) g^2
+ *                param -= step_size * exp_avg / (sqrt(exp_avg_sq) / bias_correction2_sqrt + eps)
+ *   with step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t) computed by the caller.
+ * tensors: device array of mtts_adam_tensor; chunks: device array of (tensor index, chunk index) int32 pairs,
+ * chunk = mtts_adam_chunk_elems() consecutive elements.  The gradients are not modified.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} mtts_adam_tensor;
+typedef struct {
+  const mtts_adam_tensor* tensors;
+  const int32_t* chunks;
+  int32_t num_chunks;
+  float max_norm;
+  float* grad_sumsq;
+  float step_size, beta1, beta2, eps, bias_correction2_sqrt;
+  int32_t reserved;
+} mtts_adam_params;
+int mtts_grad_sumsq(const mtts_adam_params* p, mtts_stream_t stream);
+int mtts_adam_step(const mtts_adam_params* p, mtts_stream_t stream);
+int mtts_adam_chunk_elems(void);
 
 #ifdef __cplusplus
 }

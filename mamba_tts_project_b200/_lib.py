@@ -134,12 +134,35 @@ LengthRegulateFwdParams = _struct("LengthRegulateFwdParams", """
 LengthRegulateBwdParams = _struct("LengthRegulateBwdParams", """
     i:batch i:t_text i:dim i:max_len i:io_dtype i:reserved p:durations p:dexpanded p:dhidden""")
 
+GemmParams = _struct("GemmParams", """
+    i:m i:n i:k i:batch_outer i:batch_inner i:k_batches i:a_major i:b_major i:out_dtype i:epilogue
+    i:accumulate i:split_k
+    p:a l:lda l:a_bo_stride l:a_bi_stride
+    p:b l:ldb l:b_bo_stride l:b_bi_stride
+    p:out l:ldc l:c_bo_stride l:c_bi_stride
+    p:bias_n p:bias_m
+    p:aux l:ld_aux l:aux_bo_stride l:aux_bi_stride
+    p:mask l:mask_bo_stride f:scale i:flags""")
+GEMM_SINGLE_CTA = 1
+EPI_STORE, EPI_GELU, EPI_GELU_BWD, EPI_SOFTMAX, EPI_DSOFTMAX = range(5)
+
+EmbedSumParams = _struct("EmbedSumParams", """
+    i:batch i:seqlen i:dim i:reserved p:tokens p:pos_ids p:quant_ids p:token_embed p:pos_embed p:quant_embed p:x""")
+CeLossParams = _struct("CeLossParams", """
+    l:rows i:vocab i:io_dtype l:ld l:ignore_index p:logits p:targets p:n_valid f:grad_scale i:reserved
+    p:loss_sum p:row_loss p:dlogits""")
+AdamParams = _struct("AdamParams", """
+    p:tensors p:chunks i:num_chunks f:max_norm p:grad_sumsq f:step_size f:beta1 f:beta2 f:eps
+    f:bias_correction2_sqrt i:reserved""")
+AdamTensor = _struct("AdamTensor", "p:param p:grad p:exp_avg p:exp_avg_sq l:numel")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
                  GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
-                 LengthRegulateFwdParams, LengthRegulateBwdParams]
+                 LengthRegulateFwdParams, LengthRegulateBwdParams, GemmParams,
+                 EmbedSumParams, CeLossParams, AdamParams, AdamTensor]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -164,6 +187,13 @@ ENTRY_POINTS = {
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
     "mtts_skinny_linear": SkinnyLinearParams,
     "mtts_gemm_bf16": GemmBf16Params,
+    "mtts_gemm": GemmParams,
+    "mtts_embed_sum_fwd": EmbedSumParams,
+    "mtts_embed_sum_bwd": EmbedSumParams,
+    "mtts_ce_loss": CeLossParams,
+    "mtts_grad_sumsq": AdamParams,
+    "mtts_adam_step": AdamParams,
+    "mtts_adam_chunk_elems": None,
     "mtts_bias_gelu_fwd": BiasGeluParams,
     "mtts_bias_gelu_bwd": BiasGeluParams,
     "mtts_colsum": BiasGeluParams,

@@ -42,6 +42,11 @@ extern "C" int mtts_sizeof_params(int which) {
     case 15: return (int)sizeof(mtts_decode_greedy_params);
     case 16: return (int)sizeof(mtts_length_regulate_fwd_params);
     case 17: return (int)sizeof(mtts_length_regulate_bwd_params);
+    case 18: return (int)sizeof(mtts_gemm_params);
+    case 19: return (int)sizeof(mtts_embed_sum_params);
+    case 20: return (int)sizeof(mtts_ce_loss_params);
+    case 21: return (int)sizeof(mtts_adam_params);
+    case 22: return (int)sizeof(mtts_adam_tensor);
     default: return -1;
   }
 }

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import dense, ops
 from .mamba import Mamba, compute_dtype
 
 
@@ -73,6 +73,14 @@ class CrossAttention(nn.Module):
         residual-add + LayerNorm launch together with its gradient)."""
         B, T, E = query.shape
         H, dh = self.num_heads, self.head_dim
+        Tk = memory.shape[1]
+        if dense.tc_enabled(compute_dtype(query)) and E % 8 == 0 and dh % 8 == 0 and 0 < Tk <= dense.MAX_FUSED_KEYS \
+                and T > 0:
+            # bf16: projections, QK^T + masked softmax, PV and the whole backward on mtts_gemm (tcgen05)
+            out = dense.cross_attention(query, memory, self.in_proj_weight, self.in_proj_bias,
+                                        self.out_proj.weight,
+                                        None if key_padding_mask is None else ~key_padding_mask, H)
+            return out + self.out_proj.bias.to(out.dtype) if add_out_bias else out
         q = ops.linear(query, self.in_proj_weight[:E], self.in_proj_bias[:E])
         k, v = self.project_kv(memory)
         q = q.view(B, T, H, dh).transpose(1, 2)
@@ -122,7 +130,12 @@ class MambaTTSDecoderLayer(nn.Module):
                                  delta_bias=self.cross_attn.out_proj.bias)
         # ff[0].bias is added inside the GELU kernel (and its gradient is that kernel's column sum);
         # ff[2].bias rides with delta into the next LayerNorm
-        f = F.linear(ops.bias_gelu(F.linear(h, self.ff[0].weight), self.ff[0].bias), self.ff[2].weight)
+        d_ff = self.ff[0].out_features
+        if dense.tc_enabled(cdt) and h.shape[-1] % 8 == 0 and d_ff % 8 == 0:
+            # both GEMMs on mtts_gemm; bias + GELU in the first one's epilogue, GELU' in the backward's
+            f = dense.ffn(h, self.ff[0].weight, self.ff[0].bias, self.ff[2].weight)
+        else:
+            f = F.linear(ops.bias_gelu(F.linear(h, self.ff[0].weight), self.ff[0].bias), self.ff[2].weight)
         return x, f, self.ff[2].bias, new_state
 
     def forward(self, x, text_hidden, z_style, text_mask=None, mamba_state=None):
@@ -262,8 +275,11 @@ class MambaTTSDecoder(nn.Module):
         for layer in self.layers:
             x, delta, dbias, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask,
                                                      delta_bias=dbias)
+        cdt = compute_dtype(x)
         _, h = ops.add_layernorm(x, delta, self.norm_out.weight, self.norm_out.bias,
-                                 self.norm_out.eps, out_dtype=compute_dtype(x), delta_bias=dbias)
+                                 self.norm_out.eps, out_dtype=cdt, delta_bias=dbias)
+        if dense.tc_enabled(cdt) and h.shape[-1] % 8 == 0 and self.vocab_size_audio % 8 == 0:
+            return dense.linear(h, self.head.weight, self.head.bias)
         return self.head(h)
 
     # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------

@@ -344,13 +344,25 @@ class _MambaBlockFn(torch.autograd.Function):
         N = A_log.shape[1]
         dev = h.device
         hc = h if h.dtype == dtype else h.to(dtype)
-        Wi, Wx, Wdt, Wo = (w.detach().to(dtype) for w in (in_w, xproj_w, dtproj_w, out_w))
+        if not hc.is_contiguous():
+            hc = hc.contiguous()
+        from . import dense
+        # bf16: every projection on mtts_gemm (tcgen05), reading the channel-major activations in place
+        tc = dense.tc_enabled(dtype) and T % 8 == 0 and Dm % 8 == 0 and Di % 8 == 0 and R % 8 == 0 and N % 4 == 0
+        if tc:
+            Wi, Wx, Wdt, Wo = (dense.bf16_weight(w) for w in (in_w, xproj_w, dtproj_w, out_w))
+        else:
+            Wi, Wx, Wdt, Wo = (w.detach().to(dtype) for w in (in_w, xproj_w, dtproj_w, out_w))
+        bc = lambda w: w.unsqueeze(0).expand(Bsz, -1, -1)
         cw32, cb32 = _f32c(conv_w), _f32c(conv_b)
         A = -torch.exp(A_log.detach().float())
         D32, db32 = _f32c(D), _f32c(dt_bias)
         io = _lib.io_dtype(hc)
         with torch.autocast("cuda", enabled=False):
-            xz = torch.bmm(Wi.unsqueeze(0).expand(Bsz, -1, -1), hc.transpose(1, 2))     # (B, 2Di, T)
+            if tc:
+                xz = dense.gemm(bc(Wi), hc)                                              # (B, 2Di, T)
+            else:
+                xz = torch.bmm(bc(Wi), hc.transpose(1, 2))
             x, z = xz[:, :Di], xz[:, Di:]
             xc = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
             _lib.call("mtts_causal_conv1d_fwd", _lib.Conv1dFwdParams(
@@ -358,8 +370,12 @@ class _MambaBlockFn(torch.autograd.Function):
                 x_batch_stride=x.stride(0), x_dim_stride=x.stride(1), weight=ptr(cw32), bias=ptr(cb32),
                 initial_states=None, init_batch_stride=0, init_dim_stride=0, out=ptr(xc),
                 out_batch_stride=xc.stride(0), out_dim_stride=xc.stride(1)))
-            x_dbl = torch.bmm(Wx.unsqueeze(0).expand(Bsz, -1, -1), xc)                   # (B, R+2N, T)
-            delta = torch.bmm(Wdt.unsqueeze(0).expand(Bsz, -1, -1), x_dbl[:, :R])        # (B, Di, T)
+            if tc:
+                x_dbl = dense.gemm(bc(Wx), xc.transpose(1, 2))                           # (B, R+2N, T)
+                delta = dense.gemm(bc(Wdt), x_dbl[:, :R].transpose(1, 2))                # (B, Di, T)
+            else:
+                x_dbl = torch.bmm(bc(Wx), xc)
+                delta = torch.bmm(bc(Wdt), x_dbl[:, :R])
             Bm, Cm = x_dbl[:, R:R + N], x_dbl[:, R + N:]
             y = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
             last = torch.empty((Bsz, Di, N), dtype=torch.float32, device=dev)
@@ -376,8 +392,12 @@ class _MambaBlockFn(torch.autograd.Function):
                 out_batch_stride=y.stride(0), out_dim_stride=y.stride(1), last_state=ptr(last),
                 checkpoints=ptr(chk), y_pre=ptr(ypre), y_batch_stride=ypre.stride(0),
                 y_dim_stride=ypre.stride(1)))
-            out = torch.bmm(y.transpose(1, 2), Wo.t().unsqueeze(0).expand(Bsz, -1, -1))  # (B, T, D)
+            if tc:
+                out = dense.gemm(y.transpose(1, 2), bc(Wo))                              # (B, T, D)
+            else:
+                out = torch.bmm(y.transpose(1, 2), bc(Wo.t()))
             new_conv = F.pad(x[..., -W:], (max(0, W - T), 0)) if T < W else x[..., -W:].clone()
+        ctx.tc = tc
         ctx.save_for_backward(hc, xz, xc, x_dbl, delta, y, chk, A, D32, db32, cw32, cb32, Wi, Wx, Wdt, Wo,
                               ypre)
         ctx.meta = (h.dtype, tuple(t.dtype for t in (in_w, conv_w, conv_b, xproj_w, dtproj_w, dt_bias,
@@ -400,10 +420,19 @@ class _MambaBlockFn(torch.autograd.Function):
         if not dout.is_contiguous():
             dout = dout.contiguous()
         f32 = torch.float32
+        tc = ctx.tc
+        if tc:
+            from . import dense
+            g = dense.gemm
+        bc = lambda w: w.unsqueeze(0).expand(Bsz, -1, -1)
         with torch.autocast("cuda", enabled=False):
             doutT = dout.transpose(1, 2)                                                  # (B, D, T)
-            dy = torch.bmm(Wo.t().unsqueeze(0).expand(Bsz, -1, -1), doutT)                 # (B, Di, T)
-            dWo = torch.bmm(doutT, y.transpose(1, 2)).sum(0)                               # (D, Di)
+            if tc:
+                dy = g(bc(Wo.t()), dout)                                                  # (B, Di, T)
+                dWo = g(doutT, y, out_dtype=f32, reduce_batch=True, split_k=-1)           # (D, Di)
+            else:
+                dy = torch.bmm(bc(Wo.t()), doutT)
+                dWo = torch.bmm(doutT, y.transpose(1, 2)).sum(0)
             dxz = torch.empty_like(xz)
             dxh, dzh = dxz[:, :Di], dxz[:, Di:]
             x, z = xz[:, :Di], xz[:, Di:]
@@ -431,15 +460,23 @@ class _MambaBlockFn(torch.autograd.Function):
                 y_pre=ptr(ypre), y_batch_stride=ypre.stride(0), y_dim_stride=ypre.stride(1)))
             # d x_dbl = [W_dt^T ddelta | dB | dC]  (B, R + 2N, T), small
             dx_dbl = torch.empty((Bsz, R + 2 * N, T), dtype=dtype, device=dev)
-            dx_dbl[:, :R].copy_(torch.bmm(Wdt.t().unsqueeze(0).expand(Bsz, -1, -1), ddelta))
+            if tc:
+                g(bc(Wdt.t()), ddelta.transpose(1, 2), out=dx_dbl[:, :R])
+            else:
+                dx_dbl[:, :R].copy_(torch.bmm(bc(Wdt.t()), ddelta))
             dx_dbl[:, R:R + N].copy_(dBC[0])
             dx_dbl[:, R + N:].copy_(dBC[1])
-            dWdt = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)                  # (Di, R)
-            # d xc = du + W_x^T d x_dbl : du is the GEMM's accumulator
-            dxc = du.baddbmm_(Wx.t().unsqueeze(0).expand(Bsz, -1, -1), dx_dbl)
-            dWx = torch.bmm(dx_dbl, xc.transpose(1, 2)).sum(0)                             # (R+2N, Di)
             dcw = torch.zeros_like(cw32)
             dcb = torch.zeros(Di, dtype=f32, device=dev)
+            if tc:
+                dWdt = g(ddelta, x_dbl[:, :R], out_dtype=f32, reduce_batch=True, split_k=-1)      # (Di, R)
+                # d xc = du + W_x^T d x_dbl : the GEMM accumulates onto du
+                dxc = g(bc(Wx.t()), dx_dbl.transpose(1, 2), out=du, accumulate=True)
+                dWx = g(dx_dbl, xc, out_dtype=f32, reduce_batch=True, split_k=-1)                 # (R+2N, Di)
+            else:
+                dWdt = torch.bmm(ddelta, x_dbl[:, :R].transpose(1, 2)).sum(0)
+                dxc = du.baddbmm_(bc(Wx.t()), dx_dbl)
+                dWx = torch.bmm(dx_dbl, xc.transpose(1, 2)).sum(0)
             _lib.call("mtts_causal_conv1d_bwd", _lib.Conv1dBwdParams(
                 batch=Bsz, dim=Di, seqlen=T, width=W, io_dtype=io, silu=1, x=ptr(x),
                 x_batch_stride=x.stride(0), x_dim_stride=x.stride(1), weight=ptr(cw32), bias=ptr(cb32),
@@ -447,8 +484,12 @@ class _MambaBlockFn(torch.autograd.Function):
                 dout=ptr(dxc), dout_batch_stride=dxc.stride(0), dout_dim_stride=dxc.stride(1),
                 dx=ptr(dxh), dx_batch_stride=dxh.stride(0), dx_dim_stride=dxh.stride(1),
                 dweight=ptr(dcw), dbias=ptr(dcb)))
-            dh = torch.bmm(dxz.transpose(1, 2), Wi.unsqueeze(0).expand(Bsz, -1, -1))       # (B, T, D)
-            dWi = torch.bmm(dxz, hc).sum(0)                                                # (2Di, D)
+            if tc:
+                dh = g(dxz.transpose(1, 2), bc(Wi.t()))                                           # (B, T, D)
+                dWi = g(dxz, hc.transpose(1, 2), out_dtype=f32, reduce_batch=True, split_k=-1)    # (2Di, D)
+            else:
+                dh = torch.bmm(dxz.transpose(1, 2), bc(Wi))
+                dWi = torch.bmm(dxz, hc).sum(0)
             dA_log = dA * A                                                                # A = -exp(A_log)
         return (dh.to(t_h), dWi.to(t_in), dcw.to(t_cw), None if t_cb is None else dcb.to(t_cb),
                 dWx.to(t_xw), dWdt.to(t_dtw), ddb.to(t_dtb), dA_log.to(t_A), dD.to(t_D), dWo.to(t_ow),
@@ -939,3 +980,155 @@ def gemm_bf16(a, w, bias=None, gelu=False, return_pre=False):
     _lib.call("mtts_gemm_bf16", p)
     out = out.view(*a.shape[:-1], n)
     return (out, pre.view(*a.shape[:-1], n)) if return_pre else out
+
+
+# ------------------------------------------------------------------------------------------------
+# the caller's side of the training step (train.py:31-42,115-131,152-159,230-235)
+# ------------------------------------------------------------------------------------------------
+class _EmbedSumFn(torch.autograd.Function):
+    """x = token_embed[tokens] + pos_embed[pos_ids] (+ quant_embed[quant_ids]) in one launch, fp32."""
+
+    @staticmethod
+    def forward(ctx, tokens, pos_ids, quant_ids, tok_w, pos_w, quant_w):
+        _lib.require_cuda(tokens, pos_ids, quant_ids, tok_w, pos_w, quant_w)
+        B, L = tokens.shape
+        D = tok_w.shape[1]
+        if tokens.dtype != torch.long or pos_ids.dtype != torch.long or pos_ids.shape != (L,):
+            raise RuntimeError("tokens (B, L) and pos_ids (L) must be int64")
+        if (quant_ids is None) != (quant_w is None):
+            raise RuntimeError("quant_ids and quant_embed come together")
+        for w in (tok_w, pos_w, quant_w):
+            if w is not None and (w.dtype != torch.float32 or not w.is_contiguous() or w.shape[1] != D):
+                raise RuntimeError("embedding tables must be contiguous fp32 (rows, dim)")
+        tokens, pos_ids = tokens.contiguous(), pos_ids.contiguous()
+        quant_ids = None if quant_ids is None else quant_ids.to(torch.long).contiguous()
+        x = torch.empty((B, L, D), dtype=torch.float32, device=tokens.device)
+        p = _lib.EmbedSumParams(batch=B, seqlen=L, dim=D, reserved=0, tokens=ptr(tokens), pos_ids=ptr(pos_ids),
+                                quant_ids=ptr(quant_ids), token_embed=ptr(tok_w), pos_embed=ptr(pos_w),
+                                quant_embed=ptr(quant_w), x=ptr(x))
+        _lib.call("mtts_embed_sum_fwd", p)
+        ctx.save_for_backward(tokens, pos_ids, quant_ids)
+        ctx.shapes = (tok_w.shape, pos_w.shape, None if quant_w is None else quant_w.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        tokens, pos_ids, quant_ids = ctx.saved_tensors
+        st, sp, sq = ctx.shapes
+        B, L = tokens.shape
+        dx = dx.float().contiguous()
+        need = ctx.needs_input_grad
+        z = lambda shape, on: torch.zeros(shape, dtype=torch.float32, device=dx.device) if on and shape else None
+        dt, dp, dq = z(st, need[3]), z(sp, need[4]), z(sq, need[5])
+        p = _lib.EmbedSumParams(batch=B, seqlen=L, dim=st[1], reserved=0, tokens=ptr(tokens), pos_ids=ptr(pos_ids),
+                                quant_ids=ptr(quant_ids) if dq is not None else None, token_embed=ptr(dt),
+                                pos_embed=ptr(dp), quant_embed=ptr(dq), x=ptr(dx))
+        _lib.call("mtts_embed_sum_bwd", p)
+        return None, None, None, dt, dp, dq
+
+
+def embed_sum(tokens, pos_ids, quant_ids, token_embed, pos_embed, quant_embed=None):
+    """(B, L) ids -> (B, L, D) fp32: ``tok + pos + quant`` of ``mamba_decoder.py:167-171`` /
+    ``train.py:115-131``.  pos_ids / quant_ids are per position (L,), shared by the batch."""
+    return _EmbedSumFn.apply(tokens, pos_ids, quant_ids, token_embed, pos_embed, quant_embed)
+
+
+class _CeLossFn(torch.autograd.Function):
+    """Sum of token cross entropies over targets != ignore_index and, in the same pass, its gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, n_valid, ignore_index):
+        _lib.require_cuda(logits, targets, n_valid)
+        V = logits.shape[-1]
+        l2 = logits.reshape(-1, V)
+        if l2.stride(-1) != 1:
+            l2 = l2.contiguous()
+        t = targets.reshape(-1).contiguous()
+        nv = n_valid.detach().float().reshape(1).contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        dl = torch.empty_like(l2, memory_format=torch.contiguous_format) if need else None
+        p = _lib.CeLossParams(rows=l2.shape[0], vocab=V, io_dtype=_lib.io_dtype(l2), ld=l2.stride(0),
+                              ignore_index=int(ignore_index), logits=ptr(l2), targets=ptr(t), n_valid=ptr(nv),
+                              grad_scale=1.0, reserved=0, loss_sum=ptr(loss), row_loss=None, dlogits=ptr(dl))
+        _lib.call("mtts_ce_loss", p)
+        ctx.save_for_backward(dl)
+        ctx.shape = logits.shape
+        return loss / nv[0].clamp(min=1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g.to(dl.dtype)).view(ctx.shape), None, None, None
+
+
+def ce_loss(logits, targets, ignore_index=0, n_valid=None):
+    """``F.cross_entropy(logits.view(-1, V), targets.view(-1), ignore_index=...)`` (``train.py:31-42``) on the
+    logits' own dtype (no fp32 copy), gradient computed in the forward pass.  ``n_valid``: the divisor (default:
+    this call's count of non-ignored targets; pass the global count under data parallelism / micro-batching)."""
+    if n_valid is None:
+        n_valid = (targets != ignore_index).sum()
+    return _CeLossFn.apply(logits, targets, n_valid, ignore_index)
+
+
+class FusedClipAdam:
+    """``clip_grad_norm_(params, max_norm)`` + ``torch.optim.Adam(params, lr).step()`` (``train.py:152-159,233-234``)
+    as two launches over a device-resident table of the parameters (``mtts_grad_sumsq`` + ``mtts_adam_step``):
+    the clip coefficient is applied inside the update, gradients are never rescaled in memory.  Plain Adam
+    (no weight decay, no amsgrad), fp32 parameters with contiguous fp32 gradients."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self.step_count = 0
+        dev = self.params[0].device
+        self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._table_key = None
+        self._dev = dev
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def _tables(self):
+        import ctypes as C
+        act = [(p, m, v) for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq) if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p, _, _ in act)
+        if key != self._table_key:
+            chunk = _lib.load().mtts_adam_chunk_elems()
+            arr = (_lib.AdamTensor * max(len(act), 1))()
+            chunks = []
+            for i, (p, m, v) in enumerate(act):
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() \
+                        or not p.grad.is_contiguous():
+                    raise RuntimeError("FusedClipAdam needs contiguous fp32 parameters and gradients")
+                arr[i] = _lib.AdamTensor(param=p.data_ptr(), grad=p.grad.data_ptr(), exp_avg=m.data_ptr(),
+                                         exp_avg_sq=v.data_ptr(), numel=p.numel())
+                chunks += [(i, c) for c in range((p.numel() + chunk - 1) // chunk)]
+            raw = bytes(memoryview(arr).cast("B"))[: C.sizeof(_lib.AdamTensor) * len(act)]
+            self._tensors = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self._dev)
+            self._chunks = torch.tensor(chunks, dtype=torch.int32).reshape(-1, 2).to(self._dev)
+            self._table_key = key
+        return self._tensors, self._chunks
+
+    @torch.no_grad()
+    def step(self):
+        tensors, chunks = self._tables()
+        self.step_count += 1
+        b1, b2 = self.betas
+        p = _lib.AdamParams(tensors=tensors.data_ptr(), chunks=chunks.data_ptr(), num_chunks=chunks.shape[0],
+                            max_norm=float(self.max_norm or 0.0), grad_sumsq=self.sumsq.data_ptr(),
+                            step_size=self.lr / (1.0 - b1 ** self.step_count), beta1=b1, beta2=b2, eps=self.eps,
+                            bias_correction2_sqrt=(1.0 - b2 ** self.step_count) ** 0.5, reserved=0)
+        if self.max_norm:
+            _lib.call("mtts_grad_sumsq", p)
+        _lib.call("mtts_adam_step", p)
+
+    def grad_norm(self):
+        """Total gradient norm seen by the last step (before clipping)."""
+        return self.sumsq.sqrt()[0]

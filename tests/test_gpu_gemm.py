@@ -1,0 +1,164 @@
+"""tcgen05 GEMM (csrc/gemm_sm100.cu, ``mtts_gemm``) against fp32 torch on the same bf16-rounded operands:
+all four operand layouts, tails, batch / broadcast / (batch, head) views, the batch-reducing split-k weight
+gradient, and every fused epilogue."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+BF16_OUT = 6e-3      # one bf16 rounding of the result: 2^-9 relative to the element, here relative to the max
+F32_OUT = 2e-5       # fp32 accumulation order only
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _view(t, major):
+    """(.., rows, k) logical view of t stored K-major (major 0) or MN-major (major 1)."""
+    return t if major == 0 else t.transpose(-1, -2).contiguous().transpose(-1, -2)
+
+
+@pytest.mark.parametrize("am,bm", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(300, 520, 200), (128, 256, 64), (64, 64, 32), (1000, 100, 4160), (130, 2048, 512)])
+def test_gemm_layouts_and_tails(am, bm, m, n, k):
+    from mamba_tts_project_b200.gemm import gemm
+    # MN-major operands need their contiguous extent to be a multiple of 8 elements (16-byte TMA strides)
+    m_ = m + (-m) % 8
+    a = _view(_rand(m_, k + (-k) % 8, seed=1), am)[:m, :k]
+    b = _view(_rand(n + (-n) % 8, k + (-k) % 8, seed=2), bm)[:n, :k]
+    ref = a.float() @ b.float().t()
+    out = gemm(a, b)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < BF16_OUT
+    out32 = gemm(a, b, out_dtype=torch.float32)
+    assert rel_err(out32, ref) < F32_OUT
+
+
+def test_gemm_bias_accumulate_and_strided_out():
+    from mamba_tts_project_b200.gemm import gemm
+    m, n, k = 260, 384, 192
+    a, b = _rand(m, k, seed=3), _rand(n, k, seed=4)
+    bn = torch.randn(n, device="cuda")
+    bm_ = torch.randn(m, device="cuda")
+    ref = a.float() @ b.float().t()
+    assert rel_err(gemm(a, b, bias_n=bn), ref + bn) < BF16_OUT
+    assert rel_err(gemm(a, b, bias_m=bm_, out_dtype=torch.float32), ref + bm_[:, None]) < F32_OUT
+    big = torch.zeros(m, 2 * n, device="cuda")          # ldc > n: write into the right half only
+    gemm(a, b, out=big[:, n:])
+    assert rel_err(big[:, n:], ref) < F32_OUT and big[:, :n].abs().max() == 0
+    acc32 = torch.ones(m, n, device="cuda")
+    gemm(a, b, out=acc32, accumulate=True)
+    assert rel_err(acc32, ref + 1) < F32_OUT
+    acc16 = torch.ones(m, n, device="cuda", dtype=torch.bfloat16)
+    gemm(a, b, out=acc16, accumulate=True)
+    assert rel_err(acc16, ref + 1) < BF16_OUT
+
+
+def test_gemm_batched_broadcast_and_head_views():
+    from mamba_tts_project_b200.gemm import gemm
+    B, H, T, dh, Tk = 3, 4, 200, 64, 136
+    E = H * dh
+    # in_proj-like: weight shared by the batch (stride 0), activations channel-major out
+    w = _rand(2 * E, E, seed=5, scale=E ** -0.5)
+    h = _rand(B, T, E, seed=6)
+    xz = gemm(w.unsqueeze(0).expand(B, -1, -1), h)                     # (B, 2E, T)
+    assert rel_err(xz, torch.einsum("ce,bte->bct", w.float(), h.float())) < BF16_OUT
+    # out_proj-like: A is the transpose view of a channel-major tensor
+    y = _rand(B, E, T, seed=7)
+    wo = _rand(E, E, seed=8, scale=E ** -0.5)
+    o = gemm(y.transpose(1, 2), wo.unsqueeze(0).expand(B, -1, -1))     # (B, T, E)
+    assert rel_err(o, torch.einsum("bct,dc->btd", y.float(), wo.float())) < BF16_OUT
+    # attention scores: (B, H, T, dh) views of (B, T, E) projections, two batch dimensions
+    q, kk = _rand(B, T, E, seed=9), _rand(B, Tk, E, seed=10)
+    qv = q.view(B, T, H, dh).transpose(1, 2)
+    kv = kk.view(B, Tk, H, dh).transpose(1, 2)
+    s = gemm(qv, kv, out_dtype=torch.float32)                          # (B, H, T, Tk)
+    assert rel_err(s, qv.float() @ kv.float().transpose(-1, -2)) < F32_OUT
+    # P V with V read N-major from the (B, Tk, E) tensor and O written straight into (B, T, E)
+    p = _rand(B, H, T, Tk, seed=11, scale=0.1)
+    vv = _rand(B, Tk, E, seed=12)
+    o = torch.empty(B, T, E, device="cuda", dtype=torch.bfloat16)
+    gemm(p, vv.view(B, Tk, H, dh).permute(0, 2, 3, 1), out=o.view(B, T, H, dh).transpose(1, 2))
+    ref = (p.float() @ vv.view(B, Tk, H, dh).transpose(1, 2).float()).transpose(1, 2).reshape(B, T, E)
+    assert rel_err(o, ref) < BF16_OUT
+
+
+@pytest.mark.parametrize("split", [1, 5, -1])
+def test_gemm_weight_gradient_reduces_over_batch(split):
+    from mamba_tts_project_b200.gemm import gemm
+    B, C, T, D = 4, 192, 520, 128
+    dxz, h = _rand(B, C, T, seed=13), _rand(B, T, D, seed=14)
+    # dW[c, d] = sum_b sum_t dxz[b, c, t] h[b, t, d]:  A K-major (k = t), B N-major
+    dw = gemm(dxz, h.transpose(1, 2), out_dtype=torch.float32, reduce_batch=True, split_k=split)
+    ref = torch.einsum("bct,btd->cd", dxz.float(), h.float())
+    assert dw.shape == (C, D) and rel_err(dw, ref) < F32_OUT
+    # token-major activations on both sides (FFN weight gradient): both operands MN-major, one long k
+    dy, x = _rand(B * T, C, seed=15), _rand(B * T, D, seed=16)
+    dw2 = gemm(dy.t(), x.t(), out_dtype=torch.float32, split_k=split)
+    assert rel_err(dw2, dy.float().t() @ x.float()) < F32_OUT
+
+
+def test_gemm_gelu_epilogues():
+    from mamba_tts_project_b200.gemm import gemm
+    m, n, k = 520, 768, 256
+    x, w = _rand(m, k, seed=17), _rand(n, k, seed=18, scale=k ** -0.5)
+    bias = torch.randn(n, device="cuda")
+    pre = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    act = gemm(x, w, bias_n=bias, epilogue="gelu", aux=pre)
+    ref_pre = x.float() @ w.float().t() + bias
+    assert rel_err(pre, ref_pre) < BF16_OUT
+    assert rel_err(act, torch.nn.functional.gelu(ref_pre)) < BF16_OUT
+    # backward: dpre = (dy @ W2) * gelu'(pre), W2 (d, n) read N-major
+    d = 128
+    dy, w2 = _rand(m, d, seed=19), _rand(d, n, seed=20, scale=d ** -0.5)
+    dpre = gemm(dy, w2.t(), epilogue="gelu_bwd", aux=pre)
+    pf = pre.float().requires_grad_()
+    (g,) = torch.autograd.grad(torch.nn.functional.gelu(pf), pf, dy.float() @ w2.float())
+    assert rel_err(dpre, g) < BF16_OUT
+
+
+@pytest.mark.parametrize("tk", [256, 200, 72])
+def test_gemm_softmax_epilogues(tk):
+    from mamba_tts_project_b200.gemm import gemm
+    B, H, T, dh = 2, 4, 300, 64
+    E = H * dh
+    q, kk = _rand(B, T, E, seed=21), _rand(B, tk, E, seed=22)
+    mask = torch.rand(B, tk, generator=torch.Generator().manual_seed(1)) > 0.3
+    mask[:, 0] = True
+    qv = q.view(B, T, H, dh).transpose(1, 2)
+    kv = kk.view(B, tk, H, dh).transpose(1, 2)
+    scale = 1 / math.sqrt(dh)
+    tkp = tk + (-tk) % 8
+    P = torch.zeros(B, H, T, tkp, device="cuda", dtype=torch.bfloat16)
+    gemm(qv, kv, out=P[..., :tk], epilogue="softmax", mask=mask.cuda(), scale=scale)
+    s = (qv.float() @ kv.float().transpose(-1, -2)) * scale
+    s = s.masked_fill(~mask.cuda()[:, None, None, :], float("-inf"))
+    ref = torch.softmax(s, -1)
+    assert rel_err(P[..., :tk], ref) < BF16_OUT
+    assert tkp == tk or P[..., tk:].abs().max() == 0
+    # softmax backward fused into dP = dO V^T
+    do, vv = _rand(B, T, E, seed=23), _rand(B, tk, E, seed=24)
+    dov = do.view(B, T, H, dh).transpose(1, 2)
+    vvv = vv.view(B, tk, H, dh).transpose(1, 2)
+    dS = torch.zeros_like(P)
+    gemm(dov, vvv, out=dS[..., :tk], epilogue="dsoftmax", aux=P[..., :tk], scale=scale)
+    Pf = P[..., :tk].float()
+    dP = dov.float() @ vvv.float().transpose(-1, -2)
+    ref_ds = scale * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    assert rel_err(dS[..., :tk], ref_ds) < BF16_OUT
+
+
+def test_gemm_persistent_many_tiles_and_legacy_entry():
+    from mamba_tts_project_b200 import ops
+    from mamba_tts_project_b200.gemm import gemm
+    a, w = _rand(4096, 512, seed=25), _rand(2048, 512, seed=26, scale=512 ** -0.5)   # 256 tiles > 148 CTAs
+    ref = a.float() @ w.float().t()
+    assert rel_err(gemm(a, w), ref) < BF16_OUT
+    bias = torch.randn(2048, device="cuda")
+    out, pre = ops.gemm_bf16(a, w, bias, gelu=True, return_pre=True)
+    assert rel_err(pre, ref + bias) < BF16_OUT and rel_err(out, torch.nn.functional.gelu(ref + bias)) < BF16_OUT
+    assert rel_err(ops.gemm_bf16(a, w, bias), ref + bias) < BF16_OUT

@@ -358,7 +358,8 @@ def test_graphed_forward_backward_matches_eager():
         tok, text, z, tgt = (t.cuda() for t in b)
         dec.zero_grad(set_to_none=True)
         logits = dec(tok, text, z)
-        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, 48).float(), tgt.reshape(-1))
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, 48).float(), tgt.reshape(-1),
+                                                 ignore_index=0)     # codec_ce_loss, train.py:31-42
         loss.backward()
         return loss.item(), {n: p.grad.clone() for n, p in dec.named_parameters()}
 

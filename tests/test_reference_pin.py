@@ -135,3 +135,89 @@ def test_cuda_decoder_matches_reference_c1(no_tf32):
     g, inp = _case("c1")
     dec = _load(MambaTTSDecoder(**g["config"]), g).cuda().eval()
     _check_c1(dec, g, inp, "cuda", FP32_TOL, 5e-4)
+
+
+# ---- bf16 convention at the BASELINE shapes ----------------------------------------------------------
+# Fixtures: the reference classes in fp32 on weights / float inputs rounded through bf16
+# (oracle/make_golden_reference_decoder.py --big).  The CUDA decoder runs under bf16 autocast with the same
+# rounded fp32 master weights.  Tolerance (BASELINE.json): 2e-2, as max|diff| / max|ref| per tensor.
+BF16_TOL = 2e-2
+
+
+def _bf16_case(name):
+    g = load_golden(f"ref_decoder_{name}.pt")
+    inp = make_inputs(g["case"], g["config"], g["B"], g["T"], g["T_text"], g["T_ref"], g["seed"], g["masks"],
+                      round_to=g["round_to"])
+    return g, inp
+
+
+def _load_bf16(model, g):
+    sd = seeded_state_dict(model.state_dict(), g["seed"], round_to=g["round_to"])
+    if g["zero_quant_embed"]:
+        sd["quant_embed.weight"].zero_()
+    model.load_state_dict(sd)
+    return model
+
+
+def _bf16_fwd_bwd_check(name):
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    g, inp = _bf16_case(name)
+    dec = _load_bf16(MambaTTSDecoder(**g["config"]), g).cuda().eval()
+    mv = lambda t: None if t is None else t.cuda()
+    V = g["config"]["vocab_size_audio"]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = dec(mv(inp["tokens"]), mv(inp["text_hidden"]), mv(inp["z_style"]), text_mask=mv(inp["text_mask"]),
+                     ref_hidden=mv(inp["ref_hidden"]), ref_mask=mv(inp["ref_mask"]))
+    assert logits.dtype == torch.bfloat16
+    loss = F.cross_entropy(logits.reshape(-1, V).float(), mv(inp["target"]).reshape(-1), ignore_index=0)
+    loss.backward()
+    lg = logits.detach().float()
+    e = rel_err(lg[:, ::g["every"]], g["logits_sub"])
+    assert e < BF16_TOL, f"logits rel err {e:.3e}"
+    assert rel_err(torch.logsumexp(lg, -1), g["logsumexp"]) < BF16_TOL
+    assert abs(loss.item() - g["loss"].item()) < BF16_TOL * abs(g["loss"].item())
+    worst = {}
+    for k, p in dec.named_parameters():
+        n_ref = g["grad_norms"][k].item()
+        assert abs(p.grad.float().norm().item() - n_ref) < 2 * BF16_TOL * max(n_ref, 1e-12), f"|grad {k}|"
+        if k in g["grads_small"]:
+            worst[k] = rel_err(p.grad, g["grads_small"][k])
+    bad = {k: round(v, 4) for k, v in worst.items() if v >= BF16_TOL}
+    assert not bad, f"gradient rel err >= {BF16_TOL}: {bad}"
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_bf16_c2_shape_logits_and_gradients():
+    """BASELINE configs[1] model and sequence length (12 x d_model 512, T 2048, T_text 256; B 2): bf16 autocast
+    forward + backward -- the benched precision mode and code path -- against the reference's fp32 result."""
+    _bf16_fwd_bwd_check("c2_bf16")
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_bf16_c5_layer_shape_logits_and_gradients():
+    """One layer of BASELINE configs[4]: d_model 1024, 16 heads, d_ff 4096, [ref || text] = 256 + 128 keys with
+    padding masks, bf16 autocast forward + backward."""
+    _bf16_fwd_bwd_check("c5_layer_bf16")
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_bf16_c3_shape_decode_steps():
+    """BASELINE configs[2] shape: the 12-layer d512 model decoding B 64 against 256 keys (ref 64 + text 192,
+    masked) for 64 teacher-forced steps in bf16, through the serving step path (_step_core, states in place)."""
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    g, inp = _bf16_case("c3_bf16")
+    dec = _load_bf16(MambaTTSDecoder(**g["config"]), g).cuda().eval()
+    mv = lambda t: None if t is None else t.cuda()
+    with torch.no_grad():
+        ctx = dec.prepare_generation(mv(inp["text_hidden"]), mv(inp["z_style"]), text_mask=mv(inp["text_mask"]),
+                                     ref_hidden=mv(inp["ref_hidden"]), ref_mask=mv(inp["ref_mask"]),
+                                     dtype=torch.bfloat16)
+        st = dec.allocate_states(g["B"], torch.bfloat16)
+        tok = inp["tokens"].cuda()
+        got = []
+        for i in range(g["T"]):
+            x = (ctx.tok[tok[:, i]] + ctx.pos[i]).float().contiguous()
+            got.append(dec._step_core(ctx, x, st)[:, None].float())
+        lg = torch.cat(got, 1)
+    assert rel_err(lg[::8], g["logits_rows"]) < BF16_TOL
+    assert rel_err(torch.logsumexp(lg, -1), g["logsumexp"]) < BF16_TOL
