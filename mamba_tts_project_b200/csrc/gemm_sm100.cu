@@ -396,6 +396,42 @@ __device__ __forceinline__ void warp_store32(unsigned char* stage, int lane, uns
   __syncwarp();   // the staging tile is rewritten by the next block
 }
 
+// The reverse for a bf16 operand of the epilogue (aux), in two steps so that the global loads can be issued long
+// before their data is needed (before the accumulator is even complete):
+//   warp_ldg32      the warp's 32-row x 32-column block, lanes of a quarter-warp on consecutive 16-byte vectors of
+//                   two rows (zeros outside the matrix) -> 4 registers of raw data per lane, any row
+//   warp_own_rows   parks them in the staging tile and hands every lane its OWN row:
+//                   raw[sl] = columns [col + 8 sl, col + 8 sl + 8) of row `lane`
+__device__ __forceinline__ void warp_ldg32(const unsigned char* warp_base, long long ld_bytes, int rows_valid, int col,
+                                           int n, int lane, uint4 (&w)[4]) {
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int idx = pass * 32 + lane;
+    const int r = idx >> 2, c = col + (idx & 3) * 8;
+    w[pass] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && c + 8 <= n)
+      w[pass] = __ldg(reinterpret_cast<const uint4*>(warp_base + (long long)r * ld_bytes + (size_t)c * 2));
+  }
+}
+__device__ __forceinline__ void warp_own_rows(unsigned char* stage, int lane, const uint4 (&w)[4], uint4 (&raw)[4]) {
+  // (w and raw may be the same array: w is consumed before raw is written)
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int idx = pass * 32 + lane;
+    const int r = idx >> 2, sl = idx & 3;
+    *reinterpret_cast<uint4*>(stage + r * 64 + ((sl ^ ((r >> 1) & 3)) << 4)) = w[pass];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl)
+    raw[sl] = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((sl ^ ((lane >> 1) & 3)) << 4));
+  __syncwarp();
+}
+__device__ __forceinline__ void unpack32(const uint4 (&raw)[4], float* v) {
+#pragma unroll
+  for (int sl = 0; sl < 4; ++sl) unpack_bf16x8(raw[sl], v + 8 * sl);
+}
+
 // 32 bf16 of a row starting at column col -> fp32 (zeros past n)
 __device__ __forceinline__ void load_row32_bf16(const void* row_base, int col, int n, float* v, bool vec) {
   const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(row_base) + col;
@@ -643,6 +679,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           else if (row_ok) store_row32<false>(out_row, col, p_n, v, false, p_acc, false);
         }
       };
+      // operands of the epilogue that do not depend on the accumulator are requested before waiting for it
+      [[maybe_unused]] uint4 wq[4];                      // GELU': the next 32-column block of the pre-activation
+      [[maybe_unused]] uint4 wall[BN / 64][4];           // dsoftmax: the warp's whole block of P
+      if constexpr (EPI == EPI_GELU_BWD) {
+        if (p_vec && n0 < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0, p_n, lane, wq);
+      } else if constexpr (EPI == EPI_DSOFTMAX) {
+        if (p_vec) {
+#pragma unroll
+          for (int c = 0; c < BN / 2; c += 32)
+            if (n0 + c < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0 + c, p_n, lane, wall[c / 32]);
+        }
+      }
       mbar_wait_warp(tfull_bar + acc, aph, lane);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN + half * CW);
@@ -687,8 +735,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int j = 0; j < 32; ++j) v[j] = gelu_tc(v[j]);
           } else if constexpr (EPI == EPI_GELU_BWD) {
             float pre[32];
-            if (row_ok) {
-              load_row32_bf16(aux_row, n0 + c, ncols, pre, g.vec_ok);
+            if (p_vec) {
+              uint4 raw[4];
+              warp_own_rows(stg, lane, wq, raw);
+              if (c + 32 < CW && n0 + c + 32 < ncols)     // the block after this one, a whole block ahead of its use
+                warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0 + c + 32, ncols, lane, wq);
+              unpack32(raw, pre);
+            } else if (row_ok) {
+              load_row32_bf16(aux_row, n0 + c, ncols, pre, false);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) pre[j] = 0.f;
@@ -767,19 +821,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         pair_sync(lg);   // the exchange slots are reused by the next item
       } else {
-        // dS = scale * P o (dP - delta),  delta = sum_n P o dP  (softmax backward; P read from aux)
+        // dS = scale * P o (dP - delta),  delta = sum_n P o dP  (softmax backward; P read from aux, once: its
+        // 128 columns stay packed in 64 registers between the two sweeps over dP in TMEM)
         static_assert(BN == 256, "row-wise epilogues use the 256-column tile");
         const float sc = g.scale;
-        const bool vec = g.vec_ok;
+        uint4 (&praw)[CW / 32][4] = wall;      // the prefetched block, turned into own rows in place
         float delta = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < CW; c += 32) {
-          if (n0 + c >= ncols) break;
-          uint32_t rr[32];
-          tmem_ld32(taddr + c, rr);
-          if (row_ok) {
+          if (n0 + c < ncols) {                  // warp-uniform
+            uint32_t rr[32];
+            tmem_ld32(taddr + c, rr);
+            if (p_vec) {
+              warp_own_rows(stg, lane, wall[c / 32], praw[c / 32]);
+            } else {
+              float pv[32];
+              if (row_ok) {
+                load_row32_bf16(aux_row, n0 + c, ncols, pv, false);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pv[j] = 0.f;
+              }
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl)
+                praw[c / 32][sl] = make_uint4(pack_bf16(pv[8 * sl], pv[8 * sl + 1]), pack_bf16(pv[8 * sl + 2], pv[8 * sl + 3]),
+                                              pack_bf16(pv[8 * sl + 4], pv[8 * sl + 5]), pack_bf16(pv[8 * sl + 6], pv[8 * sl + 7]));
+            }
             float pv[32];
-            load_row32_bf16(aux_row, n0 + c, ncols, pv, vec);
+            unpack32(praw[c / 32], pv);
 #pragma unroll
             for (int j = 0; j < 32; ++j) delta = fmaf(pv[j], __uint_as_float(rr[j]), delta);
           }
@@ -789,21 +858,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         my[0] = delta;
         pair_sync(lg);
         delta += other[0];
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < CW; c += 32) {
-          if (n0 + c >= ncols) break;
-          uint32_t rr[32];
-          tmem_ld32(taddr + c, rr);
-          float pv[32], v[32];
-          if (row_ok) {
-            load_row32_bf16(aux_row, n0 + c, ncols, pv, vec);
-          } else {
+          if (n0 + c < ncols) {
+            uint32_t rr[32];
+            tmem_ld32(taddr + c, rr);
+            float pv[32], v[32];
+            unpack32(praw[c / 32], pv);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pv[j] = 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = sc * pv[j] * (__uint_as_float(rr[j]) - delta);
+            put(n0 + c, v, false);
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = sc * pv[j] * (__uint_as_float(rr[j]) - delta);
-          put(n0 + c, v, false);
         }
         pair_sync(lg);
       }
@@ -964,7 +1029,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
     split = 1;
     const long long units = mtts::kNumSMs / CG;      // CTAs or CTA pairs that run at a time
     if (base_items < units) {
-      split = (int)((2 * units + base_items - 1) / base_items);
+      split = (int)((2 * units) / base_items);         // at most two full rounds of work items
       if (split > a.kb_total / 4) split = a.kb_total / 4;
       if (split < 1) split = 1;
     }

@@ -72,6 +72,11 @@ def main():
         ("attn scores + softmax", 2 * B * T * Tk * D,
          lambda: gemm(qv, kv, epilogue="softmax", scale=1 / math.sqrt(dh)),
          lambda: torch.softmax((qv @ kv.transpose(-1, -2)) / math.sqrt(dh), -1)),
+        ("attn dS = dsoftmax(dO V^T)", 2 * B * T * Tk * D,
+         lambda: gemm(qv, kv, epilogue="dsoftmax", aux=P, scale=1 / math.sqrt(dh)),
+         lambda: P * ((qv @ kv.transpose(-1, -2)) - 0.5)),
+        ("ffn dgrad + gelu' (K,N)", 2 * B * T * D * F, lambda: gemm(X, W2.t(), epilogue="gelu_bwd", aux=A1),
+         lambda: torch.nn.functional.gelu(A1) * (X @ W2)),
         ("attn PV n64", 2 * B * T * Tk * D, lambda: gemm(P, kv.transpose(-1, -2)), lambda: P @ kv),
         ("attn dV (M,N) n64 k2048", 2 * B * T * Tk * D, lambda: gemm(P.transpose(-1, -2), qv.transpose(-1, -2)),
          lambda: P.transpose(-1, -2) @ qv),
