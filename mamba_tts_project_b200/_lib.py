@@ -13,7 +13,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmamba_tts_b200.so")
+# MTTS_LIB: another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("MTTS_LIB") or os.path.join(_HERE, "libmamba_tts_b200.so")
 
 F32, BF16 = 0, 1
 SCAN_CHUNK = 32

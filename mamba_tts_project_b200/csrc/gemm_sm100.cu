@@ -28,8 +28,14 @@ namespace mtts {
 namespace g100 {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // 320
+enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GELU_BWD = 2, EPI_SOFTMAX = 3, EPI_DSOFTMAX = 4 };
+// Epilogue warps: EPW / 4 per 32-lane group of TMEM, each draining its share of the tile's columns.  The epilogue is
+// a chain of dependent fixed-latency steps (tcgen05.ld -> math -> staging -> store), so what hides its latency is
+// warps: the row-wise epilogues (one k-block of MMA per tile, so the epilogue IS the kernel) and the two-output
+// GELU epilogue run 16 (softmax 82 -> 56 us, dsoftmax 103 -> 86 us at C2), the others 8 -- there the extra 32 KB
+// of store staging would cost a pipeline stage (-5 % on the K >= 512 GEMMs).
+template <int EPI>
+__host__ __device__ constexpr int epi_warps() { return (EPI == EPI_SOFTMAX || EPI == EPI_DSOFTMAX || EPI == EPI_GELU) ? 16 : 8; }
 constexpr uint32_t kABytes = BM * BK * 2;       // 16 KiB
 constexpr float kInvSqrt2 = 0.70710678118654752f;
 constexpr float kInvSqrt2Pi = 0.39894228040143268f;
@@ -37,17 +43,20 @@ constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 // CG = CTAs per MMA (tcgen05 cta_group): with CG = 2 a pair of CTAs on neighbouring SMs computes one 256 x BN tile,
 // each CTA staging its own 128 rows of A and HALF of B -- L2 -> SM traffic per flop drops by a third against two
 // independent 128 x BN tiles and the shared-memory read rate of the MMA by the same amount.
-template <int BN, int CG>
+template <int BN, int CG, int EPW>
 struct Tile {
   static constexpr uint32_t kBBytes = BN / CG * BK * 2;
-  static constexpr int kStages = (kABytes + kBBytes) == 49152 ? 4 : ((kABytes + kBBytes) == 32768 ? 6 : 8);
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr size_t kStagingBytes = (size_t)EPW * 4096;
+  static constexpr size_t kMiscBytes = 8 * (2 * 8 + 4) + 16;   // barriers of up to 8 stages + 4 + the TMEM slot
+  // as many stages as fit beside the store staging (227 KB per CTA, minus the alignment slack), at most 8
+  static constexpr int kFit = (int)((232448 - 1024 - kStagingBytes - kMiscBytes) / kStageBytes);
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr uint32_t kTmemCols = 2 * BN;
-  // stages + per-epilogue-warp store staging (32 rows x 128 B) + barriers (full, empty, tmem full/empty) + tmem
-  // slot + softmax exchange; the dynamic shared window is declared 1024-byte aligned (swizzle-128B atoms)
-  static constexpr size_t kStagingBytes = (size_t)kEpiWarps * 4096;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 8 * (2 * kStages + 4) + 16 +
-                                       sizeof(float) * 4 * 2 * 32 * 2;
+  // stages + per-epilogue-warp store staging (32 rows x 128 B; its first 256 B double as the warp's slot of the
+  // row-statistics exchange) + barriers (full, empty, tmem full/empty) + tmem slot; the dynamic shared window is
+  // declared 1024-byte aligned (swizzle-128B atoms)
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kMiscBytes;
 };
 
 struct Args {
@@ -196,6 +205,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same without the wait: several loads can be in flight before one tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// The wait that makes the registers of earlier tmem_ld32_nowait() calls valid.  The registers are tied to the
+// statement ("+r") so that the compiler cannot schedule a use of them above it; reg_tie32 ties a further block of
+// 32 registers to the same point (volatile asm statements keep their order) without emitting anything.
+__device__ __forceinline__ void tmem_wait_ld_tied(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) : : "memory");
+}
+__device__ __forceinline__ void reg_tie32(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
 // the reverse: registers -> 32 lanes x 32 columns of TMEM (row-wise epilogues park intermediate rows there)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -336,7 +367,7 @@ __device__ __forceinline__ void store_row32(void* row_base, int col, int n, cons
 template <bool kF32>
 __device__ __forceinline__ void warp_store32(unsigned char* stage, int lane, unsigned char* warp_base,
                                              long long ld_bytes, int rows_valid, int col, int n, const float* v,
-                                             bool accumulate, bool atomic) {
+                                             bool accumulate, bool atomic, const uint4* old_bf16 = nullptr) {
   constexpr int SLOTS = kF32 ? 8 : 4;      // 16-byte slots per row
   constexpr int EL = kF32 ? 4 : 8;         // elements per slot
   constexpr int PITCH = SLOTS * 16;
@@ -385,7 +416,7 @@ __device__ __forceinline__ void warp_store32(unsigned char* stage, int lane, uns
         if (accumulate) {
           float a[8], b[8];
           unpack_bf16x8(w, a);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(dst), b);
+          unpack_bf16x8(old_bf16 ? old_bf16[pass] : *reinterpret_cast<const uint4*>(dst), b);
           w = make_uint4(pack_bf16(a[0] + b[0], a[1] + b[1]), pack_bf16(a[2] + b[2], a[3] + b[3]),
                          pack_bf16(a[4] + b[4], a[5] + b[5]), pack_bf16(a[6] + b[6], a[7] + b[7]));
         }
@@ -394,6 +425,50 @@ __device__ __forceinline__ void warp_store32(unsigned char* stage, int lane, uns
     }
   }
   __syncwarp();   // the staging tile is rewritten by the next block
+}
+
+// 64 bf16 columns at a time (lane = row, v = its 64 columns starting at `col`, a multiple of 64): the rows leave as
+// whole 128-byte lines, eight lanes per row.  v is scaled by `mul` on the way (softmax normalisation).
+__device__ __forceinline__ void warp_store64_bf16(unsigned char* stage, int lane, unsigned char* warp_base,
+                                                  long long ld_bytes, int rows_valid, int col, int n, const float* v,
+                                                  float mul) {
+  {
+    const int key = lane & 7;
+    unsigned char* srow = stage + lane * 128;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) {
+      const uint4 w = make_uint4(pack_bf16(v[8 * sl] * mul, v[8 * sl + 1] * mul),
+                                 pack_bf16(v[8 * sl + 2] * mul, v[8 * sl + 3] * mul),
+                                 pack_bf16(v[8 * sl + 4] * mul, v[8 * sl + 5] * mul),
+                                 pack_bf16(v[8 * sl + 6] * mul, v[8 * sl + 7] * mul));
+      *reinterpret_cast<uint4*>(srow + ((sl ^ key) << 4)) = w;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int idx = pass * 32 + lane;
+    const int r = idx >> 3, sl = idx & 7;
+    const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 128 + ((sl ^ (r & 7)) << 4));
+    const int c = col + sl * 8;
+    if (r < rows_valid && c + 8 <= n)
+      *reinterpret_cast<uint4*>(warp_base + (long long)r * ld_bytes + (size_t)c * 2) = w;
+  }
+  __syncwarp();
+}
+
+// Prefetch of the bf16 values a warp_store32<false>(.., accumulate) will add to, in that function's own
+// (row, slot) assignment, so that the loads are in flight before the accumulator is waited for.
+__device__ __forceinline__ void warp_ldg_old32(const unsigned char* warp_base, long long ld_bytes, int rows_valid,
+                                               int col, int n, int lane, uint4 (&old)[4]) {
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int idx = pass * 32 + lane;
+    const int r = idx >> 2, c = col + (idx & 3) * 8;
+    old[pass] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && c + 8 <= n)
+      old[pass] = *reinterpret_cast<const uint4*>(warp_base + (long long)r * ld_bytes + (size_t)c * 2);
+  }
 }
 
 // The reverse for a bf16 operand of the epilogue (aux), in two steps so that the global loads can be issued long
@@ -446,15 +521,18 @@ __device__ __forceinline__ void load_row32_bf16(const void* row_base, int col, i
   }
 }
 
-enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GELU_BWD = 2, EPI_SOFTMAX = 3, EPI_DSOFTMAX = 4 };
-
-// pair barrier: the two epilogue warps that share a TMEM lane group (ids 1..4; 0 is __syncthreads)
-__device__ __forceinline__ void pair_sync(int lg) { asm volatile("bar.sync %0, 64;" ::"r"(lg + 1) : "memory"); }
+// group barrier: the PARTS epilogue warps that share a TMEM lane group (ids 1..4; 0 is __syncthreads)
+template <int PARTS>
+__device__ __forceinline__ void group_sync(int lg) {
+  asm volatile("bar.sync %0, %1;" ::"r"(lg + 1), "n"(32 * PARTS) : "memory");
+}
 
 template <int BN, int AMAJ, int BMAJ, int EPI, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(64 + 32 * epi_warps<EPI>(), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Args g) {
-  using T = Tile<BN, CG>;
+  constexpr int kEpiWarps = epi_warps<EPI>();
+  constexpr int kEpiParts = kEpiWarps / 4;
+  using T = Tile<BN, CG, kEpiWarps>;
   constexpr int BNH = BN / CG;                       // rows of B staged by one CTA
   constexpr int kStages = T::kStages;
   constexpr uint32_t kStageBytes = T::kStageBytes;
@@ -467,7 +545,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* xchg = reinterpret_cast<float*>(tmem_slot + 4);   // [4 lane groups][2 halves][32 lanes][2]
 
   unsigned long long gt_entry;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
@@ -638,8 +715,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // ===== epilogue: TMEM -> registers -> fused elementwise / row-wise work -> global =====
     const int ew = warp - 2;
     const int lg = warp & 3;             // TMEM lane group this warp may touch
-    const int half = ew >> 2;            // which half of the tile's columns
-    constexpr int CW = BN / 2;           // columns per warp
+    const int part = ew >> 2;            // which share of the tile's columns
+    constexpr int CW = (BN / kEpiParts) < 32 ? 32 : (BN / kEpiParts);   // columns per warp
+    const bool active = part * CW < BN;  // (narrow tiles have fewer 32-column blocks than warps)
     int acc = 0;
     uint32_t aph = 0;
     for (int item = cta; item < items; item += ncta) {
@@ -653,7 +731,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int row = row0 + lane;
       const bool row_ok = row < g.m;
       const int rows_valid = min(32, g.m - row0);
-      const int n0 = n_blk * BN + half * CW;     // first global column of this warp
+      const int n0 = n_blk * BN + part * CW;     // first global column of this warp
       const size_t esz = g.out_f32 ? 4 : 2;
       unsigned char* out_w = reinterpret_cast<unsigned char*>(g.out) +
                              esz * (size_t)(bo * g.c_bo + bi * g.c_bi + (long long)row0 * g.ldc);
@@ -666,7 +744,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const bool p_vec = g.vec_ok, p_f32 = g.out_f32, p_acc = g.accumulate, p_atomic = g.atomic, p_skip = g.debug & 1;
       const long long p_ldc = g.ldc, p_ldaux = g.ld_aux;
       const int p_n = g.n;
-      auto put = [&](int col, const float* v, bool to_aux) {
+      auto put = [&](int col, const float* v, bool to_aux, const uint4* old = nullptr) {
         if (p_skip) return;
         if (to_aux) {
           if (p_vec) warp_store32<false>(stg, lane, aux_w, 2 * p_ldaux, rows_valid, col, p_n, v, false, false);
@@ -675,30 +753,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (p_vec) warp_store32<true>(stg, lane, out_w, 4 * p_ldc, rows_valid, col, p_n, v, p_acc, p_atomic);
           else if (row_ok) store_row32<true>(out_row, col, p_n, v, false, p_acc, p_atomic);
         } else {
-          if (p_vec) warp_store32<false>(stg, lane, out_w, 2 * p_ldc, rows_valid, col, p_n, v, p_acc, false);
+          if (p_vec) warp_store32<false>(stg, lane, out_w, 2 * p_ldc, rows_valid, col, p_n, v, p_acc, false, old);
           else if (row_ok) store_row32<false>(out_row, col, p_n, v, false, p_acc, false);
         }
       };
       // operands of the epilogue that do not depend on the accumulator are requested before waiting for it
-      [[maybe_unused]] uint4 wq[4];                      // GELU': the next 32-column block of the pre-activation
-      [[maybe_unused]] uint4 wall[BN / 64][4];           // dsoftmax: the warp's whole block of P
-      if constexpr (EPI == EPI_GELU_BWD) {
-        if (p_vec && n0 < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0, p_n, lane, wq);
-      } else if constexpr (EPI == EPI_DSOFTMAX) {
-        if (p_vec) {
+      [[maybe_unused]] uint4 wq[4];                      // GELU': the next 32-column block of the pre-activation;
+                                                         // accumulating bf16 store: the next block of old values
+      [[maybe_unused]] uint4 wall[CW / 32][4];           // dsoftmax: the warp's whole block of P
+      const bool pre_old = EPI == EPI_STORE && p_acc && !p_f32 && p_vec;
+      if (active) {
+        if constexpr (EPI == EPI_GELU_BWD) {
+          if (p_vec && n0 < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0, p_n, lane, wq);
+        } else if constexpr (EPI == EPI_DSOFTMAX) {
+          if (p_vec) {
 #pragma unroll
-          for (int c = 0; c < BN / 2; c += 32)
-            if (n0 + c < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0 + c, p_n, lane, wall[c / 32]);
+            for (int c = 0; c < CW; c += 32)
+              if (n0 + c < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0 + c, p_n, lane, wall[c / 32]);
+          }
+        } else if constexpr (EPI == EPI_STORE) {
+          if (pre_old && n0 < p_n) warp_ldg_old32(out_w, 2 * p_ldc, rows_valid, n0, p_n, lane, wq);
         }
       }
       mbar_wait_warp(tfull_bar + acc, aph, lane);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN + half * CW);
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN + part * CW);
 
       // kernel parameters used per element are hoisted into registers: tested where they are used they cost a
       // constant-bank load and a uniform-register move per ELEMENT (measured: 2x on the whole kernel)
       const int ncols = g.n;
       if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_GELU_BWD) {
+        if (active) {
         const float* bias_n = g.bias_n;
         const bool has_bm = g.bias_m != nullptr;
         const float bm = (has_bm && row_ok) ? g.bias_m[row] : 0.f;
@@ -750,15 +835,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_tc(pre[j]);
           }
-          put(n0 + c, v, false);
+          if constexpr (EPI == EPI_STORE) {
+            if (pre_old) {
+              uint4 old[4] = {wq[0], wq[1], wq[2], wq[3]};
+              if (c + 32 < CW && n0 + c + 32 < ncols)
+                warp_ldg_old32(out_w, 2 * p_ldc, rows_valid, n0 + c + 32, ncols, lane, wq);
+              put(n0 + c, v, false, old);
+            } else {
+              put(n0 + c, v, false);
+            }
+          } else {
+            put(n0 + c, v, false);
+          }
+        }
         }
       } else if constexpr (EPI == EPI_SOFTMAX) {
-        // P = softmax_n(scale * S + key mask): the whole row lives in this tile (n <= BN); the two warps of a
-        // lane group own half of the columns each and exchange (max, sum) through shared memory.  Three sweeps over
-        // the warp's TMEM columns -- max; exp and sum, the exponentials written back to TMEM in place; normalise
-        // and store -- keep one 32-column block in registers at a time (one MUFU.EX2 per element, no spills).
-        static_assert(BN == 256, "row-wise epilogues use the 256-column tile");
-        const float sc = g.scale * kLog2e;
+        // P = softmax_n(scale * S + key mask): the whole row lives in this tile (n <= BN); the kEpiParts warps of a
+        // lane group own a share of the columns each and exchange (max, sum) through shared memory.  The warp's
+        // columns are read from TMEM ONCE and stay in registers (one MUFU.EX2 per element); the reductions run on
+        // four independent accumulators (the chains, not the issue slots, bound the two-warps-per-scheduler epilogue).
+        static_assert(BN == 256 && CW % 32 == 0, "row-wise epilogues use the 256-column tile");
+        const float sc = g.scale * kLog2e;       // > 0 (checked by the host side)
         const unsigned char* mk = g.mask ? g.mask + (size_t)bo * g.mask_bo : nullptr;
         uint32_t keep[CW / 32];                  // bit j of keep[c / 32]: column n0 + c + j takes part
 #pragma unroll
@@ -767,71 +864,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const bool on = col < ncols && (mk == nullptr || mk[col] != 0);
           keep[c / 32] = __ballot_sync(0xffffffffu, on);
         }
-        float mx = -INFINITY;
+        uint32_t sr[CW];
+#pragma unroll
+        for (int c = 0; c < CW; c += 32) tmem_ld32_nowait(taddr + c, sr + c);
+        tmem_wait_ld_tied(sr);
+#pragma unroll
+        for (int c = 32; c < CW; c += 32) reg_tie32(sr + c);
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < CW; c += 32) {
-          if (keep[c / 32] != 0u) {              // warp-uniform
-            uint32_t rr[32];
-            tmem_ld32(taddr + c, rr);
+          if (keep[c / 32] != 0xffffffffu) {     // warp-uniform: some column of the block is masked or out of range
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if ((keep[c / 32] >> j) & 1u) mx = fmaxf(mx, __uint_as_float(rr[j]) * sc);
+              if (!((keep[c / 32] >> j) & 1u)) sr[c + j] = 0xff800000u;   // -inf
           }
-        }
-        float* my = xchg + ((lg * 2 + half) * 32 + lane) * 2;
-        float* other = xchg + ((lg * 2 + (half ^ 1)) * 32 + lane) * 2;
-        my[0] = mx;
-        pair_sync(lg);
-        mx = fmaxf(mx, other[0]);
-        const float base = mx == -INFINITY ? 0.f : mx;   // fully masked row: zeros (the reference gives NaN)
-        float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < CW; c += 32) {
-          if (keep[c / 32] != 0u) {
-            uint32_t rr[32];
-            tmem_ld32(taddr + c, rr);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float e = ((keep[c / 32] >> j) & 1u) ? ex2f(fmaf(__uint_as_float(rr[j]), sc, -base)) : 0.f;
-              sum += e;
-              rr[j] = __float_as_uint(e);
-            }
-            tmem_st32(taddr + c, rr);
-          }
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(sr[c + j]));
         }
-        my[1] = sum;
-        pair_sync(lg);
-        sum += other[1];
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        // exchange slots: the head of every warp's own staging tile; the warps of this lane group are ew & 3 (mod 4)
+        float* slot = reinterpret_cast<float*>(stg);
+        auto other_slot = [&](int q) { return reinterpret_cast<float*>(staging + (size_t)(q * 4 + (ew & 3)) * 4096); };
+        slot[2 * lane] = mx;
+        group_sync<kEpiParts>(lg);
+#pragma unroll
+        for (int q = 0; q < kEpiParts; ++q) mx = fmaxf(mx, other_slot(q)[2 * lane]);
+        const float base = mx == -INFINITY ? 0.f : mx * sc;   // fully masked row: zeros (the reference gives NaN)
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        float* e = reinterpret_cast<float*>(sr);
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+          e[j] = ex2f(fmaf(__uint_as_float(sr[j]), sc, -base));      // ex2(-inf) = 0 for the masked columns
+          s4[j & 3] += e[j];
+        }
+        float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        slot[2 * lane + 1] = sum;
+        group_sync<kEpiParts>(lg);
+        sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < kEpiParts; ++q) sum += other_slot(q)[2 * lane + 1];
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        group_sync<kEpiParts>(lg);    // every warp has read the slots: the staging tiles are free for the stores
+        if (!p_skip) {
+          if (p_vec && CW % 64 == 0) {
 #pragma unroll
-        for (int c = 0; c < CW; c += 32) {
-          if (n0 + c < ncols) {
-            float v[32];
-            if (keep[c / 32] != 0u) {
-              uint32_t rr[32];
-              tmem_ld32(taddr + c, rr);
+            for (int c = 0; c < CW; c += 64)
+              if (n0 + c < ncols) warp_store64_bf16(stg, lane, out_w, 2 * p_ldc, rows_valid, n0 + c, ncols, e + c, inv);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * inv;
-            } else {
+            for (int c = 0; c < CW; c += 32) {
+              if (n0 + c < ncols) {
+                float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                for (int j = 0; j < 32; ++j) v[j] = e[c + j] * inv;
+                put(n0 + c, v, false);
+              }
             }
-            put(n0 + c, v, false);
           }
         }
-        pair_sync(lg);   // the exchange slots are reused by the next item
+        group_sync<kEpiParts>(lg);    // the staging tiles double as exchange slots of the next item
       } else {
         // dS = scale * P o (dP - delta),  delta = sum_n P o dP  (softmax backward; P read from aux, once: its
-        // 128 columns stay packed in 64 registers between the two sweeps over dP in TMEM)
-        static_assert(BN == 256, "row-wise epilogues use the 256-column tile");
+        // columns stay packed in registers between the two sweeps over dP in TMEM; 8 columns are unpacked at a time
+        // so that the sweeps fit the 96 registers of the 16-warp epilogue)
+        static_assert(BN == 256 && CW % 32 == 0, "row-wise epilogues use the 256-column tile");
         const float sc = g.scale;
         uint4 (&praw)[CW / 32][4] = wall;      // the prefetched block, turned into own rows in place
-        float delta = 0.f;
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < CW; c += 32) {
           if (n0 + c < ncols) {                  // warp-uniform
             uint32_t rr[32];
-            tmem_ld32(taddr + c, rr);
+            tmem_ld32_nowait(taddr + c, rr);
             if (p_vec) {
               warp_own_rows(stg, lane, wall[c / 32], praw[c / 32]);
             } else {
@@ -847,30 +951,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 praw[c / 32][sl] = make_uint4(pack_bf16(pv[8 * sl], pv[8 * sl + 1]), pack_bf16(pv[8 * sl + 2], pv[8 * sl + 3]),
                                               pack_bf16(pv[8 * sl + 4], pv[8 * sl + 5]), pack_bf16(pv[8 * sl + 6], pv[8 * sl + 7]));
             }
-            float pv[32];
-            unpack32(praw[c / 32], pv);
+            tmem_wait_ld_tied(rr);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) delta = fmaf(pv[j], __uint_as_float(rr[j]), delta);
+            for (int sl = 0; sl < 4; ++sl) {
+              float pv[8];
+              unpack_bf16x8(praw[c / 32][sl], pv);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d4[q & 3] = fmaf(pv[q], __uint_as_float(rr[8 * sl + q]), d4[q & 3]);
+            }
           }
         }
-        float* my = xchg + ((lg * 2 + half) * 32 + lane) * 2;
-        float* other = xchg + ((lg * 2 + (half ^ 1)) * 32 + lane) * 2;
-        my[0] = delta;
-        pair_sync(lg);
-        delta += other[0];
+        float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        reinterpret_cast<float*>(stg)[lane] = delta;       // exchange slot: the head of the warp's own staging tile
+        group_sync<kEpiParts>(lg);
+        delta = 0.f;
+#pragma unroll
+        for (int q = 0; q < kEpiParts; ++q)
+          delta += reinterpret_cast<float*>(staging + (size_t)(q * 4 + (ew & 3)) * 4096)[lane];
+        group_sync<kEpiParts>(lg);      // all slots read: the staging tiles are free for the stores
 #pragma unroll
         for (int c = 0; c < CW; c += 32) {
           if (n0 + c < ncols) {
             uint32_t rr[32];
             tmem_ld32(taddr + c, rr);
-            float pv[32], v[32];
-            unpack32(praw[c / 32], pv);
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = sc * pv[j] * (__uint_as_float(rr[j]) - delta);
+            for (int sl = 0; sl < 4; ++sl) {
+              float pv[8];
+              unpack_bf16x8(praw[c / 32][sl], pv);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[8 * sl + q] = sc * pv[q] * (__uint_as_float(rr[8 * sl + q]) - delta);
+            }
             put(n0 + c, v, false);
           }
         }
-        pair_sync(lg);
+        group_sync<kEpiParts>(lg);
       }
 
       tc_fence_before();
@@ -948,7 +1063,7 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t d0, int64_t d1,
 template <int BN, int AMAJ, int BMAJ, int EPI, int CG>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Args& a, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, AMAJ, BMAJ, EPI, CG>;
-  const size_t smem = Tile<BN, CG>::kSmemBytes;
+  const size_t smem = Tile<BN, CG, epi_warps<EPI>()>::kSmemBytes;
   static bool configured = false;   // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -957,7 +1072,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Args& a, i
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid * CG);          // `grid` CTAs or CTA pairs
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(64 + 32 * epi_warps<EPI>());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1005,6 +1120,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
     return MTTS_ERR_ALIGN;
   const bool row_epi = p->epilogue == EPI_SOFTMAX || p->epilogue == EPI_DSOFTMAX;
   if (row_epi && (p->n > 256 || p->out_dtype != MTTS_BF16)) return MTTS_ERR_SHAPE;
+  if (p->epilogue == EPI_SOFTMAX && !(p->scale > 0.f)) return MTTS_ERR_UNSUPPORTED;   // the row max is taken before scaling
   if ((p->epilogue == EPI_GELU_BWD || p->epilogue == EPI_DSOFTMAX) && !p->aux) return MTTS_ERR_NULL;
   if (p->epilogue != EPI_STORE && p->out_dtype != MTTS_BF16) return MTTS_ERR_DTYPE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
