@@ -53,10 +53,13 @@ def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None,
              else initial_state[:, sl].float().clone())
         deltaA = torch.exp(torch.einsum("bdl,dn->bdln", dl, A[sl]))
         deltaB_u = torch.einsum("bdl,bnl,bdl->bdln", dl, Bf, uf)
+        # (unbind, not deltaA[:, :, i]: same values, but the backward of T slices is ONE stack instead of T
+        # zero-filled (batch, Di, T, N) tensors -- the C2-shape fixtures take minutes instead of hours)
+        dA_t, dBu_t, C_t = deltaA.unbind(2), deltaB_u.unbind(2), Cf.unbind(2)
         ys = []
         for i in range(T):
-            x = deltaA[:, :, i] * x + deltaB_u[:, :, i]
-            ys.append(torch.einsum("bdn,bn->bd", x, Cf[:, :, i]))
+            x = dA_t[i] * x + dBu_t[i]
+            ys.append(torch.einsum("bdn,bn->bd", x, C_t[i]))
         y = torch.stack(ys, dim=2) if T > 0 else uf.new_zeros((batch, uf.shape[1], 0))
         if D is not None:
             y = y + uf * D[sl].float()[None, :, None]
