@@ -127,10 +127,11 @@ def build_decoder(cfg, device):
 
 
 def train_step(model, inp, reducer=None):
+    from mamba_tts_project_b200 import codec_ce_loss
     model.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         logits = model(inp["tokens"], inp["text"], inp["z"])
-    loss = F.cross_entropy(logits.float().view(-1, logits.shape[-1]), inp["targets"].view(-1))
+    loss = codec_ce_loss(logits, inp["targets"])      # train.py:31-42 (ignore_index = 0), fused CE kernel
     loss.backward()
     if reducer is not None:
         reducer.finish()
@@ -274,14 +275,14 @@ def run_reference_arm(args):
         return
     steps = max(1, args.steps)
     warm = min(args.warmup, 1)
-    tps, dt, cores, sample = cpu_oracle_tokens_per_s(C2, steps, warm, t_sample=64)
+    tps, dt, cores, sample = cpu_oracle_tokens_per_s(C2, steps, warm, t_sample=128)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(tps, 2), "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "C2: 12-layer d_model 512 MambaTTSDecoder fwd+bwd, T_text 256 "
-                               "(CPU reference path on a bounded sample: B=1, T_audio=64 per step)"},
+                               "(CPU reference path on a bounded sample: B=1, T_audio=128 per step, the same sample as cpu_baseline)"},
         "cpu_baseline": {"value": round(tps, 2), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": round(tps, 2), "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -393,13 +394,11 @@ def run_ours(args):
     # per step: the ~1600 per-kernel launch gaps disappear.  Data parallel: the gradient all-reduce follows
     # the replay (GradAllReducer.finish()).
     from mamba_tts_project_b200 import GraphedForwardBackward
-    if reducer is not None:
-        reducer.pause()          # no all-reduce from inside the capture
-    gstep = GraphedForwardBackward(model, inp["tokens"], inp["text"], inp["z"], inp["targets"])
+    gstep = GraphedForwardBackward(model, inp["tokens"], inp["text"], inp["z"], inp["targets"], reducer=reducer)
 
     def graphed_step(src):
         loss = gstep(src["tokens"], src["text"], src["z"], src["targets"])
-        if reducer is not None:
+        if gstep.reduce_after_replay:      # the collectives could not be captured: reduce after the replay
             reducer.finish()
         return loss
 
@@ -436,7 +435,7 @@ def run_ours(args):
            "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_s.item() * 1e3, 3),
            "api": "GraphedForwardBackward(decoder, ...)(pinned host tokens/text/z/targets) = "
                   "MambaTTSDecoder.forward + cross_entropy + backward replayed from a CUDA graph"
-                  + (" + GradAllReducer.finish()" if world > 1 else "") + ", loss.item() every step"}
+                  + (" + gradient all-reduce" if world > 1 else "") + ", loss.item() every step"}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
@@ -448,7 +447,11 @@ def run_ours(args):
                    "global_batch": world * B, "seq_len": T, "d_state": N, "vocab": cfg["vocab"],
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "working set (>10 GB of activations per step) is far larger than the 126 MB L2",
-                   "execution": "CUDA-graph replay of forward + loss + backward (one graph launch per step)",
+                   "execution": "CUDA-graph replay of forward + loss + backward (one graph launch per step)"
+                                + ("" if world == 1 else
+                                   (", bucketed NCCL all-reduce after the replay" if gstep.reduce_after_replay else
+                                    ", bucketed NCCL all-reduces captured inside the graph (forked off the backward "
+                                    "as each bucket completes)")),
                    "eager_ms_per_step": round(eager_ms, 3),
                    "loss": round(float(loss_val), 4)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
@@ -473,8 +476,211 @@ def run_ours(args):
     if rank == 0:
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
+    _teardown(dist, world)
+
+
+
+# ---------------------------------------------------------------------------------------------
+# the other two multi-GPU workloads of BASELINE.json (not the driver's default line): --workload c3 / c5
+# ---------------------------------------------------------------------------------------------
+C5 = dict(vocab=1024, d_model=1024, n_layers=24, n_heads=16, d_ff=4096, d_style=256, d_state=16,
+          batch=64, t_audio=4096, t_text=128, t_ref=128, micro_batch=8)
+
+
+def _teardown(dist, world):
+    """Leave without tearing the communicator down: a CUDA graph that captured NCCL work keeps it referenced, and
+    destroy_process_group() then waits forever (observed at N = 2).  All ranks meet, drain the GPU and exit."""
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _dist_setup():
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU path for the product")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    return dist, world, rank, local, dev, json_out, barrier, max_over_ranks
+
+
+def run_c3(args):
+    """BASELINE configs[2]: batched greedy decode_step generation, the C2 model, T_kv 256, 1500 steps; the batch
+    of 64 utterances is sharded over the GPUs (--decode-weak: 64 PER GPU instead), no collective on the data path."""
+    dist, world, rank, local, dev, json_out, barrier, max_over_ranks = _dist_setup()
+    from mamba_tts_project_b200 import _lib
+    _lib.load()
+    cfg = C2
+    B = 64 if args.decode_weak else 64 // world
+    steps = args.decode_steps
+    model = build_decoder(cfg, dev).eval()
+    g = torch.Generator().manual_seed(1 + rank)
+    text = torch.randn(B, cfg["t_text"], cfg["d_model"], generator=g)
+    z = torch.randn(B, cfg["d_style"], generator=g)
+    text_p, z_p = text.pin_memory(), z.pin_memory()
+    first = torch.ones(B, 1, dtype=torch.long, device=dev)
+    text_d, z_d = text.to(dev), z.to(dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        model.generate(first, 16, text_d, z_d, dtype=torch.bfloat16)
+    sampler = ClockSampler(local)
+    sampler.start()
+    walls, loops = [], []
+    n0 = _lib.launch_count
+    for _ in range(max(1, min(args.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        toks = model.generate(first, steps, text_d, z_d, dtype=torch.bfloat16)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+        e0, e1, ns = model.last_generate_events
+        loops.append(e0.elapsed_time(e1) / ns)
+    launches = _lib.launch_count - n0
+    # e2e: host (pinned) conditioning copied in, the generated ids copied back
+    barrier()
+    t0 = time.perf_counter()
+    out_ids = model.generate(first, steps, text_p.to(dev, non_blocking=True), z_p.to(dev, non_blocking=True),
+                             dtype=torch.bfloat16).cpu()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    wall = max_over_ranks(min(walls))
+    loop_ms = max_over_ranks(min(loops))
+    e2e_s = max_over_ranks(e2e_s)
+    e = 2
+    D, L = cfg["d_model"], cfg["n_layers"]
+    Di, N, W = 2 * D, cfg["d_state"], 4
+    layer_params = sum(p.numel() for p in model.layers[0].parameters())
+    step_bytes = L * (2 * B * Di * N * 4 + 2 * B * Di * W * e + 2 * B * cfg["t_text"] * D * e + e * layer_params) \
+        + e * (cfg["vocab"] * D)
+    peak, peak_src = measured_peaks()
+    line = {
+        "metric": "decoder_decode_tokens_per_sec", "value": round(world * B * steps / wall, 1), "unit": UNIT,
+        "n_gpus": world, "steps": steps, "warmup": 16, "ms_per_step": round(wall / steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak" if args.decode_weak else "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"C3: greedy decode_step generation, 12-layer d_model 512, T_kv 256, {steps} steps, "
+                               f"B={B} per GPU ({'64 per GPU' if args.decode_weak else '64 utterances sharded'}), "
+                               "per-layer conv / SSM state cache, CUDA-graph replay of one step",
+                   "global_batch": world * B, "parallelism": f"shard{world}" if world > 1 else "single",
+                   "collectives": "none (decode is shard-local)"},
+        "clocks": clocks,
+        "e2e": {"value": round(world * B * steps / e2e_s, 1), "unit": UNIT,
+                "h2d_bytes_per_step": (text.numel() + z.numel()) * 4 // steps, "d2h_bytes_per_step": B * 8,
+                "api": "MambaTTSDecoder.generate(first, steps, text, z) with pinned host conditioning copied in "
+                       "and the generated ids copied back; includes K/V + FiLM precompute and graph capture"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "one replayed decode step (all kernels)", "bound": "hbm",
+                     "achieved": round(step_bytes / loop_ms / 1e6, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(step_bytes / loop_ms / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": step_bytes, "ms_per_launch": round(loop_ms, 4),
+                     "note": "steady-state step time from CUDA events around the replay loop, max over ranks"},
+    }
+    if rank == 0:
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
+    _teardown(dist, world)
+
+
+def run_c5(args):
+    """BASELINE configs[4]: 24 x d_model 1024 training step (fwd + CE + bwd + all-reduce + clip + Adam) with
+    ref_hidden built from the decoder's embeddings ([ref || text] cross-attention) and FiLM, GLOBAL batch 64 x T 4096
+    sharded over the GPUs (strong scaling), micro-batches of 8 on every GPU."""
+    dist, world, rank, local, dev, json_out, barrier, max_over_ranks = _dist_setup()
+    from mamba_tts_project_b200 import MambaTTSDecoder, TrainStep, _lib
+    from mamba_tts_project_b200.dp import GradAllReducer, broadcast_parameters
+    _lib.load()
+    cfg = C5
+    Bg, T = cfg["batch"], cfg["t_audio"]
+    B = Bg // world
+    torch.manual_seed(0)
+    dec = MambaTTSDecoder(cfg["vocab"], d_model=cfg["d_model"], n_layers=cfg["n_layers"], n_heads=cfg["n_heads"],
+                          d_ff=cfg["d_ff"], d_style=cfg["d_style"], max_len=8192, num_quantizers=1,
+                          d_state=cfg["d_state"]).to(dev)
+    reducer = None
+    if world > 1:
+        broadcast_parameters(dec)
+        reducer = GradAllReducer(dec, bucket_bytes=64 << 20)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = dict(tok=torch.randint(1, cfg["vocab"], (B, T), generator=g),
+                text=torch.randn(B, cfg["t_text"], cfg["d_model"], generator=g),
+                z=torch.randn(B, cfg["d_style"], generator=g),
+                voice=torch.randint(1, cfg["vocab"], (B, 1, cfg["t_ref"]), generator=g),
+                tmask=torch.ones(B, cfg["t_text"], dtype=torch.bool))
+    host = {k: v.pin_memory() for k, v in host.items()}
+    devin = {k: v.to(dev) for k, v in host.items()}
+    step = TrainStep(dec, micro_batch=min(cfg["micro_batch"], B), reducer=reducer, world_size=world)
+
+    def one(src):
+        return step(src["tok"], src["text"], src["z"], text_mask=src["tmask"], ref_tokens=src["voice"])
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        one(devin)
+    nsteps = max(1, min(args.steps, 3))
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(nsteps):
+        loss = one(devin)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count - n0
+    ms = max_over_ranks(e0.elapsed_time(e1) / nsteps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        loss_val = one({k: v.to(dev, non_blocking=True) for k, v in host.items()}).item()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / nsteps)
+    clocks = sampler.stop()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    line = {
+        "metric": METRIC, "value": round(Bg * T / ms * 1e3, 1), "unit": UNIT, "n_gpus": world, "steps": nsteps,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(ms, 2), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C5: 24-layer d_model 1024 (16 heads, d_ff 4096) MambaTTSDecoder training step: fwd + CE "
+                               "+ bwd + NCCL all-reduce + clip_grad_norm + Adam, ref_hidden from the decoder's own "
+                               f"embeddings, [ref {cfg['t_ref']} || text {cfg['t_text']}] cross-attention + FiLM, "
+                               f"global B={Bg} x T_audio={T}, {B} per GPU in micro-batches of {min(cfg['micro_batch'], B)}",
+                   "global_batch": Bg, "seq_len": T, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "params": sum(p.numel() for p in dec.parameters()),
+                   "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1), "loss": round(float(loss_val), 4),
+                   "all_reduce": "bucketed (64 MB), launched from the gradient hooks of the last micro-batch: "
+                                 "overlaps the rest of that backward"},
+        "clocks": clocks,
+        "e2e": {"value": round(Bg * T / e2e_s, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_s * 1e3, 2),
+                "api": "TrainStep(decoder, micro_batch=8, reducer)(pinned host tokens / text / z / voice-prompt ids), "
+                       "loss.item() every step"},
+        "gpu_launches": launches,
+    }
+    if rank == 0:
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
+    _teardown(dist, world)
 
 
 def main():
@@ -484,9 +690,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 (default, the driver's line): BASELINE configs[1]; c3: decode, configs[2]; c5: configs[4]")
+    ap.add_argument("--decode-steps", type=int, default=1500)
+    ap.add_argument("--decode-weak", action="store_true", help="c3: 64 utterances PER GPU instead of 64 in total")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c3":
+        run_c3(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

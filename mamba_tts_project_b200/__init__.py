@@ -10,7 +10,8 @@ CUDA-only.  The shared library must have been built (``python -m mamba_tts_proje
 importing this package does not need a GPU, calling any op does.
 """
 from . import _lib
-from .style import LengthRegulator
+from .style import (LengthRegulator, StyleConditioningPipeline, StyleDecoderCrossAttention, StyleProjection,
+                    StyleTextCrossAttention)
 from .data import PreprocessedItems, collate_codec_batch
 from .decoder import (CrossAttention, GenerationContext, MambaTTSDecoder, MambaTTSDecoderLayer,
                       flatten_codes, unflatten_codes)
@@ -20,7 +21,8 @@ from .ops import (causal_conv1d_fn, causal_conv1d_update, cross_attn_decode, cro
                   mamba_decode_step, mamba_inner_fn, selective_scan_fn, selective_state_update,
                   skinny_linear, gemm_bf16, bias_gelu, colsum)
 
-__all__ = ["TrainStep", "GraphedForwardBackward", "codec_ce_loss", "embed_codec_tokens", "Mamba", "MambaTTSDecoder", "MambaTTSDecoderLayer", "CrossAttention", "GenerationContext", "flatten_codes", "unflatten_codes", "LengthRegulator", "PreprocessedItems", "collate_codec_batch",
+__all__ = ["TrainStep", "GraphedForwardBackward", "codec_ce_loss", "embed_codec_tokens", "Mamba", "MambaTTSDecoder", "MambaTTSDecoderLayer", "CrossAttention", "GenerationContext", "flatten_codes", "unflatten_codes", "LengthRegulator", "StyleConditioningPipeline", "StyleProjection", "StyleTextCrossAttention",
+           "StyleDecoderCrossAttention", "PreprocessedItems", "collate_codec_batch",
            "selective_scan_fn", "selective_state_update", "causal_conv1d_fn", "causal_conv1d_update",
            "mamba_inner_fn", "mamba_decode_step", "cross_attn_decode", "cross_attn_block_decode", "add_layernorm", "skinny_linear", "gemm_bf16", "bias_gelu", "colsum"]
 __version__ = "0.1.0"

@@ -256,12 +256,11 @@ class MambaTTSDecoder(nn.Module):
         if audio_tokens.dim() == 3:
             B, Q, T = audio_tokens.shape
             audio_tokens = audio_tokens.reshape(B, Q * T)
-            quant_ids = torch.arange(Q, device=audio_tokens.device).repeat_interleave(T)
-            quant_ids = quant_ids.unsqueeze(0).expand(B, -1)
+            quant_row = torch.arange(Q, device=audio_tokens.device).repeat_interleave(T)
             pos_ids = torch.arange(T, device=audio_tokens.device).repeat(Q)  # train.py:123 (D4)
         elif audio_tokens.dim() == 2:
             B, T = audio_tokens.shape
-            quant_ids = torch.zeros_like(audio_tokens)
+            quant_row = torch.zeros(T, dtype=torch.long, device=audio_tokens.device)
             pos_ids = torch.arange(T, device=audio_tokens.device)
         else:
             raise ValueError("audio_tokens must be (B, T) or (B, Q, T)")
@@ -270,8 +269,14 @@ class MambaTTSDecoder(nn.Module):
                 "text_mask must be shape (B, T_text) with dtype=bool")
         memory, mask = _join_memory(text_hidden, text_mask, ref_hidden, ref_mask)
 
-        x = self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None] + self.quant_embed(quant_ids)
-        x, delta, dbias = x.float(), None, None
+        if self.token_embed.weight.dtype == torch.float32 and self.token_embed.weight.shape[1] % 4 == 0:
+            # one launch: gather + (tok + pos) + quant, backward = scatter-add with the batch pre-summed for pos / quant
+            x = ops.embed_sum(audio_tokens, pos_ids, quant_row, self.token_embed.weight, self.pos_embed.weight,
+                              self.quant_embed.weight)
+        else:
+            x = (self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None]
+                 + self.quant_embed(quant_row)[None]).float()
+        delta, dbias = None, None
         for layer in self.layers:
             x, delta, dbias, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask,
                                                      delta_bias=dbias)

@@ -15,6 +15,8 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 
 def embed_codec_tokens(tokens_3d, decoder):
     """tokens_3d (B, Q, T) codec ids -> (ref_hidden (B, Q*T, d_model), mask (B, Q*T) True = pad)."""
@@ -22,14 +24,20 @@ def embed_codec_tokens(tokens_3d, decoder):
     flat = tokens_3d.reshape(B, Q * T_ref)
     quant_ids = torch.arange(Q, device=flat.device).repeat_interleave(T_ref)
     pos_ids = torch.arange(T_ref, device=flat.device).repeat(Q)
-    ref_hidden = (decoder.token_embed(flat) + decoder.pos_embed(pos_ids)[None]
-                  + decoder.quant_embed(quant_ids)[None])
+    if flat.is_cuda and decoder.token_embed.weight.dtype == torch.float32 and decoder.token_embed.weight.shape[1] % 4 == 0:
+        ref_hidden = ops.embed_sum(flat, pos_ids, quant_ids, decoder.token_embed.weight, decoder.pos_embed.weight,
+                                   decoder.quant_embed.weight)
+    else:
+        ref_hidden = (decoder.token_embed(flat) + decoder.pos_embed(pos_ids)[None]
+                      + decoder.quant_embed(quant_ids)[None])
     return ref_hidden, (tokens_3d == 0).reshape(B, Q * T_ref)
 
 
 def codec_ce_loss(logits, targets, pad_id=0):
     """logits (B, T, V), targets (B, T) -> mean cross entropy over targets != pad_id."""
     B, T, V = logits.shape
+    if logits.is_cuda:      # one pass over the logits in their own dtype: loss and d loss / d logits together
+        return ops.ce_loss(logits, targets, ignore_index=pad_id)
     return F.cross_entropy(logits.reshape(B * T, V).float(), targets.reshape(B * T),
                            ignore_index=pad_id)
 
@@ -43,7 +51,11 @@ class TrainStep:
         self.decoder, self.max_norm, self.pad_id = decoder, max_norm, pad_id
         self.reducer, self.world_size = reducer, world_size
         self.amp_dtype, self.micro_batch = amp_dtype, micro_batch
-        self.optim = torch.optim.Adam(decoder.parameters(), lr=lr, fused=fused_adam)
+        # clip_grad_norm_ + Adam as two launches over all parameters (ops.FusedClipAdam); fused_adam=False keeps
+        # torch.optim.Adam + torch's clip (the arithmetic the fused kernels are tested against)
+        self.fused = bool(fused_adam) and next(decoder.parameters()).is_cuda
+        self.optim = (ops.FusedClipAdam(decoder.parameters(), lr=lr, max_norm=max_norm) if self.fused
+                      else torch.optim.Adam(decoder.parameters(), lr=lr))
 
     def __call__(self, audio_tokens, text_hidden, z_style, targets=None, text_mask=None,
                  ref_hidden=None, ref_mask=None, ref_tokens=None):
@@ -70,10 +82,14 @@ class TrainStep:
                 logits = self.decoder(audio_tokens[sl], text_hidden[sl], z_style[sl], opt(text_mask),
                                       rh, rm)
             V = logits.shape[-1]
-            loss_sum = F.cross_entropy(logits.reshape(-1, V).float(), targets[sl].reshape(-1),
-                                       ignore_index=self.pad_id, reduction="sum")
             # averaged gradients x world_size / global token count == gradient of the global mean
-            loss = loss_sum * (self.world_size / n_valid)
+            if logits.is_cuda:
+                loss = ops.ce_loss(logits, targets[sl], ignore_index=self.pad_id, n_valid=n_valid / self.world_size)
+                loss_sum = loss.detach() * (n_valid / self.world_size)
+            else:
+                loss_sum = F.cross_entropy(logits.reshape(-1, V).float(), targets[sl].reshape(-1),
+                                           ignore_index=self.pad_id, reduction="sum")
+                loss = loss_sum * (self.world_size / n_valid)
             if self.reducer is not None and k + 1 < len(starts):
                 self.reducer.pause()          # only the last micro-batch triggers the all-reduce
             loss.backward()
@@ -82,7 +98,8 @@ class TrainStep:
             total = total + loss_sum.detach()
         if self.reducer is not None:
             self.reducer.finish()
-        torch.nn.utils.clip_grad_norm_(self.decoder.parameters(), self.max_norm)
+        if not self.fused:
+            torch.nn.utils.clip_grad_norm_(self.decoder.parameters(), self.max_norm)
         self.optim.step()
         return total / n_valid   # this rank's share of the global mean loss
 
@@ -102,40 +119,64 @@ class GraphedForwardBackward:
     ``GradAllReducer.finish()`` after it (the all-reduce then runs after the backward, not under it)."""
 
     def __init__(self, decoder, tokens, text_hidden, z_style, targets=None, amp_dtype=torch.bfloat16,
-                 pad_id=0, warmup=3):
+                 pad_id=0, warmup=3, reducer=None):
+        """``reducer``: a ``dp.GradAllReducer`` over ``decoder`` -- its bucketed NCCL all-reduces are then captured
+        INSIDE the graph, each one forked off the backward at the point where its bucket is complete, so a replay
+        overlaps communication with the rest of the backward exactly like the eager hooks do (and ``finish()`` must
+        not be called after a replay: it is part of it).  If the capture of the collectives fails (backend that
+        cannot be captured), the graph is re-captured without them and ``reduce_after_replay`` is set: the caller's
+        ``reducer.finish()`` then follows each replay as before."""
         self.decoder, self.amp_dtype, self.pad_id = decoder, amp_dtype, pad_id
+        self.reducer, self.reduce_after_replay = reducer, False
         dev = next(decoder.parameters()).device
         targets = tokens if targets is None else targets
         self._in = [torch.empty(t.shape, dtype=t.dtype, device=dev)
                     for t in (tokens, text_hidden, z_style, targets)]
         for dst, src in zip(self._in, (tokens, text_hidden, z_style, targets)):
             dst.copy_(src, non_blocking=True)
+        if reducer is not None:
+            reducer.resume()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):          # warm-up: lazy initialisation, autotuning, workspaces
+        with torch.cuda.stream(side):          # warm-up: lazy initialisation, autotuning, workspaces, NCCL channels
             for _ in range(warmup):
                 self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        decoder.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
         from . import _lib
+        try:
+            self._capture(_lib)
+        except Exception:
+            if reducer is None:
+                raise
+            torch.cuda.synchronize()
+            reducer.reset()
+            reducer.pause()
+            self.reducer, self.reduce_after_replay = None, True
+            self._capture(_lib)
+            reducer.resume()
+        # the graph writes its gradients into THESE tensors on every replay
+        self._params = [p for p in decoder.parameters() if p.grad is not None]
+        self._grads = [p.grad for p in self._params]
+
+    def _capture(self, _lib):
+        self.graph = torch.cuda.CUDAGraph()
+        self.decoder.zero_grad(set_to_none=True)
         n0 = _lib.launch_count
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
         self.library_launches = _lib.launch_count - n0     # kernels of the C-ABI library inside one replay
-        # the graph writes its gradients into THESE tensors on every replay
-        self._params = [p for p in decoder.parameters() if p.grad is not None]
-        self._grads = [p.grad for p in self._params]
 
     def _fwd_bwd(self):
         tok, text, z, tgt = self._in
         self.decoder.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             logits = self.decoder(tok, text, z)
-        V = logits.shape[-1]
-        kw = {} if self.pad_id is None else {"ignore_index": self.pad_id}
-        loss = F.cross_entropy(logits.reshape(-1, V).float(), tgt.reshape(-1), **kw)
+        # (ignore_index = -1 never matches a codec id: every token counts)
+        loss = ops.ce_loss(logits, tgt, ignore_index=-1 if self.pad_id is None else self.pad_id)
         loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()          # waits for the bucket all-reduces launched by the gradient hooks
         return loss.detach()
 
     def __call__(self, tokens, text_hidden, z_style, targets=None):
