@@ -515,14 +515,17 @@ int mtts_gemm_bf16(const mtts_gemm_bf16_params* p, mtts_stream_t stream);
  * Epilogues:
  *   MTTS_EPI_STORE     C = acc + bias_n[n] + bias_m[m]                      (either bias may be NULL)
  *   MTTS_EPI_GELU      aux = pre = acc + bias_n (bf16, optional);  C = gelu(pre)        exact-erf GELU
+ *                      with flag MTTS_GEMM_AUX_GELU_GRAD: aux = gelu'(pre) instead (one tanh serves both)
  *   MTTS_EPI_GELU_BWD  C = acc * gelu'(aux)                                 aux = the forward's pre (bf16)
+ *   MTTS_EPI_MUL_AUX   C = acc * aux                                        aux = the forward's gelu'(pre) (bf16)
  *   MTTS_EPI_SOFTMAX   C = softmax_n(scale * acc + key mask)                n <= 256; mask (batch_outer, n)
  *                      uint8, 1 = attend, NULL = all; a fully masked row gives zeros
  *   MTTS_EPI_DSOFTMAX  C = scale * P o (acc - sum_n P o acc)                aux = P (bf16), n <= 256
  * aux is addressed like C with ld_aux / aux_bo_stride / aux_bi_stride.
  * ------------------------------------------------------------------------------------------- */
-enum { MTTS_GEMM_SINGLE_CTA = 1 };
-enum { MTTS_EPI_STORE = 0, MTTS_EPI_GELU = 1, MTTS_EPI_GELU_BWD = 2, MTTS_EPI_SOFTMAX = 3, MTTS_EPI_DSOFTMAX = 4 };
+enum { MTTS_GEMM_SINGLE_CTA = 1, MTTS_GEMM_AUX_GELU_GRAD = 2 };
+enum { MTTS_EPI_STORE = 0, MTTS_EPI_GELU = 1, MTTS_EPI_GELU_BWD = 2, MTTS_EPI_SOFTMAX = 3, MTTS_EPI_DSOFTMAX = 4,
+       MTTS_EPI_MUL_AUX = 5 };
 typedef struct {
   int32_t m, n, k;
   int32_t batch_outer, batch_inner;
@@ -545,9 +548,86 @@ typedef struct {
   const uint8_t* mask;
   int64_t mask_bo_stride;
   float scale;
-  int32_t flags;         /* MTTS_GEMM_SINGLE_CTA: never pair CTAs (cta_group::1 tiles of 128 rows; measurements) */
+  int32_t flags;         /* MTTS_GEMM_SINGLE_CTA: never pair CTAs (cta_group::1 tiles of 128 rows; measurements);
+                            MTTS_GEMM_AUX_GELU_GRAD: see MTTS_EPI_GELU */
 } mtts_gemm_params;
 int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * film_ffn_fwd / film_ffn_bwd -- the FiLM'd feed-forward branch of a decoder layer as ONE call each
+ * (mamba_decoder.py:38-48,81-89: gamma/beta FiLM on LayerNorm(x), Linear -> GELU -> Linear), bf16 tensor-core path:
+ *   fwd:  [x_out = x + delta (+ delta_bias);  h = FiLM(LN(x_out))]        when ln.x != NULL (mtts_add_layernorm_fwd)
+ *         act = gelu(h W1^T + b1), gprime = gelu'(.)                      one mtts_gemm, both from its epilogue
+ *         f   = act W2^T                                                  (W2's bias rides into the next add_layernorm)
+ *   bwd:  dpre = (df W2) o gprime;  dW2 = df^T act;  dW1 = dpre^T h;  db1 = colsum(dpre);  dh = dpre W1  (dh optional)
+ * tokens = rows of every activation; h (tokens, d_model), act / gprime / dpre (tokens, d_ff), f / df / dh
+ * (tokens, d_model): bf16, contiguous; w1 (d_ff, d_model), w2 (d_model, d_ff): bf16; b1 fp32 or NULL;
+ * dw1 / dw2 fp32 (overwritten), db1 fp32 (d_ff) or NULL, ACCUMULATED INTO (zero it first).  d_model, d_ff multiples of 8.
+ * The same struct serves both directions: the forward reads h (or produces it through ln) and writes
+ * act / gprime / f; the backward reads h / act / gprime / df and writes dpre / dw1 / db1 / dw2 / dh.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t tokens;
+  int32_t d_model, d_ff;
+  mtts_add_layernorm_fwd_params ln; /* ln.x == NULL: h is given; else ln.out must be h and ln.io_dtype MTTS_BF16 */
+  const void* h;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  void* act;
+  void* gprime;
+  void* f;
+  const void* df;
+  void* dpre;
+  float* dw1;
+  float* db1;
+  float* dw2;
+  void* dh; /* or NULL */
+} mtts_film_ffn_params;
+int mtts_film_ffn_fwd(const mtts_film_ffn_params* p, mtts_stream_t stream);
+int mtts_film_ffn_bwd(const mtts_film_ffn_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * cross_attn_fwd / cross_attn_bwd -- nn.MultiheadAttention(batch_first=True) of the teacher-forced path
+ * (mamba_decoder.py:32-36,72-77; key_padding_mask = ~mask) without its out-projection bias, as ONE call each; every
+ * contraction is an mtts_gemm launch (q / kv projections, QK^T with scale + key mask + softmax in the epilogue,
+ * PV, out projection; backward: dO, dW_o, dV = P^T dO, dS = dsoftmax(dO V^T), dQ = dS K, dK = dS^T Q, dW_in,
+ * db_in, d query, d memory).  t_kv <= 256, head_dim and d_model multiples of 8.
+ *   query (batch, t_q, E), memory (batch, t_kv, E): bf16 contiguous;  w_in (3E, E) = [Wq; Wk; Wv], w_out (E, E): bf16;
+ *   b_in (3E) fp32;  mask (batch, t_kv) uint8, 1 = attend, or NULL.
+ *   saved by the forward (caller's buffers): q (batch, t_q, E), kv (batch, t_kv, 2E), p (batch, heads, t_q, t_kvp)
+ *   with t_kvp = t_kv rounded up to 8, o (batch, t_q, E);  out (batch, t_q, E).
+ *   backward: dout (batch, t_q, E); workspaces d_o (batch, t_q, E), ds (like p), dq (like q), dkv (like kv);
+ *   results dw_in (3E, E), dw_out (E, E) fp32 overwritten, db_in (3E) fp32 ACCUMULATED INTO, dquery / dmemory
+ *   (like query / memory; either may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, t_q, t_kv, d_model, heads;
+  int32_t reserved;
+  const void* query;
+  const void* memory;
+  const void* w_in;
+  const float* b_in;
+  const void* w_out;
+  const uint8_t* mask;
+  void* q;
+  void* kv;
+  void* p;
+  void* o;
+  void* out;
+  const void* dout;
+  void* d_o;
+  void* ds;
+  void* dq;
+  void* dkv;
+  float* dw_in;
+  float* db_in;
+  float* dw_out;
+  void* dquery;
+  void* dmemory;
+} mtts_cross_attn_params;
+int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
+int mtts_cross_attn_bwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FFN / projection glue (mamba_decoder.py:39-43,86-88: Linear -> GELU -> Linear, and the bias gradients

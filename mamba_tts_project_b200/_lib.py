@@ -144,8 +144,8 @@ GemmParams = _struct("GemmParams", """
     p:bias_n p:bias_m
     p:aux l:ld_aux l:aux_bo_stride l:aux_bi_stride
     p:mask l:mask_bo_stride f:scale i:flags""")
-GEMM_SINGLE_CTA = 1
-EPI_STORE, EPI_GELU, EPI_GELU_BWD, EPI_SOFTMAX, EPI_DSOFTMAX = range(5)
+GEMM_SINGLE_CTA, GEMM_AUX_GELU_GRAD = 1, 2
+EPI_STORE, EPI_GELU, EPI_GELU_BWD, EPI_SOFTMAX, EPI_DSOFTMAX, EPI_MUL_AUX = range(6)
 
 EmbedSumParams = _struct("EmbedSumParams", """
     i:batch i:seqlen i:dim i:reserved p:tokens p:pos_ids p:quant_ids p:token_embed p:pos_embed p:quant_embed p:x""")
@@ -157,13 +157,26 @@ AdamParams = _struct("AdamParams", """
     f:bias_correction2_sqrt i:reserved""")
 AdamTensor = _struct("AdamTensor", "p:param p:grad p:exp_avg p:exp_avg_sq l:numel")
 
+
+
+class FilmFfnParams(C.Structure):
+    _fields_ = [("tokens", _i64), ("d_model", _i32), ("d_ff", _i32), ("ln", AddLayerNormFwdParams),
+                ("h", _ptr), ("w1", _ptr), ("b1", _ptr), ("w2", _ptr), ("act", _ptr), ("gprime", _ptr), ("f", _ptr),
+                ("df", _ptr), ("dpre", _ptr), ("dw1", _ptr), ("db1", _ptr), ("dw2", _ptr), ("dh", _ptr)]
+
+
+CrossAttnParams = _struct("CrossAttnParams", """
+    i:batch i:t_q i:t_kv i:d_model i:heads i:reserved
+    p:query p:memory p:w_in p:b_in p:w_out p:mask p:q p:kv p:p p:o p:out
+    p:dout p:d_o p:ds p:dq p:dkv p:dw_in p:db_in p:dw_out p:dquery p:dmemory""")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
                  GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
                  LengthRegulateFwdParams, LengthRegulateBwdParams, GemmParams,
-                 EmbedSumParams, CeLossParams, AdamParams, AdamTensor]
+                 EmbedSumParams, CeLossParams, AdamParams, AdamTensor, FilmFfnParams, CrossAttnParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -189,6 +202,10 @@ ENTRY_POINTS = {
     "mtts_skinny_linear": SkinnyLinearParams,
     "mtts_gemm_bf16": GemmBf16Params,
     "mtts_gemm": GemmParams,
+    "mtts_film_ffn_fwd": FilmFfnParams,
+    "mtts_film_ffn_bwd": FilmFfnParams,
+    "mtts_cross_attn_fwd": CrossAttnParams,
+    "mtts_cross_attn_bwd": CrossAttnParams,
     "mtts_embed_sum_fwd": EmbedSumParams,
     "mtts_embed_sum_bwd": EmbedSumParams,
     "mtts_ce_loss": CeLossParams,
@@ -268,8 +285,9 @@ def require_cuda(*tensors):
             raise RuntimeError(f"operands on different devices: {dev} and {t.device}")
 
 
-def call(name: str, params) -> None:
-    """Enqueue one library call on torch's current stream of the current device."""
+def call(name: str, params, launches: int = 1) -> None:
+    """Enqueue one library call on torch's current stream of the current device.  ``launches``: kernels the call
+    launches (the branch-level entry points launch several), for ``launch_count``."""
     global launch_count
     lib = load()
     stream = torch.cuda.current_stream().cuda_stream
@@ -284,4 +302,4 @@ def call(name: str, params) -> None:
     if rec is not None:
         ev1.record()
         rec.append((ev0, ev1))
-    launch_count += 1
+    launch_count += launches

@@ -47,6 +47,8 @@ extern "C" int mtts_sizeof_params(int which) {
     case 20: return (int)sizeof(mtts_ce_loss_params);
     case 21: return (int)sizeof(mtts_adam_params);
     case 22: return (int)sizeof(mtts_adam_tensor);
+    case 23: return (int)sizeof(mtts_film_ffn_params);
+    case 24: return (int)sizeof(mtts_cross_attn_params);
     default: return -1;
   }
 }

@@ -28,7 +28,7 @@ namespace mtts {
 namespace g100 {
 
 constexpr int BM = 128, BK = 64;
-enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GELU_BWD = 2, EPI_SOFTMAX = 3, EPI_DSOFTMAX = 4 };
+enum : int { EPI_STORE = 0, EPI_GELU = 1, EPI_GELU_BWD = 2, EPI_SOFTMAX = 3, EPI_DSOFTMAX = 4, EPI_MUL_AUX = 5 };
 // Epilogue warps: EPW / 4 per 32-lane group of TMEM, each draining its share of the tile's columns.  The epilogue is
 // a chain of dependent fixed-latency steps (tcgen05.ld -> math -> staging -> store), so what hides its latency is
 // warps: the row-wise epilogues (one k-block of MMA per tile, so the epilogue IS the kernel) and the two-output
@@ -64,7 +64,7 @@ struct Args {
   int nb_m, nb_n, split_k, kb_total, kb_per_split, kpb, k_batches;
   int batch_inner, batches;
   int a_bi, a_bo, b_bi, b_bo;      // 1 when the operand has that batch dimension, 0 when it is broadcast
-  int out_f32, accumulate, atomic, vec_ok, debug;
+  int out_f32, accumulate, atomic, vec_ok, debug, aux_gelu_grad;
   void* out;
   long long ldc, c_bo, c_bi;
   const float* bias_n;
@@ -284,6 +284,16 @@ __device__ __forceinline__ float gelu_grad_tc(float x) {
   const float t = tanh_approx(x * fmaf(kGeluC1, x2, kGeluC0));
   const float dy = fmaf(3.f * kGeluC1, x2, kGeluC0);          // d/dx of the tanh argument
   return fmaf(0.5f * x * dy, fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
+}
+
+// value and derivative from ONE tanh (the forward can leave gelu'(pre) for the backward instead of pre: the
+// data-gradient GEMM's epilogue is then a single multiply per element instead of a second tanh evaluation)
+__device__ __forceinline__ void gelu_both_tc(float x, float& y, float& dy) {
+  const float x2 = x * x;
+  const float t = tanh_approx(x * fmaf(kGeluC1, x2, kGeluC0));
+  const float h = fmaf(0.5f, t, 0.5f);
+  y = x * h;
+  dy = fmaf(0.5f * x * fmaf(3.f * kGeluC1, x2, kGeluC0), fmaf(-t, t, 1.f), h);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -763,7 +773,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       [[maybe_unused]] uint4 wall[CW / 32][4];           // dsoftmax: the warp's whole block of P
       const bool pre_old = EPI == EPI_STORE && p_acc && !p_f32 && p_vec;
       if (active) {
-        if constexpr (EPI == EPI_GELU_BWD) {
+        if constexpr (EPI == EPI_GELU_BWD || EPI == EPI_MUL_AUX) {
           if (p_vec && n0 < p_n) warp_ldg32(aux_w, 2 * p_ldaux, rows_valid, n0, p_n, lane, wq);
         } else if constexpr (EPI == EPI_DSOFTMAX) {
           if (p_vec) {
@@ -782,7 +792,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // kernel parameters used per element are hoisted into registers: tested where they are used they cost a
       // constant-bank load and a uniform-register move per ELEMENT (measured: 2x on the whole kernel)
       const int ncols = g.n;
-      if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_GELU_BWD) {
+      if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_GELU_BWD || EPI == EPI_MUL_AUX) {
         if (active) {
         const float* bias_n = g.bias_n;
         const bool has_bm = g.bias_m != nullptr;
@@ -815,10 +825,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             __syncwarp();
           }
           if constexpr (EPI == EPI_GELU) {
-            if (g.aux) put(n0 + c, v, true);
+            if (g.aux && g.aux_gelu_grad) {
+              float gp[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tc(v[j]);
-          } else if constexpr (EPI == EPI_GELU_BWD) {
+              for (int j = 0; j < 32; ++j) gelu_both_tc(v[j], v[j], gp[j]);
+              put(n0 + c, gp, true);
+            } else {
+              if (g.aux) put(n0 + c, v, true);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_tc(v[j]);
+            }
+          } else if constexpr (EPI == EPI_GELU_BWD || EPI == EPI_MUL_AUX) {
             float pre[32];
             if (p_vec) {
               uint4 raw[4];
@@ -832,8 +849,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 32; ++j) pre[j] = 0.f;
             }
+            if constexpr (EPI == EPI_GELU_BWD) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_tc(pre[j]);
+              for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_tc(pre[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= pre[j];
+            }
           }
           if constexpr (EPI == EPI_STORE) {
             if (pre_old) {
@@ -1095,7 +1117,7 @@ static int launch_major(int am, int bm, const CUtensorMap& ma, const CUtensorMap
     if (am == 0 && bm == 1) return launch<BN, 0, 1, EPI, CG>(ma, mb, a, grid, s);
     if (am == 1 && bm == 0) return launch<BN, 1, 0, EPI, CG>(ma, mb, a, grid, s);
     return launch<BN, 1, 1, EPI, CG>(ma, mb, a, grid, s);
-  } else if constexpr (EPI == EPI_GELU_BWD) {
+  } else if constexpr (EPI == EPI_GELU_BWD || EPI == EPI_MUL_AUX) {
     if (am == 0 && bm == 1) return launch<BN, 0, 1, EPI, CG>(ma, mb, a, grid, s);
   }
   return MTTS_ERR_UNSUPPORTED;
@@ -1109,7 +1131,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
   if (!p || !p->a || !p->b || !p->out) return MTTS_ERR_NULL;
   if (p->m < 0 || p->n < 1 || p->k < 1 || p->batch_outer < 0 || p->batch_inner < 1) return MTTS_ERR_SHAPE;
   if (p->a_major < 0 || p->a_major > 1 || p->b_major < 0 || p->b_major > 1) return MTTS_ERR_UNSUPPORTED;
-  if (p->epilogue < EPI_STORE || p->epilogue > EPI_DSOFTMAX) return MTTS_ERR_UNSUPPORTED;
+  if (p->epilogue < EPI_STORE || p->epilogue > EPI_MUL_AUX) return MTTS_ERR_UNSUPPORTED;
   if (p->out_dtype != MTTS_F32 && p->out_dtype != MTTS_BF16) return MTTS_ERR_DTYPE;
   if (p->m == 0 || p->batch_outer == 0) return MTTS_OK;
   const int k_batches = p->k_batches > 1 ? p->k_batches : 1;
@@ -1121,11 +1143,13 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
   const bool row_epi = p->epilogue == EPI_SOFTMAX || p->epilogue == EPI_DSOFTMAX;
   if (row_epi && (p->n > 256 || p->out_dtype != MTTS_BF16)) return MTTS_ERR_SHAPE;
   if (p->epilogue == EPI_SOFTMAX && !(p->scale > 0.f)) return MTTS_ERR_UNSUPPORTED;   // the row max is taken before scaling
-  if ((p->epilogue == EPI_GELU_BWD || p->epilogue == EPI_DSOFTMAX) && !p->aux) return MTTS_ERR_NULL;
+  if ((p->epilogue == EPI_GELU_BWD || p->epilogue == EPI_DSOFTMAX || p->epilogue == EPI_MUL_AUX) && !p->aux)
+    return MTTS_ERR_NULL;
   if (p->epilogue != EPI_STORE && p->out_dtype != MTTS_BF16) return MTTS_ERR_DTYPE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  const int BN = (row_epi || p->epilogue == EPI_GELU || p->epilogue == EPI_GELU_BWD || p->n > 128) ? 256
+  const int BN = (row_epi || p->epilogue == EPI_GELU || p->epilogue == EPI_GELU_BWD || p->epilogue == EPI_MUL_AUX ||
+                  p->n > 128) ? 256
                  : (p->n > 64 ? 128 : 64);
   Args a{};
   a.m = p->m;
@@ -1176,6 +1200,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
   a.mask_bo = p->mask_bo_stride;
   a.scale = p->scale;
   a.debug = p->flags >> 8;
+  a.aux_gelu_grad = (p->flags & MTTS_GEMM_AUX_GELU_GRAD) != 0;
   const int ov = a.out_f32 ? 4 : 8;   // elements per 16-byte vector of the output
   a.vec_ok = mtts::aligned16(p->out) && p->ldc % ov == 0 && p->c_bo_stride % ov == 0 && p->c_bi_stride % ov == 0 &&
              p->n % 8 == 0 &&
@@ -1213,6 +1238,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
     case EPI_GELU: return MTTS_GEMM_LAUNCH(256, EPI_GELU);
     case EPI_GELU_BWD: return MTTS_GEMM_LAUNCH(256, EPI_GELU_BWD);
     case EPI_SOFTMAX: return MTTS_GEMM_LAUNCH(256, EPI_SOFTMAX);
+    case EPI_MUL_AUX: return MTTS_GEMM_LAUNCH(256, EPI_MUL_AUX);
     default: return MTTS_GEMM_LAUNCH(256, EPI_DSOFTMAX);
   }
 #undef MTTS_GEMM_LAUNCH

@@ -21,6 +21,7 @@ import math
 import torch
 
 from . import _lib
+from ._lib import ptr
 from .gemm import gemm
 
 _BACKEND = "tc"          # "tc": mtts_gemm for bf16;  "library": torch / cuBLASLt everywhere (A/B measurements)
@@ -108,30 +109,45 @@ def linear(x, weight, bias=None):
 
 class _FfnTC(torch.autograd.Function):
     """f = W2 gelu(W1 h + b1)  (``ff[0]``, ``nn.GELU()``, ``ff[2]`` of ``mamba_decoder.py:39-43``; ``ff[2].bias`` is
-    added by the caller's next fused residual + LayerNorm launch)."""
+    added by the caller's next fused residual + LayerNorm launch).  One library call per direction
+    (``mtts_film_ffn_fwd`` / ``_bwd``): the forward leaves gelu'(pre) -- from the same tanh as gelu(pre) -- so the
+    backward's data-gradient GEMM multiplies by it in its epilogue."""
 
     @staticmethod
     def forward(ctx, h, w1, b1, w2):
         h2 = _rows(h if h.dtype == torch.bfloat16 else h.to(torch.bfloat16))
         w1b, w2b = bf16_weight(w1), bf16_weight(w2)
-        pre = torch.empty((h2.shape[0], w1.shape[0]), dtype=torch.bfloat16, device=h.device)
-        act = gemm(h2, w1b, bias_n=_f32(b1), epilogue="gelu", aux=pre)
-        f = gemm(act, w2b)
-        ctx.save_for_backward(h2, pre, act, w1b, w2b)
+        T, D, Fd = h2.shape[0], w1.shape[1], w1.shape[0]
+        bf, dev = torch.bfloat16, h.device
+        act = torch.empty((T, Fd), dtype=bf, device=dev)
+        gprime = torch.empty((T, Fd), dtype=bf, device=dev)
+        f = torch.empty((T, D), dtype=bf, device=dev)
+        b32 = _f32(b1)
+        p = _lib.FilmFfnParams(tokens=T, d_model=D, d_ff=Fd, h=ptr(h2), w1=ptr(w1b), b1=ptr(b32), w2=ptr(w2b),
+                               act=ptr(act), gprime=ptr(gprime), f=ptr(f))
+        _lib.require_cuda(h2, w1b, w2b, b32)
+        _lib.call("mtts_film_ffn_fwd", p, launches=2)
+        ctx.save_for_backward(h2, gprime, act, w1b, w2b)
         ctx.meta = (h.shape, h.dtype, None if b1 is None else b1.dtype)
-        return f.view(*h.shape[:-1], w2.shape[0])
+        return f.view(*h.shape[:-1], D)
 
     @staticmethod
     def backward(ctx, df):
-        h2, pre, act, w1b, w2b = ctx.saved_tensors
+        h2, gprime, act, w1b, w2b = ctx.saved_tensors
         shape, t_h, t_b = ctx.meta
         df2 = _rows(df if df.dtype == torch.bfloat16 else df.to(torch.bfloat16))
-        dpre = gemm(df2, w2b.t(), epilogue="gelu_bwd", aux=pre)        # (tokens, d_ff)
-        dw2 = gemm(df2.t(), act.t(), out_dtype=torch.float32, split_k=-1)
-        dw1 = gemm(dpre.t(), h2.t(), out_dtype=torch.float32, split_k=-1)
-        db1 = None if t_b is None else _colsum(dpre).to(t_b)
-        dh = gemm(dpre, w1b.t()).view(shape).to(t_h) if ctx.needs_input_grad[0] else None
-        return dh, dw1, db1, dw2
+        T, D, Fd = h2.shape[0], h2.shape[1], act.shape[1]
+        dev, f32 = df.device, torch.float32
+        dpre = torch.empty_like(act)
+        dw1 = torch.empty((Fd, D), dtype=f32, device=dev)
+        dw2 = torch.empty((D, Fd), dtype=f32, device=dev)
+        db1 = None if t_b is None else torch.zeros(Fd, dtype=f32, device=dev)
+        need_h = ctx.needs_input_grad[0]
+        dh = torch.empty((T, D), dtype=torch.bfloat16, device=dev) if need_h else None
+        p = _lib.FilmFfnParams(tokens=T, d_model=D, d_ff=Fd, h=ptr(h2), w1=ptr(w1b), w2=ptr(w2b), act=ptr(act), gprime=ptr(gprime), df=ptr(df2), dpre=ptr(dpre),
+                               dw1=ptr(dw1), db1=ptr(db1), dw2=ptr(dw2), dh=ptr(dh))
+        _lib.call("mtts_film_ffn_bwd", p, launches=4 + int(need_h))
+        return (dh.view(shape).to(t_h) if need_h else None), dw1, (None if db1 is None else db1.to(t_b)), dw2
 
 
 def ffn(h, w1, b1, w2):
@@ -140,69 +156,57 @@ def ffn(h, w1, b1, w2):
 
 class _CrossAttentionTC(torch.autograd.Function):
     """``nn.MultiheadAttention(batch_first=True)`` forward without its out-projection bias
-    (``mamba_decoder.py:72-77``; packed ``in_proj_weight`` (3E, E) = [Wq; Wk; Wv]), T_kv <= 256.
-    q is scaled in the softmax epilogue (fp32), which for power-of-two head sizes is bit-identical to torch's
-    scaling of q before QK^T."""
+    (``mamba_decoder.py:72-77``; packed ``in_proj_weight`` (3E, E) = [Wq; Wk; Wv]), T_kv <= 256, as one library call
+    per direction (``mtts_cross_attn_fwd`` / ``_bwd``).  q is scaled in the softmax epilogue (fp32), which for
+    power-of-two head sizes is bit-identical to torch's scaling of q before QK^T."""
 
     @staticmethod
     def forward(ctx, query, memory, w_in, b_in, w_out, mask, heads):
         B, T, E = query.shape
         Tk = memory.shape[1]
-        H, dh = heads, E // heads
-        bf = torch.bfloat16
+        bf, dev = torch.bfloat16, query.device
         q_in = _rows(query if query.dtype == bf else query.to(bf))
         m_in = _rows(memory if memory.dtype == bf else memory.to(bf))
         wb, wob = bf16_weight(w_in), bf16_weight(w_out)
         b32 = _f32(b_in)
-        q = gemm(q_in, wb[:E], bias_n=b32[:E]).view(B, T, E)
-        kv = gemm(m_in, wb[E:], bias_n=b32[E:]).view(B, Tk, 2 * E)
-        qv = q.view(B, T, H, dh).transpose(1, 2)                       # (B, H, T, dh)
-        kvw = kv[..., :E].view(B, Tk, H, dh).transpose(1, 2)           # (B, H, Tk, dh)
-        vvw = kv[..., E:].view(B, Tk, H, dh).transpose(1, 2)
         tkp = Tk + (-Tk) % 8
-        P = torch.empty((B, H, T, tkp), dtype=bf, device=query.device)
-        scale = 1.0 / math.sqrt(dh)
-        gemm(qv, kvw, out=P[..., :Tk], epilogue="softmax", mask=mask, scale=scale)
-        o = torch.empty((B, T, E), dtype=bf, device=query.device)
-        gemm(P[..., :Tk], vvw.transpose(-1, -2), out=o.view(B, T, H, dh).transpose(1, 2))
-        out = gemm(o.view(B * T, E), wob).view(B, T, E)
-        ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, P, o)
-        ctx.meta = (query.dtype, memory.dtype, b_in.dtype, H, scale, Tk)
+        q = torch.empty((B, T, E), dtype=bf, device=dev)
+        kv = torch.empty((B, Tk, 2 * E), dtype=bf, device=dev)
+        P = torch.empty((B, heads, T, tkp), dtype=bf, device=dev)
+        o = torch.empty((B, T, E), dtype=bf, device=dev)
+        out = torch.empty((B, T, E), dtype=bf, device=dev)
+        _lib.require_cuda(q_in, m_in, wb, wob, b32, mask)
+        p = _lib.CrossAttnParams(batch=B, t_q=T, t_kv=Tk, d_model=E, heads=heads, query=ptr(q_in), memory=ptr(m_in),
+                                 w_in=ptr(wb), b_in=ptr(b32), w_out=ptr(wob), mask=ptr(mask), q=ptr(q), kv=ptr(kv),
+                                 p=ptr(P), o=ptr(o), out=ptr(out))
+        _lib.call("mtts_cross_attn_fwd", p, launches=5)
+        ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, P, o, mask)
+        ctx.meta = (query.dtype, memory.dtype, b_in.dtype, heads)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q_in, m_in, wb, wob, q, kv, P, o = ctx.saved_tensors
-        t_q, t_m, t_b, H, scale, Tk = ctx.meta
+        q_in, m_in, wb, wob, q, kv, P, o, mask = ctx.saved_tensors
+        t_q, t_m, t_b, H = ctx.meta
         B, T, E = q.shape
-        dh = E // H
-        bf = torch.bfloat16
-        f32 = torch.float32
+        Tk = kv.shape[1]
+        bf, f32, dev = torch.bfloat16, torch.float32, q.device
         d2 = _rows(dout if dout.dtype == bf else dout.to(bf))
-        do = gemm(d2, wob.t()).view(B, T, E)
-        dwo = gemm(d2.t(), o.view(B * T, E).t(), out_dtype=f32, split_k=-1)
-        dov = do.view(B, T, H, dh).transpose(1, 2)                     # (B, H, T, dh)
-        qv = q.view(B, T, H, dh).transpose(1, 2)
-        kvw = kv[..., :E].view(B, Tk, H, dh).transpose(1, 2)
-        vvw = kv[..., E:].view(B, Tk, H, dh).transpose(1, 2)
-        Pv = P[..., :Tk]
-        dkv = torch.empty_like(kv)
-        dkw = dkv[..., :E].view(B, Tk, H, dh).transpose(1, 2)
-        dvw = dkv[..., E:].view(B, Tk, H, dh).transpose(1, 2)
-        gemm(Pv.transpose(-1, -2), dov.transpose(-1, -2), out=dvw)                      # dV = P^T dO
-        dS = torch.empty_like(P)
-        gemm(dov, vvw, out=dS[..., :Tk], epilogue="dsoftmax", aux=Pv, scale=scale)      # dS from dP = dO V^T
-        dq = torch.empty_like(q)
-        gemm(dS[..., :Tk], kvw.transpose(-1, -2), out=dq.view(B, T, H, dh).transpose(1, 2))   # dQ = dS K
-        gemm(dS[..., :Tk].transpose(-1, -2), qv.transpose(-1, -2), out=dkw)             # dK = dS^T Q
-        dq2, dkv2 = dq.view(B * T, E), dkv.view(B * Tk, 2 * E)
-        dw_in = torch.empty((3 * E, E), dtype=f32, device=q.device)
-        gemm(dq2.t(), q_in.t(), out=dw_in[:E], split_k=-1)
-        gemm(dkv2.t(), m_in.t(), out=dw_in[E:], split_k=-1)
-        db_in = torch.cat([_colsum(dq2), _colsum(dkv2)]).to(t_b)
-        dquery = gemm(dq2, wb[:E].t()).view(B, T, E).to(t_q) if ctx.needs_input_grad[0] else None
-        dmem = gemm(dkv2, wb[E:].t()).view(B, Tk, E).to(t_m) if ctx.needs_input_grad[1] else None
-        return dquery, dmem, dw_in, db_in, dwo, None, None
+        d_o, dS, dq, dkv = torch.empty_like(o), torch.empty_like(P), torch.empty_like(q), torch.empty_like(kv)
+        dw_in = torch.empty((3 * E, E), dtype=f32, device=dev)
+        dw_out = torch.empty((E, E), dtype=f32, device=dev)
+        db_in = torch.zeros(3 * E, dtype=f32, device=dev)
+        need_q, need_m = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dquery = torch.empty((B, T, E), dtype=bf, device=dev) if need_q else None
+        dmem = torch.empty((B, Tk, E), dtype=bf, device=dev) if need_m else None
+        p = _lib.CrossAttnParams(batch=B, t_q=T, t_kv=Tk, d_model=E, heads=H, query=ptr(q_in), memory=ptr(m_in),
+                                 w_in=ptr(wb), b_in=ptr(db_in), w_out=ptr(wob), mask=ptr(mask), q=ptr(q), kv=ptr(kv),
+                                 p=ptr(P), o=ptr(o), dout=ptr(d2), d_o=ptr(d_o), ds=ptr(dS), dq=ptr(dq), dkv=ptr(dkv),
+                                 dw_in=ptr(dw_in), db_in=ptr(db_in), dw_out=ptr(dw_out), dquery=ptr(dquery),
+                                 dmemory=ptr(dmem))
+        _lib.call("mtts_cross_attn_bwd", p, launches=10 + int(need_q) + int(need_m))
+        return (None if dquery is None else dquery.to(t_q), None if dmem is None else dmem.to(t_m), dw_in,
+                db_in.to(t_b), dw_out, None, None)
 
 
 def cross_attention(query, memory, w_in, b_in, w_out, mask, heads):

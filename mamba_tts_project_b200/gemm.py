@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import ptr
 
 _EPI = {"store": _lib.EPI_STORE, "gelu": _lib.EPI_GELU, "gelu_bwd": _lib.EPI_GELU_BWD,
-        "softmax": _lib.EPI_SOFTMAX, "dsoftmax": _lib.EPI_DSOFTMAX}
+        "softmax": _lib.EPI_SOFTMAX, "dsoftmax": _lib.EPI_DSOFTMAX, "mul_aux": _lib.EPI_MUL_AUX}
 
 
 def _as4(t):
@@ -52,14 +52,15 @@ def _operand(t, name):
 
 
 def gemm(a, b, out=None, out_dtype=None, bias_n=None, bias_m=None, epilogue="store", aux=None, mask=None,
-         scale=1.0, accumulate=False, reduce_batch=False, split_k=1, single_cta=False, _debug=0):
+         scale=1.0, accumulate=False, reduce_batch=False, split_k=1, single_cta=False, aux_gelu_grad=False,
+         _debug=0):
     """C = epilogue(a @ b^T) on the tensor cores.
 
     a (.., m, k), b (.., n, k): bf16 views (see module docstring); leading dimensions broadcast against each other.
     out: optional (.., m, n) tensor with unit stride along n (bf16 or fp32), else allocated in ``out_dtype``.
     bias_n (n) / bias_m (m): fp32, added before the activation.
-    epilogue: "store" | "gelu" (aux = optional bf16 output receiving the pre-activation) | "gelu_bwd" (aux =
-      the forward's pre-activation) | "softmax" (row softmax of scale * acc under the key ``mask`` (bo, n) uint8,
+    epilogue: "store" | "gelu" (aux = optional bf16 output receiving the pre-activation, or gelu'(pre) with
+      ``aux_gelu_grad``) | "gelu_bwd" (aux = the forward's pre-activation) | "mul_aux" (C = acc * aux) | "softmax" (row softmax of scale * acc under the key ``mask`` (bo, n) uint8,
       n <= 256) | "dsoftmax" (aux = P; scale * P o (acc - rowsum(P o acc))).
     accumulate: C += result.  reduce_batch: the contraction also runs over the outermost batch dimension (weight
       gradients), C is (m, n); split_k = -1 lets the library split it across the SMs (fp32 out).
@@ -121,6 +122,7 @@ def gemm(a, b, out=None, out_dtype=None, bias_n=None, bias_m=None, epilogue="sto
         aux=ptr(aux4), ld_aux=0 if aux4 is None else (aux4.stride(-2) if m > 1 else max(aux4.stride(-2), n)),
         aux_bo_stride=0 if aux4 is None else bs(aux4, 0), aux_bi_stride=0 if aux4 is None else bs(aux4, 1),
         mask=ptr(m8), mask_bo_stride=0 if m8 is None else n, scale=float(scale),
-        flags=(_lib.GEMM_SINGLE_CTA if single_cta else 0) | (_debug << 8))
+        flags=(_lib.GEMM_SINGLE_CTA if single_cta else 0) | (_lib.GEMM_AUX_GELU_GRAD if aux_gelu_grad else 0)
+        | (_debug << 8))
     _lib.call("mtts_gemm", p)
     return out

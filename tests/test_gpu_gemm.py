@@ -162,3 +162,113 @@ def test_gemm_persistent_many_tiles_and_legacy_entry():
     out, pre = ops.gemm_bf16(a, w, bias, gelu=True, return_pre=True)
     assert rel_err(pre, ref + bias) < BF16_OUT and rel_err(out, torch.nn.functional.gelu(ref + bias)) < BF16_OUT
     assert rel_err(ops.gemm_bf16(a, w, bias), ref + bias) < BF16_OUT
+
+
+def test_gemm_gelu_grad_aux_and_mul_aux_epilogues():
+    """The forward can leave gelu'(pre) (same tanh as gelu(pre)); the backward then multiplies by it."""
+    from mamba_tts_project_b200.gemm import gemm
+    m, n, k, d = 392, 512, 192, 64
+    x, w = _rand(m, k, seed=27), _rand(n, k, seed=28, scale=k ** -0.5)
+    bias = torch.randn(n, device="cuda")
+    gp = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    act = gemm(x, w, bias_n=bias, epilogue="gelu", aux=gp, aux_gelu_grad=True)
+    pre = (x.float() @ w.float().t() + bias).requires_grad_()
+    y = torch.nn.functional.gelu(pre)
+    (g_ref,) = torch.autograd.grad(y.sum(), pre)
+    assert rel_err(act, y) < BF16_OUT
+    assert rel_err(gp, g_ref) < BF16_OUT
+    dy, w2 = _rand(m, d, seed=29), _rand(d, n, seed=30, scale=d ** -0.5)
+    dpre = gemm(dy, w2.t(), epilogue="mul_aux", aux=gp)
+    assert rel_err(dpre, (dy.float() @ w2.float()) * gp.float()) < BF16_OUT
+
+
+def _ref_attention(query, memory, w_in, b_in, w_out, mask, H):
+    E = query.shape[-1]
+    q = query @ w_in[:E].t() + b_in[:E]
+    k = memory @ w_in[E:2 * E].t() + b_in[E:2 * E]
+    v = memory @ w_in[2 * E:].t() + b_in[2 * E:]
+    B, T, _ = q.shape
+    sh = lambda t: t.view(B, -1, H, E // H).transpose(1, 2)
+    s = sh(q) @ sh(k).transpose(-1, -2) / math.sqrt(E // H)
+    if mask is not None:
+        s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+    o = (torch.softmax(s, -1) @ sh(v)).transpose(1, 2).reshape(B, T, E)
+    return o @ w_out.t()
+
+
+@pytest.mark.parametrize("B,T,Tk,E,H,masked", [(2, 300, 72, 128, 4, True), (3, 128, 256, 256, 4, False),
+                                                (1, 40, 13, 64, 8, True)])
+def test_cross_attn_entry_points_forward_and_all_gradients(B, T, Tk, E, H, masked):
+    """mtts_cross_attn_fwd / _bwd (one C-ABI call per direction) against fp32 nn.MultiheadAttention arithmetic."""
+    from mamba_tts_project_b200 import dense
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(torch.bfloat16).float().cuda()
+    query, memory = rnd(B, T, E).requires_grad_(), rnd(B, Tk, E).requires_grad_()
+    w_in, w_out = rnd(3 * E, E, sc=E ** -0.5).requires_grad_(), rnd(E, E, sc=E ** -0.5).requires_grad_()
+    b_in = (0.1 * torch.randn(3 * E, generator=g)).cuda().requires_grad_()
+    mask = None
+    if masked:
+        mask = (torch.rand(B, Tk, generator=g) > 0.3).cuda()
+        mask[:, 0] = True
+    dout = rnd(B, T, E)
+    ref = _ref_attention(query, memory, w_in, b_in, w_out, mask, H)
+    g_ref = torch.autograd.grad(ref, [query, memory, w_in, b_in, w_out], dout)
+    out = dense.cross_attention(query.detach().bfloat16().requires_grad_(), memory.detach().bfloat16().requires_grad_(),
+                                w_in, b_in, w_out, mask, H)
+    assert out.dtype == torch.bfloat16 and rel_err(out, ref) < 2e-2
+    qb, mb = query.detach().bfloat16().requires_grad_(), memory.detach().bfloat16().requires_grad_()
+    out = dense.cross_attention(qb, mb, w_in, b_in, w_out, mask, H)
+    got = torch.autograd.grad(out, [qb, mb, w_in, b_in, w_out], dout.bfloat16())
+    for name, a, b in zip(("dquery", "dmemory", "dw_in", "db_in", "dw_out"), got, g_ref):
+        assert rel_err(a, b) < 3e-2, name
+
+
+@pytest.mark.parametrize("T,D,Fd,bias", [(520, 128, 512, True), (96, 64, 128, False)])
+def test_film_ffn_entry_points_forward_and_all_gradients(T, D, Fd, bias):
+    """mtts_film_ffn_fwd / _bwd (one C-ABI call per direction) against fp32 Linear -> GELU -> Linear."""
+    from mamba_tts_project_b200 import dense
+    g = torch.Generator().manual_seed(6)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(torch.bfloat16).float().cuda()
+    h = rnd(T, D).requires_grad_()
+    w1, w2 = rnd(Fd, D, sc=D ** -0.5).requires_grad_(), rnd(D, Fd, sc=Fd ** -0.5).requires_grad_()
+    b1 = (0.2 * torch.randn(Fd, generator=g)).cuda().requires_grad_() if bias else None
+    df = rnd(T, D)
+    ref = torch.nn.functional.gelu(torch.nn.functional.linear(h, w1, b1)) @ w2.t()
+    ins = [h, w1, w2] + ([b1] if bias else [])
+    g_ref = torch.autograd.grad(ref, ins, df)
+    hb = h.detach().bfloat16().requires_grad_()
+    f = dense.ffn(hb, w1, b1, w2)
+    assert rel_err(f, ref) < 2e-2
+    got = torch.autograd.grad(f, [hb, w1, w2] + ([b1] if bias else []), df.bfloat16())
+    for name, a, b in zip(("dh", "dw1", "dw2", "db1"), got, g_ref):
+        assert rel_err(a, b) < 3e-2, name
+
+
+def test_film_ffn_forward_with_fused_layernorm_film():
+    """The ln member: residual add + LayerNorm + FiLM feeding the FFN inside the same C-ABI call."""
+    from mamba_tts_project_b200 import _lib
+    from mamba_tts_project_b200._lib import ptr
+    B, Tn, D, Fd = 2, 96, 128, 256
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B * Tn, D, generator=g).cuda()
+    delta = torch.randn(B * Tn, D, generator=g).bfloat16().cuda()
+    lw, lb = (1 + 0.1 * torch.randn(D, generator=g)).cuda(), (0.1 * torch.randn(D, generator=g)).cuda()
+    gam, bet = (1 + 0.2 * torch.randn(B, D, generator=g)).cuda(), (0.2 * torch.randn(B, D, generator=g)).cuda()
+    w1, w2 = _rand(Fd, D, seed=31, scale=D ** -0.5), _rand(D, Fd, seed=32, scale=Fd ** -0.5)
+    b1 = (0.1 * torch.randn(Fd, generator=g)).cuda()
+    x_out = torch.empty_like(x)
+    h = torch.empty(B * Tn, D, dtype=torch.bfloat16, device="cuda")
+    act, gp = torch.empty(B * Tn, Fd, dtype=torch.bfloat16, device="cuda"), torch.empty(B * Tn, Fd, dtype=torch.bfloat16, device="cuda")
+    f = torch.empty(B * Tn, D, dtype=torch.bfloat16, device="cuda")
+    ln = _lib.AddLayerNormFwdParams(rows=B * Tn, dim=D, rows_per_batch=Tn, io_dtype=_lib.BF16, eps=1e-5, x=ptr(x),
+                                    delta=ptr(delta), x_out=ptr(x_out), ln_weight=ptr(lw), ln_bias=ptr(lb),
+                                    film_gamma=ptr(gam), film_beta=ptr(bet), out=ptr(h))
+    p = _lib.FilmFfnParams(tokens=B * Tn, d_model=D, d_ff=Fd, ln=ln, h=ptr(h), w1=ptr(w1), b1=ptr(b1), w2=ptr(w2),
+                           act=ptr(act), gprime=ptr(gp), f=ptr(f))
+    _lib.call("mtts_film_ffn_fwd", p, launches=3)
+    xo = x + delta.float()
+    hr = torch.nn.functional.layer_norm(xo, (D,), lw, lb, 1e-5).view(B, Tn, D) * gam[:, None] + bet[:, None]
+    assert rel_err(x_out, xo) < 1e-6
+    assert rel_err(h, hr.view(-1, D)) < BF16_OUT
+    ref = torch.nn.functional.gelu(h.float() @ w1.float().t() + b1) @ w2.float().t()
+    assert rel_err(f, ref) < 2e-2

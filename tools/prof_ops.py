@@ -19,11 +19,11 @@ records = []
 _orig = _lib.call
 
 
-def traced(name, params):
+def traced(name, params, launches=1):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    _orig(name, params)
+    _orig(name, params, launches)
     e1.record()
     key = name
     if name == "mtts_gemm":
