@@ -408,6 +408,23 @@ typedef struct {
 } mtts_add_layernorm_bwd_params;
 int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream);
 
+/* The (batch, dim)-sized finishing step of a FiLM'd add_layernorm_bwd in one launch: from colsum (batch, 3, dim)
+ *   dweight = sum_b gamma_b S1_b,  dbias = sum_b gamma_b S2_b,  dgamma_b = w S1_b + bias S2_b,  dbeta_b = S2_b,
+ *   ddelta_bias = sum_b S3_b (optional).  All fp32, all overwritten. */
+typedef struct {
+  int32_t batch, dim;
+  const float* colsum;
+  const float* film_gamma;
+  const float* ln_weight;
+  const float* ln_bias;
+  float* dweight;
+  float* dbias;
+  float* dgamma;
+  float* dbeta;
+  float* ddelta_bias; /* or NULL */
+} mtts_add_layernorm_finish_params;
+int mtts_add_layernorm_bwd_finish(const mtts_add_layernorm_finish_params* p, mtts_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * length_regulate_fwd / length_regulate_bwd -- LengthRegulator.forward of the style pipeline next to the
  * decoder (style_cross_attention.py:144-198): phoneme rows repeated by their durations.

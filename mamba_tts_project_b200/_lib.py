@@ -170,13 +170,17 @@ CrossAttnParams = _struct("CrossAttnParams", """
     p:query p:memory p:w_in p:b_in p:w_out p:mask p:q p:kv p:p p:o p:out
     p:dout p:d_o p:ds p:dq p:dkv p:dw_in p:db_in p:dw_out p:dquery p:dmemory""")
 
+AddLayerNormFinishParams = _struct("AddLayerNormFinishParams", """
+    i:batch i:dim p:colsum p:film_gamma p:ln_weight p:ln_bias p:dweight p:dbias p:dgamma p:dbeta p:ddelta_bias""")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
                  AddLayerNormFwdParams, AddLayerNormBwdParams, SkinnyLinearParams,
                  GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
                  LengthRegulateFwdParams, LengthRegulateBwdParams, GemmParams,
-                 EmbedSumParams, CeLossParams, AdamParams, AdamTensor, FilmFfnParams, CrossAttnParams]
+                 EmbedSumParams, CeLossParams, AdamParams, AdamTensor, FilmFfnParams, CrossAttnParams,
+                 AddLayerNormFinishParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -199,6 +203,7 @@ ENTRY_POINTS = {
     "mtts_length_regulate_bwd": LengthRegulateBwdParams,
     "mtts_add_layernorm_fwd": AddLayerNormFwdParams,
     "mtts_add_layernorm_bwd": AddLayerNormBwdParams,
+    "mtts_add_layernorm_bwd_finish": AddLayerNormFinishParams,
     "mtts_skinny_linear": SkinnyLinearParams,
     "mtts_gemm_bf16": GemmBf16Params,
     "mtts_gemm": GemmParams,

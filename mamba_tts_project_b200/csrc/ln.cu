@@ -266,7 +266,39 @@ static int dispatch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t 
   return launch_status();
 }
 
+// Parameter gradients of a FiLM'd LayerNorm from the backward kernel's per-batch column sums: one thread per column
+// walks the batch (a (batch, dim)-sized problem: replaces two einsum, an addcmul, a mul and a sum launch).
+__global__ void __launch_bounds__(128)
+add_layernorm_film_finish_kernel(const mtts_add_layernorm_finish_params p) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= p.dim) return;
+  const float w = p.ln_weight[d], bias = p.ln_bias[d];
+  float dw = 0.f, db = 0.f, d3 = 0.f;
+  for (int b = 0; b < p.batch; ++b) {
+    const float* cs = p.colsum + (size_t)b * 3 * p.dim;
+    const float s1 = cs[d], s2 = cs[p.dim + d];
+    const float gm = p.film_gamma[(size_t)b * p.dim + d];
+    dw = fmaf(gm, s1, dw);
+    db = fmaf(gm, s2, db);
+    d3 += cs[2 * p.dim + d];
+    p.dgamma[(size_t)b * p.dim + d] = fmaf(w, s1, bias * s2);
+    p.dbeta[(size_t)b * p.dim + d] = s2;
+  }
+  p.dweight[d] = dw;
+  p.dbias[d] = db;
+  if (p.ddelta_bias) p.ddelta_bias[d] = d3;
+}
+
 }  // namespace mtts
+
+extern "C" int mtts_add_layernorm_bwd_finish(const mtts_add_layernorm_finish_params* p, mtts_stream_t stream) {
+  if (!p || !p->colsum || !p->film_gamma || !p->ln_weight || !p->ln_bias || !p->dweight || !p->dbias || !p->dgamma ||
+      !p->dbeta)
+    return MTTS_ERR_NULL;
+  if (p->batch < 1 || p->dim < 1) return MTTS_ERR_SHAPE;
+  mtts::add_layernorm_film_finish_kernel<<<(p->dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*p);
+  return mtts::launch_status();
+}
 
 extern "C" int mtts_add_layernorm_fwd(const mtts_add_layernorm_fwd_params* p, mtts_stream_t stream) {
   if (!p || !p->x || !p->ln_weight || !p->ln_bias || !p->out) return MTTS_ERR_NULL;

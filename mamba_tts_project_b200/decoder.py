@@ -107,7 +107,7 @@ class MambaTTSDecoderLayer(nn.Module):
         self.style_mlp = nn.Sequential(nn.Linear(d_style, 2 * d_model), nn.Tanh())
 
     def forward_fused(self, x, delta, text_hidden, z_style, text_mask=None, mamba_state=None,
-                      delta_bias=None):
+                      delta_bias=None, film=None):
         """The layer with every ``x = x + branch`` folded into the LayerNorm that follows it.
 
         x: fp32 residual stream (B, T, D); delta (+ delta_bias): branch output still to be added to x
@@ -124,7 +124,8 @@ class MambaTTSDecoderLayer(nn.Module):
         attn_out = self.cross_attn(h, text_hidden, key_padding_mask=key_padding_mask,
                                    add_out_bias=False)
 
-        gamma, beta = torch.chunk(self.style_mlp(z_style), 2, dim=-1)
+        # film: (gamma, beta) already computed for all layers at once (MambaTTSDecoder.film_terms)
+        gamma, beta = torch.chunk(self.style_mlp(z_style), 2, dim=-1) if film is None else film
         x, h = ops.add_layernorm(x, attn_out, self.norm_ff.weight, self.norm_ff.bias,
                                  self.norm_ff.eps, gamma=gamma, beta=beta, out_dtype=cdt,
                                  delta_bias=self.cross_attn.out_proj.bias)
@@ -277,15 +278,31 @@ class MambaTTSDecoder(nn.Module):
             x = (self.token_embed(audio_tokens) + self.pos_embed(pos_ids)[None]
                  + self.quant_embed(quant_row)[None]).float()
         delta, dbias = None, None
-        for layer in self.layers:
+        films = self.film_terms(z_style)
+        for layer, film in zip(self.layers, films):
             x, delta, dbias, _ = layer.forward_fused(x, delta, memory, z_style, text_mask=mask,
-                                                     delta_bias=dbias)
+                                                     delta_bias=dbias, film=film)
         cdt = compute_dtype(x)
         _, h = ops.add_layernorm(x, delta, self.norm_out.weight, self.norm_out.bias,
                                  self.norm_out.eps, out_dtype=cdt, delta_bias=dbias)
         if dense.tc_enabled(cdt) and h.shape[-1] % 8 == 0 and self.vocab_size_audio % 8 == 0:
             return dense.linear(h, self.head.weight, self.head.bias)
         return self.head(h)
+
+    def film_terms(self, z_style):
+        """(gamma, beta) of every layer's ``style_mlp`` (``mamba_decoder.py:45-48,81-83``: Linear + Tanh on the same
+        ``z_style``) from ONE contraction over the stacked weights instead of one small GEMM + tanh per layer (and
+        three more per layer in the backward); -> list of ((B, D), (B, D)) fp32, contiguous."""
+        L, B = len(self.layers), z_style.shape[0]
+        D2 = self.layers[0].style_mlp[0].out_features
+        w = torch.cat([l.style_mlp[0].weight for l in self.layers])            # (L * 2D, d_style)
+        b = torch.cat([l.style_mlp[0].bias for l in self.layers])
+        if dense.tc_enabled(compute_dtype(z_style)) and z_style.shape[1] % 8 == 0 and D2 % 8 == 0:
+            g = dense.linear(z_style, w, b)                                     # tcgen05 (M = B rows)
+        else:
+            g = F.linear(z_style, w, b)
+        g = torch.tanh(g.float()).view(B, L, 2, D2 // 2).permute(1, 2, 0, 3).contiguous()   # (L, 2, B, D)
+        return [(g[i, 0], g[i, 1]) for i in range(L)]
 
     # ---- incremental path (mamba_decoder.py:188-256) --------------------------------------------
     def prepare_generation(self, text_hidden, z_style, text_mask=None, ref_hidden=None,

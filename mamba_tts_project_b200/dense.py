@@ -46,8 +46,8 @@ def bf16_weight(w: torch.Tensor) -> torch.Tensor:
     """bf16 shadow of an fp32 master weight, refreshed when the parameter's version changes."""
     if w.dtype == torch.bfloat16:
         return w.detach()
-    if torch.cuda.is_current_stream_capturing():
-        return w.detach().to(torch.bfloat16)           # the cast belongs to the captured step
+    if torch.cuda.is_current_stream_capturing() or not w.is_leaf:
+        return w.detach().to(torch.bfloat16)           # the cast belongs to the captured step / a temporary
     key = id(w)
     hit = _shadow.get(key)
     if hit is not None and hit[0] is w and hit[1] == w._version and hit[2] == w.data_ptr():

@@ -439,10 +439,11 @@ class _MambaBlockFn(torch.autograd.Function):
             Bm, Cm = x_dbl[:, R:R + N], x_dbl[:, R + N:]
             du = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
             ddelta = torch.empty((Bsz, Di, T), dtype=dtype, device=dev)
-            dA = torch.zeros((Di, N), dtype=f32, device=dev)
-            dBC = torch.zeros((2, Bsz, N, T), dtype=f32, device=dev)
-            dD = torch.zeros(Di, dtype=f32, device=dev)
-            ddb = torch.zeros(Di, dtype=f32, device=dev)
+            # every accumulated-into fp32 gradient of the block lives in ONE zero-filled buffer (one fill launch)
+            sizes = (Di * N, 2 * Bsz * N * T, Di, Di, Di * W, Di)
+            pool = torch.zeros(sum(sizes), dtype=f32, device=dev)
+            dA, dBC, dD, ddb, dcw, dcb = (t.view(sh) for t, sh in zip(
+                pool.split(sizes), ((Di, N), (2, Bsz, N, T), (Di,), (Di,), (Di, W), (Di,))))
             _lib.call("mtts_selective_scan_bwd", _lib.ScanBwdParams(
                 batch=Bsz, dim=Di, seqlen=T, dstate=N, io_dtype=io, delta_softplus=1,
                 u=ptr(xc), u_batch_stride=xc.stride(0), u_dim_stride=xc.stride(1),
@@ -464,10 +465,7 @@ class _MambaBlockFn(torch.autograd.Function):
                 g(bc(Wdt.t()), ddelta.transpose(1, 2), out=dx_dbl[:, :R])
             else:
                 dx_dbl[:, :R].copy_(torch.bmm(bc(Wdt.t()), ddelta))
-            dx_dbl[:, R:R + N].copy_(dBC[0])
-            dx_dbl[:, R + N:].copy_(dBC[1])
-            dcw = torch.zeros_like(cw32)
-            dcb = torch.zeros(Di, dtype=f32, device=dev)
+            dx_dbl[:, R:].view(Bsz, 2, N, T).copy_(dBC.transpose(0, 1))           # dB | dC in one cast-copy
             if tc:
                 dWdt = g(ddelta, x_dbl[:, :R], out_dtype=f32, reduce_batch=True, split_k=-1)      # (Di, R)
                 # d xc = du + W_x^T d x_dbl : the GEMM accumulates onto du
@@ -806,14 +804,23 @@ class _AddLayerNormFn(torch.autograd.Function):
             # no FiLM: one "batch element", the column sums ARE the gradients (no reduction kernels)
             dw, db, dgamma, dbeta = s1[0], s2[0], None, None
         else:
-            # (batch, dim)-sized finishing: dw, db in one small GEMV-like reduction each
-            dw, db = torch.einsum("bd,bd->d", g32, s1), torch.einsum("bd,bd->d", g32, s2)
-            dgamma, dbeta = torch.addcmul(b32 * s2, w32, s1).to(t_g), s2.to(t_g)
+            # (batch, dim)-sized finishing (dw, db, dgamma, dbeta, d delta_bias) in one launch
+            fin = torch.empty((3 + 2 * batch, dim), dtype=torch.float32, device=dev)
+            dw, db, ddb_f = fin[0], fin[1], fin[2]
+            dgamma, dbeta = fin[3:3 + batch], fin[3 + batch:]
+            _lib.call("mtts_add_layernorm_bwd_finish", _lib.AddLayerNormFinishParams(
+                batch=batch, dim=dim, colsum=ptr(colsum), film_gamma=ptr(g32), ln_weight=ptr(w32), ln_bias=ptr(b32),
+                dweight=ptr(dw), dbias=ptr(db), dgamma=ptr(dgamma), dbeta=ptr(dbeta),
+                ddelta_bias=ptr(ddb_f) if t_db is not None else None))
+            dgamma, dbeta = dgamma.to(t_g), dbeta.to(t_g)
         if has_delta and ddelta is None:
             ddelta = dx.to(t_delta)
         ddb = None
         if t_db is not None:
-            ddb = (colsum[0, 2] if batch == 1 else colsum[:, 2].sum(0)).to(t_db)
+            if g32 is not None:
+                ddb = ddb_f.to(t_db)
+            else:
+                ddb = (colsum[0, 2] if batch == 1 else colsum[:, 2].sum(0)).to(t_db)
         return (dx.view(shape), None if not has_delta else ddelta.view(shape), dw.to(t_w),
                 db.to(t_b), dgamma, dbeta, None, None, None, ddb)
 
@@ -1059,7 +1066,8 @@ class _CeLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dl,) = ctx.saved_tensors
-        return (dl * g.to(dl.dtype)).view(ctx.shape), None, None, None
+        # in place: dl is this node's private buffer (a second backward through the same node is not supported)
+        return dl.mul_(g.to(dl.dtype)).view(ctx.shape), None, None, None
 
 
 def ce_loss(logits, targets, ignore_index=0, n_valid=None):
