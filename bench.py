@@ -450,8 +450,9 @@ def run_ours(args):
                    "execution": "CUDA-graph replay of forward + loss + backward (one graph launch per step)"
                                 + ("" if world == 1 else
                                    (", bucketed NCCL all-reduce after the replay" if gstep.reduce_after_replay else
-                                    ", bucketed NCCL all-reduces captured inside the graph (forked off the backward "
-                                    "as each bucket completes)")),
+                                    ", bucketed NCCL all-reduces captured inside the graph ("
+                                    + ("forked off the backward as each bucket completes" if gstep.overlap
+                                       else "after the backward") + ")")),
                    "eager_ms_per_step": round(eager_ms, 3),
                    "loss": round(float(loss_val), 4)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

@@ -799,10 +799,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const float bm = (has_bm && row_ok) ? g.bias_m[row] : 0.f;
         // bias of the next 32 columns: one coalesced load per lane, a block ahead of its use, broadcast to the rows
         // through the staging tile
-        float bnext = (bias_n != nullptr && n0 + lane < ncols) ? __ldg(bias_n + n0 + lane) : 0.f;
+        bool done = false;
+        if constexpr (EPI == EPI_STORE && CW % 64 == 0) {
+          // plain bf16 store: 64 columns per step, so that every row segment that leaves is a whole 128-byte line
+          if (!p_f32 && p_vec && !p_acc && !p_skip) {
+            done = true;
+#pragma unroll 1
+            for (int c = 0; c < CW; c += 64) {
+              if (n0 + c >= ncols) break;
+              uint32_t rr[64];
+              tmem_ld32_nowait(taddr + c, rr);
+              tmem_ld32_nowait(taddr + c + 32, rr + 32);
+              float bl0 = 0.f, bl1 = 0.f;
+              if (bias_n != nullptr) {
+                if (n0 + c + lane < ncols) bl0 = __ldg(bias_n + n0 + c + lane);
+                if (n0 + c + 32 + lane < ncols) bl1 = __ldg(bias_n + n0 + c + 32 + lane);
+              }
+              tmem_wait_ld_tied(rr);
+              reg_tie32(rr + 32);
+              float* v = reinterpret_cast<float*>(rr);
+              if (has_bm) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] += bm;
+              }
+              if (bias_n != nullptr) {
+                reinterpret_cast<float*>(stg)[lane] = bl0;
+                reinterpret_cast<float*>(stg)[32 + lane] = bl1;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(stg + 4 * j);
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+                __syncwarp();
+              }
+              warp_store64_bf16(stg, lane, out_w, 2 * p_ldc, rows_valid, n0 + c, ncols, v, 1.f);
+            }
+          }
+        }
+        float bnext = (!done && bias_n != nullptr && n0 + lane < ncols) ? __ldg(bias_n + n0 + lane) : 0.f;
 #pragma unroll 1
         for (int c = 0; c < CW; c += 32) {
-          if (n0 + c >= ncols) break;            // warp-uniform: nothing left in this row block
+          if (done || n0 + c >= ncols) break;    // warp-uniform: nothing left in this row block
           uint32_t rr[32];
           tmem_ld32(taddr + c, rr);
           float v[32];

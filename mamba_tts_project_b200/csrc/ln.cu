@@ -230,12 +230,19 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
 
   // column sums: warps -> CTA -> one RED per column per CTA
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 3 * Dm; idx += kLnWarps * 32) {
-    const int which = idx / Dm, e = idx - which * Dm;
-    float t = 0.f;
+  // (16-byte vector REDs: a quarter of the atomic operations the L2 has to serialise per address group)
+  const int nv = Dm / 4;
+  for (int idx = threadIdx.x; idx < 3 * nv; idx += kLnWarps * 32) {
+    const int which = idx / nv, e = (idx - which * nv) * 4;
+    float4 t = *reinterpret_cast<const float4*>(&red[0][which][e]);
 #pragma unroll
-    for (int wv = 0; wv < kLnWarps; ++wv) t += red[wv][which][e];
-    atomicAdd(p.colsum + ((int64_t)bidx * 3 + which) * Dm + e, t);
+    for (int wv = 1; wv < kLnWarps; ++wv) {
+      const float4 u = *reinterpret_cast<const float4*>(&red[wv][which][e]);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* dst = p.colsum + ((int64_t)bidx * 3 + which) * Dm + e;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                 : "memory");
   }
 }
 
@@ -254,7 +261,7 @@ template <typename T>
 static int dispatch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t s) {
   const int batch = p.rows / p.rows_per_batch;
   // ~4 waves of CTAs; every warp walks `rows_per_warp` consecutive rows of one batch element
-  int rows_per_warp = (p.rows + 4 * kNumSMs * 4 * kLnWarps - 1) / (4 * kNumSMs * 4 * kLnWarps);
+  int rows_per_warp = (p.rows + 2 * kNumSMs * 4 * kLnWarps - 1) / (2 * kNumSMs * 4 * kLnWarps);
   rows_per_warp = max(1, min(rows_per_warp, 64));
   const int per_cta = rows_per_warp * kLnWarps;
   const dim3 grid((p.rows_per_batch + per_cta - 1) / per_cta, batch);
@@ -317,6 +324,7 @@ extern "C" int mtts_add_layernorm_fwd(const mtts_add_layernorm_fwd_params* p, mt
 extern "C" int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream) {
   if (!p || !p->x_out || !p->dout || !p->mean || !p->rstd || !p->ln_weight || !p->dx || !p->colsum)
     return MTTS_ERR_NULL;
+  if (!mtts::aligned16(p->colsum)) return MTTS_ERR_ALIGN;   // 16-byte vector REDs
   if (p->rows < 0 || p->dim < 4 || p->dim % 4 != 0 || p->dim > 1024 || p->rows_per_batch < 1 ||
       p->rows % p->rows_per_batch != 0 || p->rows / p->rows_per_batch > 65535)
     return MTTS_ERR_SHAPE;

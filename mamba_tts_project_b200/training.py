@@ -119,15 +119,21 @@ class GraphedForwardBackward:
     ``GradAllReducer.finish()`` after it (the all-reduce then runs after the backward, not under it)."""
 
     def __init__(self, decoder, tokens, text_hidden, z_style, targets=None, amp_dtype=torch.bfloat16,
-                 pad_id=0, warmup=3, reducer=None):
+                 pad_id=0, warmup=3, reducer=None, overlap=None):
         """``reducer``: a ``dp.GradAllReducer`` over ``decoder`` -- its bucketed NCCL all-reduces are then captured
-        INSIDE the graph, each one forked off the backward at the point where its bucket is complete, so a replay
-        overlaps communication with the rest of the backward exactly like the eager hooks do (and ``finish()`` must
-        not be called after a replay: it is part of it).  If the capture of the collectives fails (backend that
+        INSIDE the graph (``finish()`` must not be called after a replay: it is part of it).  ``overlap=True``: each
+        all-reduce is forked off the backward at the point where its bucket is complete, like the eager hooks do;
+        ``overlap=False``: all of them follow the backward, still inside the graph.  Default: environment variable
+        ``MTTS_DP_OVERLAP`` (1 / 0), else False -- measured on 2 and 8 B200s: the persistent one-CTA-per-SM GEMMs of
+        the backward wait for the SMs a concurrent NCCL kernel holds, which costs more than the overlap hides.  If the capture of the collectives fails (backend that
         cannot be captured), the graph is re-captured without them and ``reduce_after_replay`` is set: the caller's
         ``reducer.finish()`` then follows each replay as before."""
         self.decoder, self.amp_dtype, self.pad_id = decoder, amp_dtype, pad_id
         self.reducer, self.reduce_after_replay = reducer, False
+        if overlap is None:
+            import os
+            overlap = os.environ.get("MTTS_DP_OVERLAP", "0") == "1"
+        self.overlap = bool(overlap)
         dev = next(decoder.parameters()).device
         targets = tokens if targets is None else targets
         self._in = [torch.empty(t.shape, dtype=t.dtype, device=dev)
@@ -174,9 +180,12 @@ class GraphedForwardBackward:
             logits = self.decoder(tok, text, z)
         # (ignore_index = -1 never matches a codec id: every token counts)
         loss = ops.ce_loss(logits, tgt, ignore_index=-1 if self.pad_id is None else self.pad_id)
+        if self.reducer is not None and not self.overlap:
+            self.reducer.pause()           # no all-reduce from the gradient hooks: finish() launches them all
         loss.backward()
         if self.reducer is not None:
-            self.reducer.finish()          # waits for the bucket all-reduces launched by the gradient hooks
+            self.reducer.resume()
+            self.reducer.finish()          # launches what is pending, waits, re-points the gradients
         return loss.detach()
 
     def __call__(self, tokens, text_hidden, z_style, targets=None):
