@@ -377,7 +377,10 @@ def run_ours(args):
         pass
     ach = alg[dom] / kern[dom] / 1e6
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from an "
+                                  "ncu --set full capture of this kernel at this shape (not measurable inside the run)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": round(kern[dom], 4),
                 "launches_per_step": len(hook[dom]) // args.steps,
                 "share_of_step": round(kern[dom] * (len(hook[dom]) / args.steps) / ms, 4),

@@ -57,6 +57,9 @@ const char* mtts_error_string(int code);
 int mtts_abi_version(void);
 /* Compiled-for architecture, e.g. 100 for sm_100a. */
 int mtts_target_sm(void);
+/* Which selective-scan kernel family serves a shape: 0 = the library's choice (default), 1 = time-sequential,
+ * 2 = time-parallel.  Process-wide; a test / measurement hook (both families are parity-tested on the same inputs). */
+int mtts_set_scan_impl(int impl);
 /* sizeof() of the n-th parameter struct below (declaration order, from 0); -1 past the end.
  * Lets a foreign binding verify its mirror of the layout when it loads the library. */
 int mtts_sizeof_params(int which);

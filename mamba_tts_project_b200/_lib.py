@@ -187,6 +187,7 @@ ENTRY_POINTS = {
     "mtts_error_string": None,
     "mtts_abi_version": None,
     "mtts_target_sm": None,
+    "mtts_set_scan_impl": None,
     "mtts_sizeof_params": None,
     "mtts_causal_conv1d_fwd": Conv1dFwdParams,
     "mtts_causal_conv1d_bwd": Conv1dBwdParams,
@@ -256,6 +257,13 @@ def load():
                                f"{lib.mtts_sizeof_params(i)} in the library")
     _lib = lib
     return lib
+
+
+def set_scan_impl(name) -> None:
+    """Force a selective-scan kernel family: None / "auto", "seq" (time-sequential) or "wide" (time-parallel)."""
+    rc = load().mtts_set_scan_impl({None: 0, "auto": 0, "seq": 1, "wide": 2}[name])
+    if rc != 0:
+        raise RuntimeError("mtts_set_scan_impl failed")
 
 
 def io_dtype(t: torch.Tensor) -> int:

@@ -16,6 +16,19 @@ extern "C" const char* mtts_error_string(int code) {
   }
 }
 
+// The one piece of process-wide state: which selective-scan kernel family serves a shape (0 = the library's
+// choice).  A test / measurement hook, set explicitly -- the launch path reads no environment variables.
+#include <atomic>
+namespace mtts {
+static std::atomic<int> g_scan_impl{0};
+int scan_impl_override() { return g_scan_impl.load(std::memory_order_relaxed); }
+}  // namespace mtts
+extern "C" int mtts_set_scan_impl(int impl) {
+  if (impl < 0 || impl > 2) return MTTS_ERR_UNSUPPORTED;
+  mtts::g_scan_impl.store(impl, std::memory_order_relaxed);
+  return MTTS_OK;
+}
+
 extern "C" int mtts_abi_version(void) { return 1; }
 
 extern "C" int mtts_target_sm(void) { return 100; }

@@ -195,13 +195,13 @@ __device__ __forceinline__ void slice_reduce_store(float (&v)[4], int g, float* 
 
 // Which kernel family runs a scan.  The time-sequential kernels (scan_fwd.cu / scan_bwd.cu: one thread per
 // channel and 4-state slice) need batch x dim channels to fill the machine; long sequences over few
-// channels go to the time-parallel kernels (scan_*_wide.cu: lanes = timesteps).  MTTS_SCAN_IMPL=seq|wide
-// overrides the choice (tests exercise both families on the same inputs).
+// channels go to the time-parallel kernels (scan_*_wide.cu: lanes = timesteps).  mtts_set_scan_impl() overrides
+// the choice (tests exercise both families on the same inputs); no environment is read on the launch path.
+int scan_impl_override();   // api.cu: 0 = automatic, 1 = time-sequential, 2 = time-parallel ("wide")
 inline bool scan_use_wide(int batch, int dim, int seqlen) {
-  if (const char* e = getenv("MTTS_SCAN_IMPL")) {
-    if (e[0] == 's') return false;
-    if (e[0] == 'w') return true;
-  }
+  const int o = scan_impl_override();
+  if (o == 1) return false;
+  if (o == 2) return true;
   const int64_t channels = (int64_t)batch * dim;
   return channels < 8192 && channels * seqlen >= (int64_t(1) << 24);
 }

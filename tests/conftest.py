@@ -35,3 +35,11 @@ def rel_err(a, b):
         return 0.0
     denom = b.abs().max().item()
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+@pytest.fixture
+def scan_impl():
+    """Force a selective-scan kernel family for the test (``mtts_set_scan_impl``), back to automatic afterwards."""
+    from mamba_tts_project_b200 import _lib
+    yield _lib.set_scan_impl
+    _lib.set_scan_impl(None)

@@ -111,10 +111,10 @@ SCAN_CASES = [
 @pytest.mark.parametrize("case", SCAN_CASES, ids=[f"b{c[0]}d{c[1]}t{c[2]}n{c[3]}" + "".join(
     k.replace("with_", "_") + str(int(v)) for k, v in c[4].items()) for c in SCAN_CASES])
 @pytest.mark.parametrize("impl", ["seq", "wide"])
-def test_selective_scan_fwd_bwd_vs_oracle(case, dtype, impl, monkeypatch):
+def test_selective_scan_fwd_bwd_vs_oracle(case, dtype, impl, scan_impl):
     # both kernel families (time-sequential / time-parallel, csrc/scan_common.cuh::scan_use_wide) on the
     # same inputs; without the override the library picks by problem size
-    monkeypatch.setenv("MTTS_SCAN_IMPL", impl)
+    scan_impl(impl)
     batch, dim, T, N, kw = case
     inp = make_scan_inputs(batch, dim, T, N, seed=T + N, dtype=dtype, **kw)
     ref = run_scan_oracle(inp)
@@ -188,7 +188,7 @@ def test_selective_scan_state_passing_full_size():
     check("slice vs oracle", full[:1, sl], ref, BF16_TOL)
 
 
-def test_selective_scan_backward_full_size_properties(monkeypatch):
+def test_selective_scan_backward_full_size_properties(scan_impl):
     """Backward at a C4-class shape (bf16, d_inner 2048, T 4096, B 8 = 16384 channels), three size-independent
     checks: (1) the two independent kernel families (time-sequential / time-parallel) agree on every
     gradient; (2) quantities with a closed form in the inputs: dD = sum dout silu(z) u,
@@ -210,7 +210,7 @@ def test_selective_scan_backward_full_size_properties(monkeypatch):
     names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dz", "ddelta_bias"]
     res = {}
     for impl in ("seq", "wide"):
-        monkeypatch.setenv("MTTS_SCAN_IMPL", impl)
+        scan_impl(impl)
         out = selective_scan_fn(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias, delta_softplus=True)
         res[impl] = (out.detach(), torch.autograd.grad(out, leaves, dout))
     check("out seq vs wide", res["seq"][0], res["wide"][0], BF16_TOL)
@@ -231,6 +231,64 @@ def test_selective_scan_backward_full_size_properties(monkeypatch):
     check("du slice vs oracle", g["du"][:1, sl], rg[0], BF16_TOL)
     check("ddelta slice vs oracle", g["ddelta"][:1, sl], rg[1], BF16_TOL)
     check("dz slice vs oracle", g["dz"][:1, sl], rg[2], BF16_TOL)
+
+
+def test_selective_scan_longest_c4_shape_properties(scan_impl):
+    """BASELINE configs[3] at its longest sequence (B 2 x d_inner 2048 x T 65536, N 16, bf16), the shape the
+    time-parallel family exists for, through size-independent properties -- the CPU oracle would take hours here:
+    (1) time-parallel and time-sequential kernels agree on the output, the last state and every gradient;
+    (2) composition over time: the scan of [0, T) equals the scan of [0, T/2) followed by the scan of [T/2, T) started
+        from the first half's last state (the stateful contract of ``mamba_decoder.py:9-15``);
+    (3) linearity in (u, D-path): with z absent, out(u1 + u2) = out(u1) + out(u2) for fixed delta, B, C;
+    (4) a channel slice of the first 2048 timesteps against the CPU oracle."""
+    from mamba_tts_project_b200 import selective_scan_fn
+    torch.manual_seed(3)
+    Bz, Dm, T, N = 2, 2048, 65536, 16
+    dev, bf = "cuda", torch.bfloat16
+    u = torch.randn(Bz, Dm, T, device=dev, dtype=bf).requires_grad_()
+    delta = (0.5 * torch.rand(Bz, Dm, T, device=dev)).to(bf).requires_grad_()
+    A = (-0.5 * torch.rand(Dm, N, device=dev) - 1e-2).requires_grad_()
+    Bm = torch.randn(Bz, N, T, device=dev, dtype=bf).requires_grad_()
+    Cm = torch.randn(Bz, N, T, device=dev, dtype=bf).requires_grad_()
+    D = torch.randn(Dm, device=dev).requires_grad_()
+    z = torch.randn(Bz, Dm, T, device=dev, dtype=bf).requires_grad_()
+    bias = (0.5 * torch.rand(Dm, device=dev)).requires_grad_()
+    dout = torch.randn(Bz, Dm, T, device=dev, dtype=bf)
+    leaves = [u, delta, A, Bm, Cm, D, z, bias]
+    names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dz", "ddelta_bias"]
+    res = {}
+    for impl in ("seq", "wide"):
+        scan_impl(impl)
+        out, last = selective_scan_fn(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias, delta_softplus=True,
+                                      return_last_state=True)
+        res[impl] = (out.detach(), last.detach(), torch.autograd.grad(out, leaves, dout))
+    check("out seq vs wide", res["seq"][0], res["wide"][0], BF16_TOL)
+    check("last state seq vs wide", res["seq"][1], res["wide"][1], 1e-3)
+    for n, a, b in zip(names, res["seq"][2], res["wide"][2]):
+        check(n + " seq vs wide", a, b, BF16_TOL)
+    scan_impl(None)                      # the library's own choice for this shape
+    with torch.no_grad():
+        full, last = selective_scan_fn(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias, delta_softplus=True,
+                                       return_last_state=True)
+        h = T // 2
+        c = lambda t, a, b: t[..., a:b]
+        o1, s1 = selective_scan_fn(c(u, 0, h), c(delta, 0, h), A, c(Bm, 0, h), c(Cm, 0, h), D, z=c(z, 0, h),
+                                   delta_bias=bias, delta_softplus=True, return_last_state=True)
+        o2, s2 = selective_scan_fn(c(u, h, T), c(delta, h, T), A, c(Bm, h, T), c(Cm, h, T), D, z=c(z, h, T),
+                                   delta_bias=bias, delta_softplus=True, return_last_state=True, initial_state=s1)
+        check("first half", full[..., :h], o1, BF16_TOL)
+        check("second half from the carried state", full[..., h:], o2, BF16_TOL)
+        check("last state of the composition", last, s2, 1e-3)
+        u2 = torch.randn_like(u)
+        lin = lambda x: selective_scan_fn(x, delta, A, Bm, Cm, D, delta_bias=bias, delta_softplus=True).float()
+        check("linearity in u", lin((u.float() + u2.float()).to(bf)), lin(u) + lin(u2), 3e-2)
+    sl, Ts = slice(100, 108), 2048
+    ref = selective_scan_ref(u[:1, sl, :Ts].detach().cpu().float(), delta[:1, sl, :Ts].detach().cpu().float(),
+                             A[sl].detach().cpu(), Bm[:1, :, :Ts].detach().cpu().float(),
+                             Cm[:1, :, :Ts].detach().cpu().float(), D[sl].detach().cpu(),
+                             z=z[:1, sl, :Ts].detach().cpu().float(), delta_bias=bias[sl].detach().cpu(),
+                             delta_softplus=True)
+    check("slice vs oracle", full[:1, sl, :Ts], ref, BF16_TOL)
 
 
 def test_selective_scan_errors():
@@ -714,9 +772,9 @@ def _canaries_intact(buf, n, pad=4096):
 @pytest.mark.parametrize("shape", [(2, 24, 300, 16), (1, 16, 1, 16), (1, 20, 257, 16), (1, 8, 200, 5),
                                    (2, 16, 64, 16), (1, 40, 96, 64), (1, 12, 33, 40)],
                          ids=lambda s: "b%dd%dt%dn%d" % s)
-def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, monkeypatch):
+def test_selective_scan_abi_writes_stay_in_bounds(shape, dtype, impl, scan_impl):
     from mamba_tts_project_b200 import _lib
-    monkeypatch.setenv("MTTS_SCAN_IMPL", impl)
+    scan_impl(impl)
     Bz, Dm, T, N = shape
     torch.manual_seed(T)
     dev, f32 = "cuda", torch.float32

@@ -23,7 +23,10 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
-        'sm__warps_active.avg.per_cycle_active', 'smsp__inst_executed.sum']
+        'sm__warps_active.avg.per_cycle_active', 'smsp__inst_executed.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed']
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 for r in rows[2:]:
