@@ -54,9 +54,12 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
   const int bidx = row / p.rows_per_batch;
   const float* gam = p.film_gamma ? p.film_gamma + (int64_t)bidx * Dm : nullptr;
   const float* bet = p.film_beta ? p.film_beta + (int64_t)bidx * Dm : nullptr;
-  float w[kG][4], b[kG][4];
+  // (rows wider than 512: 64 more registers per thread would halve the resident warps of a kernel that lives on
+  // bytes in flight -- the operands are fetched where they are used instead, from L1)
+  constexpr bool kPre = kG <= 4;
+  float w[kPre ? kG : 1][4], b[kPre ? kG : 1][4];
 #pragma unroll
-  for (int g = 0; g < kG; ++g) {
+  for (int g = 0; g < (kPre ? kG : 0); ++g) {
     const int e = (g * 32 + lane) * 4;
     if (e < Dm) {
       load4<float>(p.ln_weight + e, w[g]);
@@ -97,8 +100,26 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
     const int e = (g * 32 + lane) * 4;
     if (e < Dm) {
       float o[4];
+      if constexpr (kPre) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = fmaf((v[g][j] - mean) * rstd, w[g][j], b[g][j]);
+        for (int j = 0; j < 4; ++j) o[j] = fmaf((v[g][j] - mean) * rstd, w[g][j], b[g][j]);
+      } else {
+        float wv[4], bv[4];
+        load4<float>(p.ln_weight + e, wv);
+        load4<float>(p.ln_bias + e, bv);
+        if (gam) {
+          float gm[4], bt[4];
+          load4<float>(gam + e, gm);
+          load4<float>(bet + e, bt);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            wv[j] *= gm[j];
+            bv[j] = fmaf(gm[j], bv[j], bt[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf((v[g][j] - mean) * rstd, wv[j], bv[j]);
+      }
       store4<T>(out + e, o);
     }
   }
@@ -110,18 +131,23 @@ add_layernorm_fwd_kernel(const mtts_add_layernorm_fwd_params p) {
 //   S1[b]  = sum_t dout xhat,  S2[b] = sum_t dout,  S3[b] = sum_t dx  (per batch element and column,
 //            accumulated into `colsum` (batch, 3, dim)); S3 is the gradient of delta's bias; the host finishes dw = sum_b gamma_b S1_b, db = sum_b gamma_b S2_b,
 //            dgamma_b = w S1_b + bias S2_b, dbeta_b = S2_b  on (batch, dim)-sized tensors.
+// warps per CTA of the backward: the per-warp column statistics (3 x dim floats) must fit the static 48 KB
+template <int kG>
+__host__ __device__ constexpr int ln_bwd_warps() { return kG <= 4 ? 4 : 2; }
+
 template <typename T, int kG>
-__global__ void __launch_bounds__(kLnWarps * 32, kG <= 4 ? 5 : 2)
+__global__ void __launch_bounds__(ln_bwd_warps<kG>() * 32, kG <= 4 ? 5 : 7)
 add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_per_warp) {
+  constexpr int kLnWarps = ln_bwd_warps<kG>();     // (shadows the forward's constant inside this kernel)
   // Column statistics live in shared memory (one private row set per warp, each lane owns its columns, so
   // plain load/add/store): keeping them in registers cost 48 registers per thread and with them half the
   // resident warps -- the kernel is bound by bytes in flight, not by LSU slots.
   __shared__ __align__(16) float red[kLnWarps][3][kG * 128];
-  // ln_weight * gamma_b: shared for dim <= 512 (frees 16 registers per thread), per-lane registers above
-  // (the 48 KB static limit is taken by `red` there)
-  constexpr bool kWsm = kG <= 4;
-  __shared__ __align__(16) float wsm[kWsm ? kG * 128 : 4];
-  float wreg[kWsm ? 1 : kG][4];
+  // ln_weight * gamma_b lives in shared memory (frees 16-32 registers per thread)
+  constexpr bool kWsm = true;
+  __shared__ __align__(16) float wsm[kG * 128];
+  float wreg[1][4];
+  constexpr bool kLateUp = false;    // (fetching the upstream gradient where it is used costs a second round trip per row: 186 -> 284 us at dim 1024)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dm = p.dim;
   // a CTA never straddles two batch elements: grid.x tiles rows_per_batch, grid.y = batch
@@ -164,11 +190,24 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
     const T* go = reinterpret_cast<const T*>(p.dout) + row * Dm;
     float xh[kG][4], gg[kG][4], up[kG][4];
     float a = 0.f, bsum = 0.f;
+    // the NEXT row of this warp is asked into L2 now (one 128-byte line per lane and tensor, no registers): its loads
+    // then cost an L2 hit instead of an HBM round trip per row of the warp's dependent row-by-row chain
+    if (r + 1 < r_end) {
+      const int64_t nrow = row + 1;
+      for (int off = lane * 128; off < Dm * 4; off += 32 * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.x_out + nrow * Dm) + off));
+        if (p.dx_out)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.dx_out + nrow * Dm) + off));
+        if (off < Dm * (int)sizeof(T))
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(
+              reinterpret_cast<const T*>(p.dout) + nrow * Dm) + off));
+      }
+    }
     // the upstream residual gradient is fetched together with x_out / dout (one round trip per row)
 #pragma unroll
     for (int g = 0; g < kG; ++g) {
       const int e = (g * 32 + lane) * 4;
-      if (p.dx_out && e < Dm) {
+      if (!kLateUp && p.dx_out && e < Dm) {
         load4<float>(p.dx_out + row * Dm + e, up[g]);
       } else {
 #pragma unroll
@@ -217,6 +256,9 @@ add_layernorm_bwd_kernel(const mtts_add_layernorm_bwd_params p, const int rows_p
       const int e = (g * 32 + lane) * 4;
       if (e < Dm) {
         float dx[4];
+        if constexpr (kLateUp) {
+          if (p.dx_out) load4<float>(p.dx_out + row * Dm + e, up[g]);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) dx[j] = rstd * (gg[g][j] - a - xh[g][j] * bsum) + up[g][j];
         float4 c3 = *reinterpret_cast<const float4*>(&red[warp][2][e]);
@@ -257,21 +299,38 @@ static int dispatch_ln_fwd(const mtts_add_layernorm_fwd_params& p, cudaStream_t 
   return launch_status();
 }
 
-template <typename T>
-static int dispatch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t s) {
+template <typename T, int kG>
+static int launch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t s) {
+  constexpr int W = ln_bwd_warps<kG>();
   const int batch = p.rows / p.rows_per_batch;
-  // ~4 waves of CTAs; every warp walks `rows_per_warp` consecutive rows of one batch element
-  int rows_per_warp = (p.rows + 2 * kNumSMs * 4 * kLnWarps - 1) / (2 * kNumSMs * 4 * kLnWarps);
+  // ONE wave of CTAs (a second, partly filled wave costs as much as a full one: 1.6 waves measured 66 us where
+  // 0.9 waves take 5x us at (32768, 512)); every warp walks `rows_per_warp` consecutive rows of one batch element
+  constexpr int kCtasPerSm = kG <= 4 ? 5 : 7;          // = the kernel's __launch_bounds__
+  const int slots = kNumSMs * kCtasPerSm * W;
+  int rows_per_warp = (p.rows + slots - 1) / slots;
   rows_per_warp = max(1, min(rows_per_warp, 64));
-  const int per_cta = rows_per_warp * kLnWarps;
+  // the grid tiles every batch element separately: shrink the tile until the whole grid fits the wave
+  while (rows_per_warp < 64 &&
+         (long long)((p.rows_per_batch + rows_per_warp * W - 1) / (rows_per_warp * W)) * batch > kNumSMs * kCtasPerSm)
+    ++rows_per_warp;
+  const int per_cta = rows_per_warp * W;
   const dim3 grid((p.rows_per_batch + per_cta - 1) / per_cta, batch);
-  const int groups = (p.dim + 127) / 128;
-  if (groups <= 2) add_layernorm_bwd_kernel<T, 2><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
-  else if (groups <= 4) add_layernorm_bwd_kernel<T, 4><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
-  else if (groups <= 8) add_layernorm_bwd_kernel<T, 8><<<grid, kLnWarps * 32, 0, s>>>(p, rows_per_warp);
-  else return MTTS_ERR_SHAPE;
+  add_layernorm_bwd_kernel<T, kG><<<grid, W * 32, 0, s>>>(p, rows_per_warp);
   return launch_status();
 }
+
+template <typename T>
+static int dispatch_ln_bwd(const mtts_add_layernorm_bwd_params& p, cudaStream_t s) {
+  const int groups = (p.dim + 127) / 128;
+  if (groups <= 2) return launch_ln_bwd<T, 2>(p, s);
+  if (groups <= 4) return launch_ln_bwd<T, 4>(p, s);
+  if (groups <= 8) return launch_ln_bwd<T, 8>(p, s);
+  return MTTS_ERR_SHAPE;
+}
+
+}  // namespace mtts
+
+namespace mtts {
 
 // Parameter gradients of a FiLM'd LayerNorm from the backward kernel's per-batch column sums: one thread per column
 // walks the batch (a (batch, dim)-sized problem: replaces two einsum, an addcmul, a mul and a sum launch).

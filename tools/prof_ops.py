@@ -36,6 +36,8 @@ def traced(name, params, launches=1):
 def main():
     out = next((a for a in sys.argv[1:] if a.endswith(".json")), None)
     cfg = bench.C2
+    if "--c5" in sys.argv:       # one micro-batch of BASELINE configs[4]: 24 x d1024, 8 x 4096 tokens, 256 keys
+        cfg = dict(bench.C5, batch=8, t_text=256)
     dev = torch.device("cuda", 0)
     model = bench.build_decoder(cfg, dev).train()
     inp = bench.make_inputs(cfg, cfg["batch"], dev)
