@@ -17,6 +17,7 @@ fp32 (the 1e-4 parity / debug precision) stays on the library GEMMs: the tensor-
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 
@@ -39,7 +40,7 @@ def tc_enabled(dtype) -> bool:
     return _BACKEND == "tc" and dtype == torch.bfloat16
 
 
-_shadow = {}
+_shadow = {}          # id(parameter) -> (weakref to it, version, data_ptr, bf16 copy); entries die with the parameter
 
 
 def bf16_weight(w: torch.Tensor) -> torch.Tensor:
@@ -50,10 +51,12 @@ def bf16_weight(w: torch.Tensor) -> torch.Tensor:
         return w.detach().to(torch.bfloat16)           # the cast belongs to the captured step / a temporary
     key = id(w)
     hit = _shadow.get(key)
-    if hit is not None and hit[0] is w and hit[1] == w._version and hit[2] == w.data_ptr():
+    if hit is not None and hit[0]() is w and hit[1] == w._version and hit[2] == w.data_ptr():
         return hit[3]
     s = w.detach().to(torch.bfloat16)
-    _shadow[key] = (w, w._version, w.data_ptr(), s)
+    if hit is None or hit[0]() is not w:
+        weakref.finalize(w, _shadow.pop, key, None)    # no strong reference: the model can be freed
+    _shadow[key] = (weakref.ref(w), w._version, w.data_ptr(), s)
     return s
 
 
