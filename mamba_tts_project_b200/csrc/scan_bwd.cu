@@ -24,6 +24,12 @@
 // Two MUFU.EX2 per state update (pre-pass + re-run), everything else packed fp32x2.
 #include "scan_common.cuh"
 
+// Timing experiments only (results are wrong when set): bit 0 skips the dB / dC channel reduction + REDs, bit 1 the
+// slice reductions, bit 2 the E phase, bit 3 the pre-pass, bit 4 the P phase math.
+#ifndef MTTS_SCAN_DBG_SKIP
+#define MTTS_SCAN_DBG_SKIP 0
+#endif
+
 namespace mtts {
 
 int dispatch_scan_bwd_wide(const mtts_scan_bwd_params& p, cudaStream_t stream);  // scan_bwd_wide.cu
@@ -360,7 +366,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
       }
       // pre-pass: state at the start of every group of 4 timesteps
 #pragma unroll 1
-      for (int s = 0; s < 7; ++s) {
+      for (int s = 0; s < ((MTTS_SCAN_DBG_SKIP & 8) ? 0 : 7); ++s) {
         float dtv[CC][4], duv[CC][4];
 #pragma unroll
         for (int k = 0; k < CC; ++k) {
@@ -479,12 +485,21 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
           dCv[j] = dC0.x; dCv[4 + j] = dC0.y; dCv[8 + j] = dC1.x; dCv[12 + j] = dC1.y;
           dBv[j] = dB0.x; dBv[4 + j] = dB0.y; dBv[8 + j] = dB1.x; dBv[12 + j] = dB1.y;
         }
+        if constexpr (!(MTTS_SCAN_DBG_SKIP & 2)) {
 #pragma unroll
-        for (int k = 0; k < CC; ++k) {
-          slice_reduce_store<NG>(sgb[k], g, sgr + k * RS + 4 * s);
-          slice_reduce_store<NG>(dda[k], g, dar + k * RS + 4 * s);
+          for (int k = 0; k < CC; ++k) {
+            slice_reduce_store<NG>(sgb[k], g, sgr + k * RS + 4 * s);
+            slice_reduce_store<NG>(dda[k], g, dar + k * RS + 4 * s);
+          }
+        } else {
+          if (sgb[0][0] + dda[0][0] + sgb[CC - 1][3] + dda[CC - 1][3] == 123.f) sgr[0] = 0.f;
         }
-        {
+        if constexpr (MTTS_SCAN_DBG_SKIP & 1) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc += dBv[i] + dCv[i];
+          if (acc == 123.f) p.dB[0] = acc;
+        } else {
           const int tg = t0 + 4 * s + red_j;
           const int nvalid = red_ok ? L - tg : 0;
           chan_reduce_red<NG, kVec>(dBv, lane, p.dB + red_off + t0 + 4 * s, nvalid);
@@ -499,7 +514,7 @@ scan_bwd_kernel(const mtts_scan_bwd_params p, const int nchunks) {
     cp_async_wait_all();
     if (tile > 0) fetch_tile(tile - 1);
 #pragma unroll
-    for (int k = 0; k < kIt; ++k) {
+    for (int k = 0; k < ((MTTS_SCAN_DBG_SKIP & 4) ? 0 : kIt); ++k) {
       const int idx = tid + k * kThreads;
       const int ich = idx / kVecPerRow, it = (idx % kVecPerRow) * VE;
       const int cc = c0 + ich;
