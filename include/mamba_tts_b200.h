@@ -570,6 +570,9 @@ typedef struct {
   float scale;
   int32_t flags;         /* MTTS_GEMM_SINGLE_CTA: never pair CTAs (cta_group::1 tiles of 128 rows; measurements);
                             MTTS_GEMM_AUX_GELU_GRAD: see MTTS_EPI_GELU */
+  float* row_stat;       /* MTTS_EPI_SOFTMAX, optional: (batch_outer, batch_inner, m) fp32, the base-2 log-sum-exp of
+                            every row, lse2 = log2(sum_n exp(scale * acc + mask)): P = exp2(scale * log2(e) * acc - lse2);
+                            +inf for a fully masked row.  What the fused attention backward needs instead of P. */
 } mtts_gemm_params;
 int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream);
 
@@ -635,6 +638,8 @@ typedef struct {
   void* p;
   void* o;
   void* out;
+  float* lse2; /* (batch, heads, t_q) fp32 or NULL: written by the forward; when given to the backward (and head_dim is
+                  64) the fused mtts_attn_core_bwd replaces the GEMM-by-GEMM core and `p` / `ds` are not touched */
   const void* dout;
   void* d_o;
   void* ds;
@@ -648,6 +653,28 @@ typedef struct {
 } mtts_cross_attn_params;
 int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
 int mtts_cross_attn_bwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * attn_core_bwd -- the backward of softmax(scale q k^T + mask) v for all heads in ONE launch, with the score-sized
+ * tensors (P, dP, dS) kept on the SM (tensor memory / shared memory): given the forward's per-row base-2
+ * log-sum-exp (mtts_gemm's row_stat), o and d_o, it produces dq and dk | dv.  head_dim = 64 (d_model = 64 heads),
+ * t_kv <= 256; q, o, d_o, dq (batch, t_q, d_model), kv, dkv (batch, t_kv, 2 d_model) bf16 contiguous; lse2
+ * (batch, heads, t_q) fp32; mask (batch, t_kv) uint8, 1 = attend, or NULL.  Used by mtts_cross_attn_bwd when the
+ * shapes allow (replaces its dV / dsoftmax / dQ / dK GEMMs).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch, heads, t_q, t_kv, d_model;
+  float scale;
+  const void* q;
+  const void* kv;
+  const void* o;
+  const void* d_o;
+  const float* lse2;
+  const uint8_t* mask;
+  void* dq;
+  void* dkv;
+} mtts_attn_core_bwd_params;
+int mtts_attn_core_bwd(const mtts_attn_core_bwd_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FFN / projection glue (mamba_decoder.py:39-43,86-88: Linear -> GELU -> Linear, and the bias gradients

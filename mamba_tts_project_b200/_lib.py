@@ -143,7 +143,7 @@ GemmParams = _struct("GemmParams", """
     p:out l:ldc l:c_bo_stride l:c_bi_stride
     p:bias_n p:bias_m
     p:aux l:ld_aux l:aux_bo_stride l:aux_bi_stride
-    p:mask l:mask_bo_stride f:scale i:flags""")
+    p:mask l:mask_bo_stride f:scale i:flags p:row_stat""")
 GEMM_SINGLE_CTA, GEMM_AUX_GELU_GRAD = 1, 2
 EPI_STORE, EPI_GELU, EPI_GELU_BWD, EPI_SOFTMAX, EPI_DSOFTMAX, EPI_MUL_AUX = range(6)
 
@@ -167,11 +167,14 @@ class FilmFfnParams(C.Structure):
 
 CrossAttnParams = _struct("CrossAttnParams", """
     i:batch i:t_q i:t_kv i:d_model i:heads i:reserved
-    p:query p:memory p:w_in p:b_in p:w_out p:mask p:q p:kv p:p p:o p:out
+    p:query p:memory p:w_in p:b_in p:w_out p:mask p:q p:kv p:p p:o p:out p:lse2
     p:dout p:d_o p:ds p:dq p:dkv p:dw_in p:db_in p:dw_out p:dquery p:dmemory""")
 
 AddLayerNormFinishParams = _struct("AddLayerNormFinishParams", """
     i:batch i:dim p:colsum p:film_gamma p:ln_weight p:ln_bias p:dweight p:dbias p:dgamma p:dbeta p:ddelta_bias""")
+
+AttnCoreBwdParams = _struct("AttnCoreBwdParams", """
+    i:batch i:heads i:t_q i:t_kv i:d_model f:scale p:q p:kv p:o p:d_o p:lse2 p:mask p:dq p:dkv""")
 
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
@@ -180,7 +183,7 @@ PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdPa
                  GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
                  LengthRegulateFwdParams, LengthRegulateBwdParams, GemmParams,
                  EmbedSumParams, CeLossParams, AdamParams, AdamTensor, FilmFfnParams, CrossAttnParams,
-                 AddLayerNormFinishParams]
+                 AddLayerNormFinishParams, AttnCoreBwdParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -212,6 +215,7 @@ ENTRY_POINTS = {
     "mtts_film_ffn_bwd": FilmFfnParams,
     "mtts_cross_attn_fwd": CrossAttnParams,
     "mtts_cross_attn_bwd": CrossAttnParams,
+    "mtts_attn_core_bwd": AttnCoreBwdParams,
     "mtts_embed_sum_fwd": EmbedSumParams,
     "mtts_embed_sum_bwd": EmbedSumParams,
     "mtts_ce_loss": CeLossParams,

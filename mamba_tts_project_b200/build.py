@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libmamba_tts_b200.so")
-SOURCES = ["api.cu", "conv1d.cu", "scan_fwd.cu", "scan_fwd_wide.cu", "scan_bwd.cu", "scan_bwd_wide.cu", "decode.cu", "ln.cu", "ffn_glue.cu", "skinny.cu", "gemm_sm100.cu", "blocks.cu", "length_regulator.cu", "train_glue.cu"]
+SOURCES = ["api.cu", "conv1d.cu", "scan_fwd.cu", "scan_fwd_wide.cu", "scan_bwd.cu", "scan_bwd_wide.cu", "decode.cu", "ln.cu", "ffn_glue.cu", "skinny.cu", "gemm_sm100.cu", "attn_sm100.cu", "blocks.cu", "length_regulator.cu", "train_glue.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-I", INCLUDE, "-I", CSRC]
 

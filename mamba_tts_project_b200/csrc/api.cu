@@ -63,6 +63,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 23: return (int)sizeof(mtts_film_ffn_params);
     case 24: return (int)sizeof(mtts_cross_attn_params);
     case 25: return (int)sizeof(mtts_add_layernorm_finish_params);
+    case 26: return (int)sizeof(mtts_attn_core_bwd_params);
     default: return -1;
   }
 }

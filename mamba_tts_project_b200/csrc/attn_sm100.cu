@@ -1,0 +1,387 @@
+// Fused backward of the training cross-attention core (mamba_decoder.py:72-77 under loss.backward(), train.py:231)
+// on the 5th-generation tensor cores: S, P, dP and dS never leave the SM.
+//
+//   given   q (B, T, E), k | v (B, Tk, 2E), o and d_o (B, T, E) bf16 (head h = columns [64 h, 64 h + 64)),
+//           lse2 (B, H, T) = base-2 log-sum-exp of every score row (the forward's softmax GEMM writes it)
+//   P  = exp2(scale log2(e) q k^T - lse2)   (masked / padded keys: 0)        delta = rowsum(d_o o)
+//   dS = scale P o (d_o v^T - delta)        dV = P^T d_o        dK = dS^T q        dQ = dS k
+//
+// One CTA per (batch, head).  Everything is computed TRANSPOSED (keys on the TMEM lanes, queries along the columns):
+// with the row statistics of the forward at hand the softmax backward is elementwise, and with keys on the lanes the
+// statistics are per-COLUMN broadcasts (LDS.128 from a 1 KB table) instead of cross-lane reductions.  The 256 keys
+// are taken in two halves of 128 (one M = 128 MMA); per half the CTA walks the query tiles of 128:
+//   MMA   S^T = K_h Q_i^T,  dP^T = V_h dO_i^T                       -> TMEM columns [0, 128), [128, 256)
+//   warps P^T, dS^T (bf16) -> shared memory, in the K-major swizzle-128B operand layout
+//   MMA   dV_h += P^T dO_i,  dK_h += dS^T Q_i   (accumulated in TMEM across the query tiles, columns [256, 384)),
+//         dQ_i(h) = dS K_h                       (columns [384, 448); the SAME shared-memory bytes of dS^T serve as
+//                                                 the MN-major A operand, Q_i / dO_i / K_h as MN-major B operands)
+//   warps dQ_i: half 0 stores it, half 1 adds its own on top;  after the last tile: dK_h, dV_h -> global.
+// warp 0 = TMA producer (K_h / V_h once per half, Q_i / dO_i / O_i double buffered), warp 1 = MMA issuer, warps 2-9 =
+// elementwise + epilogue (thread = one key row of S^T / dP^T, or one query row of dQ).  HBM traffic per layer: q, o, d_o
+// read twice, k / v once, dq written (twice with two halves), dk / dv once -- against five passes over the
+// (B, H, T, Tk) probability / score-gradient tensors of the GEMM-by-GEMM path.
+#include "tc_ptx.cuh"
+
+namespace mtts {
+namespace g100 {
+
+namespace attn {
+constexpr int DH = 64;            // head dimension
+constexpr int TQ = 128;           // query tile
+constexpr int TKH = 128;          // keys per half
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kTileBytes = 128 * 128;                 // a 128-row x 64-element bf16 operand tile
+constexpr uint32_t kStageBytes = 3 * kTileBytes;           // Q_i, dO_i, O_i
+// shared memory: K_h, V_h | 2 stages | P^T, dS^T (2 k-blocks each) | statistics [2][2][128] | barriers
+constexpr size_t kSmemBytes = 2 * kTileBytes + 2 * kStageBytes + 4 * kTileBytes + 2 * 2 * TQ * 4 + 16 * 8 + 16;
+constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+
+struct Args {
+  int B, H, T, Tk, E;
+  const float* lse2;            // (B, H, T)
+  const unsigned char* mask;    // (B, Tk) or nullptr
+  __nv_bfloat16* dq;            // (B, T, E)
+  __nv_bfloat16* dkv;           // (B, Tk, 2E)
+  float scale;
+};
+}  // namespace attn
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// release arrive: orders this warp's shared-memory stores (made visible to the async proxy by the fence above it)
+// before the MMA thread that waits on the barrier
+__device__ __forceinline__ void mbar_arrive_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+__global__ void __launch_bounds__(attn::kThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const attn::Args g) {
+  using namespace attn;
+  extern __shared__ __align__(1024) unsigned char asm_raw[];
+  unsigned char* sm = asm_raw;
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
+  unsigned char* sK = sm;
+  unsigned char* sV = sK + kTileBytes;
+  unsigned char* sStage = sV + kTileBytes;                       // [2][Q | dO | O]
+  unsigned char* sPT = sStage + 2 * kStageBytes;                 // [2 k-blocks of 64 q][128 key rows][128 B]
+  unsigned char* sDST = sPT + 2 * kTileBytes;
+  float* sStat = reinterpret_cast<float*>(sDST + 2 * kTileBytes);   // [stage][lse2 | delta][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * TQ);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* q_full = bars + 2;      // [2]
+  uint64_t* q_empty = bars + 4;     // [2]
+  uint64_t* s_ready = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* dq_ready = bars + 8;
+  uint64_t* tmem_free = bars + 9;
+  uint64_t* kv_done = bars + 10;
+  uint64_t* acc_free = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / g.H, head = blockIdx.x % g.H;
+  const int nq = (g.T + TQ - 1) / TQ;
+  const int nh = g.Tk > TKH ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_do)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      mbar_init(kv_empty, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(q_full + s, 1);
+        mbar_init(q_empty + s, 1);
+      }
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, kEpiWarps);
+      mbar_init(dq_ready, 1);
+      mbar_init(tmem_free, kEpiWarps);
+      mbar_init(kv_done, 1);
+      mbar_init(acc_free, kEpiWarps);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int h = 0; h < nh; ++h) {
+        mbar_wait(kv_empty, (uint32_t)((h & 1) ^ 1));            // every MMA of the previous half has retired
+        mbar_expect_tx(kv_full, 2 * kTileBytes);
+        tma_load_4d(sK, &map_k, kv_full, 0, h * TKH, head, b);
+        tma_load_4d(sV, &map_v, kv_full, 0, h * TKH, head, b);
+        for (int i = 0; i < nq; ++i, ++it) {
+          const int s = it & 1;
+          mbar_wait(q_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
+          unsigned char* st = sStage + (size_t)s * kStageBytes;
+          mbar_expect_tx(q_full + s, kStageBytes);
+          tma_load_4d(st, &map_q, q_full + s, 0, i * TQ, head, b);
+          tma_load_4d(st + kTileBytes, &map_do, q_full + s, 0, i * TQ, head, b);
+          tma_load_4d(st + 2 * kTileBytes, &map_o, q_full + s, 0, i * TQ, head, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t id_kk = instr_desc<128, 128, 0, 0>();   // S^T, dP^T: A K-major, B K-major, N = 128
+      constexpr uint32_t id_kn = instr_desc<128, 64, 0, 1>();    // dV, dK: A K-major (P^T / dS^T), B MN-major, N = 64
+      constexpr uint32_t id_nn = instr_desc<128, 64, 1, 1>();    // dQ: A MN-major (dS), B MN-major (K_h)
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDST = smem_u32(sDST);
+      int it = 0;
+      for (int h = 0; h < nh; ++h) {
+        mbar_wait(kv_full, (uint32_t)(h & 1));
+        mbar_wait(acc_free, (uint32_t)((h & 1) ^ 1));            // the epilogue has read the previous half's dK / dV
+        for (int i = 0; i < nq; ++i, ++it) {
+          const int s = it & 1;
+          const uint32_t aQ = smem_u32(sStage + (size_t)s * kStageBytes), aDO = aQ + kTileBytes;
+          mbar_wait(q_full + s, (uint32_t)((it >> 1) & 1));
+          mbar_wait(tmem_free, (uint32_t)((it & 1) ^ 1));        // S^T / dP^T / dQ of the previous tile were read
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) {                    // K-major operands: +32 B per 16 k
+            tc_mma(tmem_base + kColS, umma_desc<0>(aK + 32 * k), umma_desc<0>(aQ + 32 * k), id_kk, k ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) {
+            tc_mma(tmem_base + kColDP, umma_desc<0>(aV + 32 * k), umma_desc<0>(aDO + 32 * k), id_kk, k ? 1u : 0u);
+          }
+          tc_commit(s_ready);
+          mbar_wait(p_ready, (uint32_t)(it & 1));
+          tc_fence_after();
+          // contraction over the 128 queries of the tile: A k-block kb (64 q) at +16 KB, +32 B per 16 q inside it;
+          // B (dO_i / Q_i read MN-major): +16 rows of 128 B per 16 q
+#pragma unroll
+          for (int k = 0; k < TQ / 16; ++k) {
+            const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
+            tc_mma(tmem_base + kColDV, umma_desc<0>(aPT + ao), umma_desc<1>(aDO + 2048 * k), id_kn, (i | k) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < TQ / 16; ++k) {
+            const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
+            tc_mma(tmem_base + kColDK, umma_desc<0>(aDST + ao), umma_desc<1>(aQ + 2048 * k), id_kn, (i | k) ? 1u : 0u);
+          }
+          // dQ_i = dS K_h: A = the dS^T tile read MN-major (M = 128 q = two 64-q chunks 16 KB apart, 16 key rows of
+          // 128 B per step), B = K_h read MN-major
+#pragma unroll
+          for (int k = 0; k < TKH / 16; ++k) {
+            tc_mma(tmem_base + kColDQ, umma_desc_lbo<1>(aDST + 2048 * k, kTileBytes), umma_desc<1>(aK + 2048 * k), id_nn,
+                   k ? 1u : 0u);
+          }
+          tc_commit(dq_ready);
+          tc_commit(q_empty + s);
+        }
+        tc_commit(kv_done);
+        tc_commit(kv_empty);
+      }
+    }
+  } else {
+    // ===== elementwise + epilogue warps =====
+    const int ew = warp - 2;
+    const int lg = warp & 3;               // TMEM lane group
+    const int hf = ew >> 2;                // which 64 query columns of S^T / dP^T, which 32 columns of dQ / dK / dV
+    const int etid = ew * 32 + lane;       // 0..255
+    const int row = lg * 32 + lane;        // key row (S^T, dK, dV) or query row (dQ) of the tile
+    const float sc2 = g.scale * kLog2e;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    int it = 0;
+    for (int h = 0; h < nh; ++h) {
+      const int key = h * TKH + row;
+      const bool keep = key < g.Tk && (g.mask == nullptr || g.mask[(size_t)b * g.Tk + key] != 0);
+      for (int i = 0; i < nq; ++i, ++it) {
+        const int s = it & 1;
+        const int q0 = i * TQ;
+        float* stat = sStat + s * 2 * TQ;
+        const unsigned char* st = sStage + (size_t)s * kStageBytes;
+        // (a) lse2 of the tile's 128 queries -> shared memory (one value per thread of the first four warps)
+        if (etid < TQ) stat[etid] = (q0 + etid < g.T) ? g.lse2[((size_t)b * g.H + head) * g.T + q0 + etid] : 0.f;
+        // (b) delta = rowsum(dO o O) from the staged tiles: two threads per query row, 32 columns each
+        mbar_wait_warp(q_full + s, (uint32_t)((it >> 1) & 1), lane);
+        {
+          const int r = etid >> 1, part = etid & 1;
+          const unsigned char* rdo = st + kTileBytes + r * 128;
+          const unsigned char* ro = st + 2 * kTileBytes + r * 128;
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = ((part * 4 + c) ^ (r & 7)) << 4;        // swizzle-128B: 16-byte chunk index ^ (row & 7)
+            float a[8], o8[8];
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(rdo + chunk), a);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(ro + chunk), o8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(a[j], o8[j], acc);
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (part == 0) stat[TQ + r] = acc;
+        }
+        epi_sync();
+        // (c) P^T and dS^T of this thread's key row, 64 query columns, straight into the operand tiles
+        mbar_wait_warp(s_ready, (uint32_t)(it & 1), lane);
+        tc_fence_after();
+        unsigned char* prow = sPT + (size_t)hf * kTileBytes + row * 128;
+        unsigned char* drow = sDST + (size_t)hf * kTileBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32_nowait(lane_addr + kColS + hf * 64 + c, sv);
+          tmem_ld32_nowait(lane_addr + kColDP + hf * 64 + c, dv);
+          tmem_wait_ld_tied(sv);
+          reg_tie32(dv);
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float p[8], d[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; j4 += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(stat + hf * 64 + c + j8 + j4);
+              const float4 e4 = *reinterpret_cast<const float4*>(stat + TQ + hf * 64 + c + j8 + j4);
+              const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float pj = keep ? ex2f(fmaf(__uint_as_float(sv[j8 + j4 + j]), sc2, -lv[j])) : 0.f;
+                p[j4 + j] = pj;
+                d[j4 + j] = g.scale * pj * (__uint_as_float(dv[j8 + j4 + j]) - ev[j]);
+              }
+            }
+            const int chunk = ((((c + j8) >> 3)) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + chunk) =
+                make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+            *reinterpret_cast<uint4*>(drow + chunk) =
+                make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+          }
+        }
+        fence_proxy_async();               // the generic-proxy stores above are read by the tensor core (async proxy)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_release(p_ready);
+        // (d) dQ of this tile for this half of the keys: query row `row`, 32 of the 64 head columns
+        mbar_wait_warp(dq_ready, (uint32_t)(it & 1), lane);
+        tc_fence_after();
+        {
+          uint32_t qv[32];
+          tmem_ld32(lane_addr + kColDQ + hf * 32, qv);
+          const int qrow = q0 + row;
+          if (qrow < g.T) {
+            __nv_bfloat16* dst = g.dq + ((size_t)b * g.T + qrow) * g.E + head * DH + hf * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float v[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[j + q]);
+              if (h > 0) {
+                float old[8];
+                unpack_bf16x8(*reinterpret_cast<const uint4*>(dst + j), old);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] += old[q];
+              }
+              *reinterpret_cast<uint4*>(dst + j) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_free);
+      }
+      // dK_h, dV_h of this thread's key row
+      mbar_wait_warp(kv_done, (uint32_t)(h & 1), lane);
+      tc_fence_after();
+      {
+        uint32_t kv[32], vv[32];
+        tmem_ld32_nowait(lane_addr + kColDK + hf * 32, kv);
+        tmem_ld32_nowait(lane_addr + kColDV + hf * 32, vv);
+        tmem_wait_ld_tied(kv);
+        reg_tie32(vv);
+        if (key < g.Tk) {
+          __nv_bfloat16* dk = g.dkv + ((size_t)b * g.Tk + key) * (2 * g.E) + head * DH + hf * 32;
+          __nv_bfloat16* dvp = dk + g.E;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            *reinterpret_cast<uint4*>(dk + j) = make_uint4(
+                pack_bf16(__uint_as_float(kv[j]), __uint_as_float(kv[j + 1])),
+                pack_bf16(__uint_as_float(kv[j + 2]), __uint_as_float(kv[j + 3])),
+                pack_bf16(__uint_as_float(kv[j + 4]), __uint_as_float(kv[j + 5])),
+                pack_bf16(__uint_as_float(kv[j + 6]), __uint_as_float(kv[j + 7])));
+            *reinterpret_cast<uint4*>(dvp + j) = make_uint4(
+                pack_bf16(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])),
+                pack_bf16(__uint_as_float(vv[j + 2]), __uint_as_float(vv[j + 3])),
+                pack_bf16(__uint_as_float(vv[j + 4]), __uint_as_float(vv[j + 5])),
+                pack_bf16(__uint_as_float(vv[j + 6]), __uint_as_float(vv[j + 7])));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace g100
+}  // namespace mtts
+
+extern "C" int mtts_attn_core_bwd(const mtts_attn_core_bwd_params* p, mtts_stream_t stream) {
+  using namespace mtts::g100;
+  if (!p || !p->q || !p->kv || !p->o || !p->d_o || !p->lse2 || !p->dq || !p->dkv) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->heads < 1 || p->t_q < 0 || p->t_kv < 1 || p->t_kv > 256 || p->d_model != p->heads * attn::DH)
+    return MTTS_ERR_SHAPE;
+  if (!(p->scale > 0.f)) return MTTS_ERR_UNSUPPORTED;
+  if (p->batch == 0 || p->t_q == 0) return MTTS_OK;
+  if (!mtts::aligned16(p->q) || !mtts::aligned16(p->kv) || !mtts::aligned16(p->o) || !mtts::aligned16(p->d_o) ||
+      !mtts::aligned16(p->dq) || !mtts::aligned16(p->dkv))
+    return MTTS_ERR_ALIGN;
+  const int64_t B = p->batch, H = p->heads, T = p->t_q, Tk = p->t_kv, E = p->d_model;
+  CUtensorMap mq, mdo, mo, mk, mv;
+  // (d0 = head columns, d1 = rows, inner batch = heads, outer batch = batch); boxes of 64 columns x 128 rows
+  const bool ok =
+      make_map(&mq, p->q, attn::DH, T, E, H, attn::DH, B, T * E, 64, 128) &&
+      make_map(&mdo, p->d_o, attn::DH, T, E, H, attn::DH, B, T * E, 64, 128) &&
+      make_map(&mo, p->o, attn::DH, T, E, H, attn::DH, B, T * E, 64, 128) &&
+      make_map(&mk, p->kv, attn::DH, Tk, 2 * E, H, attn::DH, B, Tk * 2 * E, 64, 128) &&
+      make_map(&mv, reinterpret_cast<const unsigned char*>(p->kv) + 2 * E, attn::DH, Tk, 2 * E, H, attn::DH, B,
+               Tk * 2 * E, 64, 128);
+  if (!ok) return MTTS_ERR_UNSUPPORTED;
+  attn::Args a{};
+  a.B = (int)B; a.H = (int)H; a.T = (int)T; a.Tk = (int)Tk; a.E = (int)E;
+  a.lse2 = p->lse2;
+  a.mask = p->mask;
+  a.dq = reinterpret_cast<__nv_bfloat16*>(p->dq);
+  a.dkv = reinterpret_cast<__nv_bfloat16*>(p->dkv);
+  a.scale = p->scale;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)attn::kSmemBytes);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    configured = true;
+  }
+  attn_bwd_kernel<<<(unsigned)(B * H), attn::kThreads, attn::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      mq, mdo, mo, mk, mv, a);
+  return mtts::launch_status();
+}

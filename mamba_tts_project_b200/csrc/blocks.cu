@@ -101,8 +101,9 @@ extern "C" int mtts_film_ffn_bwd(const mtts_film_ffn_params* p, mtts_stream_t st
   return MTTS_OK;
 }
 
-static int check_attn(const mtts_cross_attn_params* p) {
-  if (!p || !p->query || !p->memory || !p->w_in || !p->b_in || !p->w_out || !p->q || !p->kv || !p->p || !p->o)
+static int check_attn(const mtts_cross_attn_params* p, bool need_p) {
+  if (!p || !p->query || !p->memory || !p->w_in || !p->b_in || !p->w_out || !p->q || !p->kv || (need_p && !p->p) ||
+      !p->o)
     return MTTS_ERR_NULL;
   if (p->batch < 0 || p->t_q < 0 || p->t_kv < 1 || p->t_kv > 256 || p->heads < 1 || p->d_model < 8 ||
       p->d_model % p->heads || (p->d_model / p->heads) % 8)
@@ -111,7 +112,7 @@ static int check_attn(const mtts_cross_attn_params* p) {
 }
 
 extern "C" int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_t stream) {
-  MTTS_TRY(check_attn(p));
+  MTTS_TRY(check_attn(p, true));
   if (!p->out) return MTTS_ERR_NULL;
   if (p->batch == 0 || p->t_q == 0) return MTTS_OK;
   const int B = p->batch, T = p->t_q, Tk = p->t_kv, E = p->d_model, H = p->heads, dh = E / H;
@@ -133,6 +134,7 @@ extern "C" int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_
       .C(p->p, Tkp, (long long)H * T * Tkp, (long long)T * Tkp);
   gs.epilogue = MTTS_EPI_SOFTMAX; gs.mask = p->mask; gs.mask_bo_stride = Tk;
   gs.scale = 1.f / std::sqrt((float)dh);
+  gs.row_stat = p->lse2;
   MTTS_TRY(mtts_gemm(&gs, stream));
   // o[b, :, h] = P[b, h] v_h: v read as B[n = dh, k = key] with n contiguous
   G go(T, dh, Tk);
@@ -147,8 +149,10 @@ extern "C" int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_
 }
 
 extern "C" int mtts_cross_attn_bwd(const mtts_cross_attn_params* p, mtts_stream_t stream) {
-  MTTS_TRY(check_attn(p));
-  if (!p->dout || !p->d_o || !p->ds || !p->dq || !p->dkv || !p->dw_in || !p->db_in || !p->dw_out) return MTTS_ERR_NULL;
+  MTTS_TRY(check_attn(p, !(p && p->lse2 != nullptr && p->d_model == p->heads * 64)));
+  const bool fused = p->lse2 != nullptr && p->d_model == p->heads * 64;
+  if (!p->dout || !p->d_o || (!fused && !p->ds) || !p->dq || !p->dkv || !p->dw_in || !p->db_in || !p->dw_out)
+    return MTTS_ERR_NULL;
   if (p->batch == 0 || p->t_q == 0) return MTTS_OK;
   const int B = p->batch, T = p->t_q, Tk = p->t_kv, E = p->d_model, H = p->heads, dh = E / H;
   const int Tkp = (Tk + 7) / 8 * 8;
@@ -160,23 +164,34 @@ extern "C" int mtts_cross_attn_bwd(const mtts_cross_attn_params* p, mtts_stream_
   G g2(E, E, B * T);
   g2.A(p->dout, 1, E).B(p->o, 1, E).C(p->dw_out, E).f32_splitk();
   MTTS_TRY(mtts_gemm(&g2, stream));
-  // dV[b, h] (Tk, dh) = P^T dO
-  G gv(Tk, dh, T);
-  gv.batches(B, H).A(p->p, 1, Tkp, sp, sph).B(p->d_o, 1, E, sq, dh).C(at(p->dkv, E), 2 * E, skv, dh);
-  MTTS_TRY(mtts_gemm(&gv, stream));
-  // dS = scale P o (dP - rowsum(P o dP)),  dP = dO V^T
-  G gs(T, Tk, dh);
-  gs.batches(B, H).A(p->d_o, 0, E, sq, dh).B(at(p->kv, E), 0, 2 * E, skv, dh).C(p->ds, Tkp, sp, sph);
-  gs.epilogue = MTTS_EPI_DSOFTMAX; gs.aux = p->p; gs.ld_aux = Tkp; gs.aux_bo_stride = sp; gs.aux_bi_stride = sph;
-  gs.scale = 1.f / std::sqrt((float)dh);
-  MTTS_TRY(mtts_gemm(&gs, stream));
-  // dQ = dS K;  dK = dS^T Q
-  G gq(T, dh, Tk);
-  gq.batches(B, H).A(p->ds, 0, Tkp, sp, sph).B(p->kv, 1, 2 * E, skv, dh).C(p->dq, E, sq, dh);
-  MTTS_TRY(mtts_gemm(&gq, stream));
-  G gk(Tk, dh, T);
-  gk.batches(B, H).A(p->ds, 1, Tkp, sp, sph).B(p->q, 1, E, sq, dh).C(p->dkv, 2 * E, skv, dh);
-  MTTS_TRY(mtts_gemm(&gk, stream));
+  if (fused) {
+    // dV, dS, dQ, dK in one launch: P, dP and dS stay in tensor / shared memory (attn_sm100.cu)
+    mtts_attn_core_bwd_params c;
+    std::memset(&c, 0, sizeof(c));
+    c.batch = B; c.heads = H; c.t_q = T; c.t_kv = Tk; c.d_model = E;
+    c.scale = 1.f / std::sqrt((float)dh);
+    c.q = p->q; c.kv = p->kv; c.o = p->o; c.d_o = p->d_o; c.lse2 = p->lse2; c.mask = p->mask;
+    c.dq = p->dq; c.dkv = p->dkv;
+    MTTS_TRY(mtts_attn_core_bwd(&c, stream));
+  } else {
+    // dV[b, h] (Tk, dh) = P^T dO
+    G gv(Tk, dh, T);
+    gv.batches(B, H).A(p->p, 1, Tkp, sp, sph).B(p->d_o, 1, E, sq, dh).C(at(p->dkv, E), 2 * E, skv, dh);
+    MTTS_TRY(mtts_gemm(&gv, stream));
+    // dS = scale P o (dP - rowsum(P o dP)),  dP = dO V^T
+    G gs(T, Tk, dh);
+    gs.batches(B, H).A(p->d_o, 0, E, sq, dh).B(at(p->kv, E), 0, 2 * E, skv, dh).C(p->ds, Tkp, sp, sph);
+    gs.epilogue = MTTS_EPI_DSOFTMAX; gs.aux = p->p; gs.ld_aux = Tkp; gs.aux_bo_stride = sp; gs.aux_bi_stride = sph;
+    gs.scale = 1.f / std::sqrt((float)dh);
+    MTTS_TRY(mtts_gemm(&gs, stream));
+    // dQ = dS K;  dK = dS^T Q
+    G gq(T, dh, Tk);
+    gq.batches(B, H).A(p->ds, 0, Tkp, sp, sph).B(p->kv, 1, 2 * E, skv, dh).C(p->dq, E, sq, dh);
+    MTTS_TRY(mtts_gemm(&gq, stream));
+    G gk(Tk, dh, T);
+    gk.batches(B, H).A(p->ds, 1, Tkp, sp, sph).B(p->q, 1, E, sq, dh).C(p->dkv, 2 * E, skv, dh);
+    MTTS_TRY(mtts_gemm(&gk, stream));
+  }
   // packed projection gradients
   G gwq(E, E, B * T);
   gwq.A(p->dq, 1, E).B(p->query, 1, E).C(p->dw_in, E).f32_splitk();

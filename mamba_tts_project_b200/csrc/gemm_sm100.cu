@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mtts {
 namespace g100 {
@@ -74,193 +75,8 @@ struct Args {
   const unsigned char* mask;
   long long mask_bo;
   float scale;
+  float* row_stat;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-// Arrivals that hand an accumulator back to the MMA thread are RELAXED: what they order is the epilogue's
-// tcgen05.ld traffic, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already cover.  A release
-// arrive (the default; at cluster scope an ERRBAR / MEMBAR) would also wait for the epilogue's global stores to
-// drain, i.e. serialise every tile's store latency with the next tile's main loop.
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// try_wait parks the thread in hardware until the phase completes or `hint_ns` have passed
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 2000) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-// A protocol error must end in an error code, never in a hung GPU: ~4 s of waiting traps the kernel.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
-  }
-}
-// A whole warp waits: one lane polls (32 lanes hammering the barrier unit slow the TMA / MMA threads' own
-// barrier traffic down), the rest park on the warp barrier.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3)
-      : "memory");
-}
-// cluster (CTA pair) helpers
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory offset in the CTA of rank `rank`
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// CTA-pair TMA load: data into THIS CTA's shared memory, bytes signalled on the (leader CTA's) barrier `bar_cluster`
-__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0,
-                                                 int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"((unsigned short)3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (row), r[j] = column j
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// the same without the wait: several loads can be in flight before one tmem_wait_ld()
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-// The wait that makes the registers of earlier tmem_ld32_nowait() calls valid.  The registers are tied to the
-// statement ("+r") so that the compiler cannot schedule a use of them above it; reg_tie32 ties a further block of
-// 32 registers to the same point (volatile asm statements keep their order) without emitting anything.
-__device__ __forceinline__ void tmem_wait_ld_tied(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]) : : "memory");
-}
-__device__ __forceinline__ void reg_tie32(uint32_t* r) {
-  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
-}
-
-// the reverse: registers -> 32 lanes x 32 columns of TMEM (row-wise epilogues park intermediate rows there)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp layout), swizzle-128B, version 1:
-//   K-major  operand tile [rows][64 k]:      8-row groups 1024 B apart (SBO); LBO unused
-//   MN-major operand tile [chunk][64 k][64 mn]: 8-k-row groups 1024 B apart (SBO), 64-element mn chunks
-//            8192 B apart (LBO) -- one TMA box {64 mn, 64 k} per chunk
-template <int MAJ>
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(MAJ == 0 ? 1 : (8192 >> 4)) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// kind::f16: D fp32 (bit 4), A / B bf16 (bits 7, 10), a_major bit 15, b_major bit 16, N >> 3 at [17,23), M >> 4 at [24,29)
-template <int MM, int BN, int AMAJ, int BMAJ>
-__host__ __device__ constexpr uint32_t instr_desc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)AMAJ << 15) | ((uint32_t)BMAJ << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
-}
 
 // ---- epilogue math ----------------------------------------------------------------------------------------
 // GELU on the bf16 tensor-core path.  The epilogue has one MUFU slot per element before it, not the main loop,
@@ -294,19 +110,6 @@ __device__ __forceinline__ void gelu_both_tc(float x, float& y, float& dy) {
   const float h = fmaf(0.5f, t, 0.5f);
   y = x * h;
   dy = fmaf(0.5f * x * fmaf(3.f * kGeluC1, x2, kGeluC0), fmaf(-t, t, 1.f), h);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float* o) {
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    o[2 * i] = __uint_as_float(w[i] << 16);
-    o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
 }
 
 // Store 32 consecutive columns v[0..32) of one row starting at column `col` (multiple of 32) of a row of n
@@ -964,6 +767,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
         for (int q = 0; q < kEpiParts; ++q) sum += other_slot(q)[2 * lane + 1];
         const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        if (g.row_stat != nullptr && part == 0 && row_ok)      // base-2 log-sum-exp of the row (fused backward)
+          g.row_stat[(size_t)bb * g.m + row] = sum > 0.f ? base + lg2f(sum) : INFINITY;
         group_sync<kEpiParts>(lg);    // every warp has read the slots: the staging tiles are free for the stores
         if (!p_skip) {
           if (p_vec && CW % 64 == 0) {
@@ -1085,41 +890,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-// bf16 operand as a 4-D tensor (d0 contiguous, d1 with stride ld, inner batch, outer batch); a batch stride of 0
-// (operand shared by the batch) becomes an extent of 1 that is always addressed with coordinate 0.
-static bool make_map(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t ld, int64_t n_bi,
-                     int64_t s_bi, int64_t n_bo, int64_t s_bo, int box0, int box1) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  const uint64_t natural = (uint64_t)ld * (uint64_t)d1 * 2;
-  if (s_bi == 0) n_bi = 1;
-  if (s_bo == 0) n_bo = 1;
-  const cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)n_bi, (cuuint64_t)n_bo};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, s_bi ? (cuuint64_t)s_bi * 2 : natural,
-                                 s_bo ? (cuuint64_t)s_bo * 2 : natural * (n_bi > 1 ? (uint64_t)n_bi : 1)};
-  const cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int BN, int AMAJ, int BMAJ, int EPI, int CG>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Args& a, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, AMAJ, BMAJ, EPI, CG>;
@@ -1237,6 +1007,7 @@ extern "C" int mtts_gemm(const mtts_gemm_params* p, mtts_stream_t stream) {
   a.mask = p->mask;
   a.mask_bo = p->mask_bo_stride;
   a.scale = p->scale;
+  a.row_stat = p->row_stat;
   a.debug = p->flags >> 8;
   a.aux_gelu_grad = (p->flags & MTTS_GEMM_AUX_GELU_GRAD) != 0;
   const int ov = a.out_f32 ? 4 : 8;   // elements per 16-byte vector of the output

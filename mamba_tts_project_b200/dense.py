@@ -17,6 +17,7 @@ fp32 (the 1e-4 parity / debug precision) stays on the library GEMMs: the tensor-
 from __future__ import annotations
 
 import math
+import os
 import weakref
 
 import torch
@@ -157,11 +158,16 @@ def ffn(h, w1, b1, w2):
     return _FfnTC.apply(h, w1, b1, w2)
 
 
+FUSED_ATTENTION_BACKWARD = os.environ.get("MTTS_ATTN_FUSED_BWD", "1") != "0"     # A/B switch (measurements)
+
+
 class _CrossAttentionTC(torch.autograd.Function):
     """``nn.MultiheadAttention(batch_first=True)`` forward without its out-projection bias
     (``mamba_decoder.py:72-77``; packed ``in_proj_weight`` (3E, E) = [Wq; Wk; Wv]), T_kv <= 256, as one library call
     per direction (``mtts_cross_attn_fwd`` / ``_bwd``).  q is scaled in the softmax epilogue (fp32), which for
-    power-of-two head sizes is bit-identical to torch's scaling of q before QK^T."""
+    power-of-two head sizes is bit-identical to torch's scaling of q before QK^T.  With 64-wide heads the forward
+    keeps only the per-row log-sum-exp (not the (B, H, T, T_kv) probabilities) and the backward recomputes P inside
+    ``mtts_attn_core_bwd`` (scores, probabilities and their gradients never leave the SM)."""
 
     @staticmethod
     def forward(ctx, query, memory, w_in, b_in, w_out, mask, heads):
@@ -173,29 +179,35 @@ class _CrossAttentionTC(torch.autograd.Function):
         wb, wob = bf16_weight(w_in), bf16_weight(w_out)
         b32 = _f32(b_in)
         tkp = Tk + (-Tk) % 8
+        fused = FUSED_ATTENTION_BACKWARD and E == heads * 64
         q = torch.empty((B, T, E), dtype=bf, device=dev)
         kv = torch.empty((B, Tk, 2 * E), dtype=bf, device=dev)
         P = torch.empty((B, heads, T, tkp), dtype=bf, device=dev)
         o = torch.empty((B, T, E), dtype=bf, device=dev)
         out = torch.empty((B, T, E), dtype=bf, device=dev)
+        lse2 = torch.empty((B, heads, T), dtype=torch.float32, device=dev) if fused else None
         _lib.require_cuda(q_in, m_in, wb, wob, b32, mask)
         p = _lib.CrossAttnParams(batch=B, t_q=T, t_kv=Tk, d_model=E, heads=heads, query=ptr(q_in), memory=ptr(m_in),
                                  w_in=ptr(wb), b_in=ptr(b32), w_out=ptr(wob), mask=ptr(mask), q=ptr(q), kv=ptr(kv),
-                                 p=ptr(P), o=ptr(o), out=ptr(out))
+                                 p=ptr(P), o=ptr(o), out=ptr(out), lse2=ptr(lse2))
         _lib.call("mtts_cross_attn_fwd", p, launches=5)
-        ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, P, o, mask)
-        ctx.meta = (query.dtype, memory.dtype, b_in.dtype, heads)
+        if fused:
+            ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, lse2, o, mask)     # P dies here
+        else:
+            ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, P, o, mask)
+        ctx.meta = (query.dtype, memory.dtype, b_in.dtype, heads, fused)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q_in, m_in, wb, wob, q, kv, P, o, mask = ctx.saved_tensors
-        t_q, t_m, t_b, H = ctx.meta
+        q_in, m_in, wb, wob, q, kv, P_or_lse, o, mask = ctx.saved_tensors
+        t_q, t_m, t_b, H, fused = ctx.meta
         B, T, E = q.shape
         Tk = kv.shape[1]
         bf, f32, dev = torch.bfloat16, torch.float32, q.device
         d2 = _rows(dout if dout.dtype == bf else dout.to(bf))
-        d_o, dS, dq, dkv = torch.empty_like(o), torch.empty_like(P), torch.empty_like(q), torch.empty_like(kv)
+        d_o, dq, dkv = torch.empty_like(o), torch.empty_like(q), torch.empty_like(kv)
+        dS = None if fused else torch.empty_like(P_or_lse)
         dw_in = torch.empty((3 * E, E), dtype=f32, device=dev)
         dw_out = torch.empty((E, E), dtype=f32, device=dev)
         db_in = torch.zeros(3 * E, dtype=f32, device=dev)
@@ -204,10 +216,11 @@ class _CrossAttentionTC(torch.autograd.Function):
         dmem = torch.empty((B, Tk, E), dtype=bf, device=dev) if need_m else None
         p = _lib.CrossAttnParams(batch=B, t_q=T, t_kv=Tk, d_model=E, heads=H, query=ptr(q_in), memory=ptr(m_in),
                                  w_in=ptr(wb), b_in=ptr(db_in), w_out=ptr(wob), mask=ptr(mask), q=ptr(q), kv=ptr(kv),
-                                 p=ptr(P), o=ptr(o), dout=ptr(d2), d_o=ptr(d_o), ds=ptr(dS), dq=ptr(dq), dkv=ptr(dkv),
+                                 p=None if fused else ptr(P_or_lse), o=ptr(o), lse2=ptr(P_or_lse) if fused else None,
+                                 dout=ptr(d2), d_o=ptr(d_o), ds=ptr(dS), dq=ptr(dq), dkv=ptr(dkv),
                                  dw_in=ptr(dw_in), db_in=ptr(db_in), dw_out=ptr(dw_out), dquery=ptr(dquery),
                                  dmemory=ptr(dmem))
-        _lib.call("mtts_cross_attn_bwd", p, launches=10 + int(need_q) + int(need_m))
+        _lib.call("mtts_cross_attn_bwd", p, launches=(7 if fused else 10) + int(need_q) + int(need_m))
         return (None if dquery is None else dquery.to(t_q), None if dmem is None else dmem.to(t_m), dw_in,
                 db_in.to(t_b), dw_out, None, None)
 

@@ -197,7 +197,10 @@ def _ref_attention(query, memory, w_in, b_in, w_out, mask, H):
 
 
 @pytest.mark.parametrize("B,T,Tk,E,H,masked", [(2, 300, 72, 128, 4, True), (3, 128, 256, 256, 4, False),
-                                                (1, 40, 13, 64, 8, True)])
+                                                (1, 40, 13, 64, 8, True),
+                                                # 64-wide heads: the backward core is the fused mtts_attn_core_bwd
+                                                (2, 300, 72, 128, 2, True), (1, 40, 13, 64, 1, True),
+                                                (2, 512, 200, 512, 8, True), (1, 1000, 129, 128, 2, False)])
 def test_cross_attn_entry_points_forward_and_all_gradients(B, T, Tk, E, H, masked):
     """mtts_cross_attn_fwd / _bwd (one C-ABI call per direction) against fp32 nn.MultiheadAttention arithmetic."""
     from mamba_tts_project_b200 import dense
