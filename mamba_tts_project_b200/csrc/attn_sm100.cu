@@ -29,7 +29,10 @@ namespace attn {
 constexpr int DH = 64;            // head dimension
 constexpr int TQ = 128;           // query tile
 constexpr int TKH = 128;          // keys per half
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;     // 4 per TMEM lane group: each thread owns 32 query columns of S^T / dP^T (16 of dQ / dK / dV)
+constexpr int kParts = kEpiWarps / 4;
+constexpr int kSC = TQ / kParts;  // S^T / dP^T columns per thread
+constexpr int kOC = DH / kParts;  // dQ / dK / dV columns per thread
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kTileBytes = 128 * 128;                 // a 128-row x 64-element bf16 operand tile
 constexpr uint32_t kStageBytes = 3 * kTileBytes;           // Q_i, dO_i, O_i
@@ -53,7 +56,27 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void epi_sync() {   // the epilogue warps
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * attn::kEpiWarps) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns, no wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld_tied16(uint32_t* a, uint32_t* b) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                 "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
 
 __global__ void __launch_bounds__(attn::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
@@ -77,7 +100,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* s_ready = bars + 6;
   uint64_t* p_ready = bars + 7;
   uint64_t* dq_ready = bars + 8;
-  uint64_t* tmem_free = bars + 9;
+  uint64_t* sdp_free = bars + 9;    // the warps have read S^T / dP^T of the tile (they may be overwritten)
+  uint64_t* dq_free = bars + 12;    // ... and its dQ
   uint64_t* kv_done = bars + 10;
   uint64_t* acc_free = bars + 11;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -105,7 +129,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(s_ready, 1);
       mbar_init(p_ready, kEpiWarps);
       mbar_init(dq_ready, 1);
-      mbar_init(tmem_free, kEpiWarps);
+      mbar_init(sdp_free, kEpiWarps);
+      mbar_init(dq_free, kEpiWarps);
       mbar_init(kv_done, 1);
       mbar_init(acc_free, kEpiWarps);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,61 +173,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       constexpr uint32_t id_kn = instr_desc<128, 64, 0, 1>();    // dV, dK: A K-major (P^T / dS^T), B MN-major, N = 64
       constexpr uint32_t id_nn = instr_desc<128, 64, 1, 1>();    // dQ: A MN-major (dS), B MN-major (K_h)
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), aDST = smem_u32(sDST);
-      int it = 0;
-      for (int h = 0; h < nh; ++h) {
-        mbar_wait(kv_full, (uint32_t)(h & 1));
-        mbar_wait(acc_free, (uint32_t)((h & 1) ^ 1));            // the epilogue has read the previous half's dK / dV
-        for (int i = 0; i < nq; ++i, ++it) {
-          const int s = it & 1;
-          const uint32_t aQ = smem_u32(sStage + (size_t)s * kStageBytes), aDO = aQ + kTileBytes;
-          mbar_wait(q_full + s, (uint32_t)((it >> 1) & 1));
-          mbar_wait(tmem_free, (uint32_t)((it & 1) ^ 1));        // S^T / dP^T / dQ of the previous tile were read
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {                    // K-major operands: +32 B per 16 k
-            tc_mma(tmem_base + kColS, umma_desc<0>(aK + 32 * k), umma_desc<0>(aQ + 32 * k), id_kk, k ? 1u : 0u);
-          }
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            tc_mma(tmem_base + kColDP, umma_desc<0>(aV + 32 * k), umma_desc<0>(aDO + 32 * k), id_kk, k ? 1u : 0u);
-          }
-          tc_commit(s_ready);
-          mbar_wait(p_ready, (uint32_t)(it & 1));
-          tc_fence_after();
-          // contraction over the 128 queries of the tile: A k-block kb (64 q) at +16 KB, +32 B per 16 q inside it;
-          // B (dO_i / Q_i read MN-major): +16 rows of 128 B per 16 q
-#pragma unroll
-          for (int k = 0; k < TQ / 16; ++k) {
-            const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
-            tc_mma(tmem_base + kColDV, umma_desc<0>(aPT + ao), umma_desc<1>(aDO + 2048 * k), id_kn, (i | k) ? 1u : 0u);
-          }
-#pragma unroll
-          for (int k = 0; k < TQ / 16; ++k) {
-            const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
-            tc_mma(tmem_base + kColDK, umma_desc<0>(aDST + ao), umma_desc<1>(aQ + 2048 * k), id_kn, (i | k) ? 1u : 0u);
-          }
-          // dQ_i = dS K_h: A = the dS^T tile read MN-major (M = 128 q = two 64-q chunks 16 KB apart, 16 key rows of
-          // 128 B per step), B = K_h read MN-major
-#pragma unroll
-          for (int k = 0; k < TKH / 16; ++k) {
-            tc_mma(tmem_base + kColDQ, umma_desc_lbo<1>(aDST + 2048 * k, kTileBytes), umma_desc<1>(aK + 2048 * k), id_nn,
-                   k ? 1u : 0u);
-          }
-          tc_commit(dq_ready);
-          tc_commit(q_empty + s);
+      // Software pipelined over the (half, tile) iterations: the score MMAs of iteration it + 1 are issued right behind
+      // the gradient MMAs of iteration it, so they run while the warps drain dQ(it) -- the warps never wait for S^T.
+      const int total = nh * nq;
+      auto issue_scores = [&](int it) {                          // S^T = K_h Q_i^T, dP^T = V_h dO_i^T
+        const int s = it & 1;
+        const uint32_t aQ = smem_u32(sStage + (size_t)s * kStageBytes), aDO = aQ + kTileBytes;
+        if (it % nq == 0) {                                      // first tile of a half: its K_h / V_h
+          const int h = it / nq;
+          mbar_wait(kv_full, (uint32_t)(h & 1));
         }
-        tc_commit(kv_done);
-        tc_commit(kv_empty);
+        mbar_wait(q_full + s, (uint32_t)((it >> 1) & 1));
+        mbar_wait(sdp_free, (uint32_t)((it & 1) ^ 1));           // S^T / dP^T of the previous iteration were read
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)                        // K-major operands: +32 B per 16 k
+          tc_mma(tmem_base + kColS, umma_desc<0>(aK + 32 * k), umma_desc<0>(aQ + 32 * k), id_kk, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          tc_mma(tmem_base + kColDP, umma_desc<0>(aV + 32 * k), umma_desc<0>(aDO + 32 * k), id_kk, k ? 1u : 0u);
+        tc_commit(s_ready);
+      };
+      issue_scores(0);
+      for (int it = 0; it < total; ++it) {
+        const int h = it / nq, i = it - h * nq;
+        const int s = it & 1;
+        const uint32_t aQ = smem_u32(sStage + (size_t)s * kStageBytes), aDO = aQ + kTileBytes;
+        if (i == 0) mbar_wait(acc_free, (uint32_t)((h & 1) ^ 1));   // the warps have read the previous half's dK / dV
+        mbar_wait(p_ready, (uint32_t)(it & 1));
+        mbar_wait(dq_free, (uint32_t)((it & 1) ^ 1));            // dQ of the previous iteration was read
+        tc_fence_after();
+        // contraction over the 128 queries of the tile: A k-block kb (64 q) at +16 KB, +32 B per 16 q inside it;
+        // B (dO_i / Q_i read MN-major): +16 rows of 128 B per 16 q
+#pragma unroll
+        for (int k = 0; k < TQ / 16; ++k) {
+          const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
+          tc_mma(tmem_base + kColDV, umma_desc<0>(aPT + ao), umma_desc<1>(aDO + 2048 * k), id_kn, (i | k) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < TQ / 16; ++k) {
+          const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
+          tc_mma(tmem_base + kColDK, umma_desc<0>(aDST + ao), umma_desc<1>(aQ + 2048 * k), id_kn, (i | k) ? 1u : 0u);
+        }
+        // dQ_i = dS K_h: A = the dS^T tile read MN-major (M = 128 q = two 64-q chunks 16 KB apart, 16 key rows of
+        // 128 B per step), B = K_h read MN-major
+#pragma unroll
+        for (int k = 0; k < TKH / 16; ++k) {
+          tc_mma(tmem_base + kColDQ, umma_desc_lbo<1>(aDST + 2048 * k, kTileBytes), umma_desc<1>(aK + 2048 * k), id_nn,
+                 k ? 1u : 0u);
+        }
+        tc_commit(dq_ready);
+        tc_commit(q_empty + s);
+        if (i == nq - 1) {                                       // last tile of the half
+          tc_commit(kv_done);
+          tc_commit(kv_empty);
+        }
+        if (it + 1 < total) issue_scores(it + 1);
       }
     }
   } else {
     // ===== elementwise + epilogue warps =====
     const int ew = warp - 2;
     const int lg = warp & 3;               // TMEM lane group
-    const int hf = ew >> 2;                // which 64 query columns of S^T / dP^T, which 32 columns of dQ / dK / dV
-    const int etid = ew * 32 + lane;       // 0..255
+    const int part = ew >> 2;              // which kSC query columns of S^T / dP^T, which kOC columns of dQ / dK / dV
+    const int etid = ew * 32 + lane;       // 0 .. 32 kEpiWarps
     const int row = lg * 32 + lane;        // key row (S^T, dK, dV) or query row (dQ) of the tile
-    const float sc2 = g.scale * kLog2e;
+    const float sc2 = g.scale * kLog2e, scale = g.scale;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
     int it = 0;
     for (int h = 0; h < nh; ++h) {
@@ -215,107 +251,122 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const unsigned char* st = sStage + (size_t)s * kStageBytes;
         // (a) lse2 of the tile's 128 queries -> shared memory (one value per thread of the first four warps)
         if (etid < TQ) stat[etid] = (q0 + etid < g.T) ? g.lse2[((size_t)b * g.H + head) * g.T + q0 + etid] : 0.f;
-        // (b) delta = rowsum(dO o O) from the staged tiles: two threads per query row, 32 columns each
+        // (b) delta = rowsum(dO o O) from the staged tiles: kParts threads per query row, 16-byte chunks dealt round robin
         mbar_wait_warp(q_full + s, (uint32_t)((it >> 1) & 1), lane);
         {
-          const int r = etid >> 1, part = etid & 1;
+          constexpr int TPR = 32 * kEpiWarps / TQ;                    // threads per row (4)
+          const int r = etid / TPR, sub = etid % TPR;
           const unsigned char* rdo = st + kTileBytes + r * 128;
           const unsigned char* ro = st + 2 * kTileBytes + r * 128;
           float acc = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int chunk = ((part * 4 + c) ^ (r & 7)) << 4;        // swizzle-128B: 16-byte chunk index ^ (row & 7)
+          for (int c = sub; c < 8; c += TPR) {
+            const int chunk = (c ^ (r & 7)) << 4;                     // swizzle-128B: 16-byte chunk index ^ (row & 7)
             float a[8], o8[8];
             unpack_bf16x8(*reinterpret_cast<const uint4*>(rdo + chunk), a);
             unpack_bf16x8(*reinterpret_cast<const uint4*>(ro + chunk), o8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc = fmaf(a[j], o8[j], acc);
           }
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          if (part == 0) stat[TQ + r] = acc;
+#pragma unroll
+          for (int o = 1; o < TPR; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (sub == 0) stat[TQ + r] = acc;
         }
         epi_sync();
-        // (c) P^T and dS^T of this thread's key row, 64 query columns, straight into the operand tiles
+        // (c) P^T and dS^T of this thread's key row, kSC query columns, straight into the operand tiles
         mbar_wait_warp(s_ready, (uint32_t)(it & 1), lane);
         tc_fence_after();
-        unsigned char* prow = sPT + (size_t)hf * kTileBytes + row * 128;
-        unsigned char* drow = sDST + (size_t)hf * kTileBytes + row * 128;
+        {
+          const int cbase = part * kSC;                               // first query column of this thread
+          unsigned char* prow = sPT + (size_t)(cbase >> 6) * kTileBytes + row * 128;
+          unsigned char* drow = sDST + (size_t)(cbase >> 6) * kTileBytes + row * 128;
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32_nowait(lane_addr + kColS + hf * 64 + c, sv);
-          tmem_ld32_nowait(lane_addr + kColDP + hf * 64 + c, dv);
-          tmem_wait_ld_tied(sv);
-          reg_tie32(dv);
+          for (int c = 0; c < kSC; c += 16) {
+            uint32_t sv[16], dv[16];
+            tmem_ld16_nowait(lane_addr + kColS + cbase + c, sv);
+            tmem_ld16_nowait(lane_addr + kColDP + cbase + c, dv);
+            tmem_wait_ld_tied16(sv, dv);
 #pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            float p[8], d[8];
+            for (int j8 = 0; j8 < 16; j8 += 8) {
+              float p[8], d[8];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; j4 += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(stat + hf * 64 + c + j8 + j4);
-              const float4 e4 = *reinterpret_cast<const float4*>(stat + TQ + hf * 64 + c + j8 + j4);
-              const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+              for (int j4 = 0; j4 < 8; j4 += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(stat + cbase + c + j8 + j4);
+                const float4 e4 = *reinterpret_cast<const float4*>(stat + TQ + cbase + c + j8 + j4);
+                const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float pj = keep ? ex2f(fmaf(__uint_as_float(sv[j8 + j4 + j]), sc2, -lv[j])) : 0.f;
-                p[j4 + j] = pj;
-                d[j4 + j] = g.scale * pj * (__uint_as_float(dv[j8 + j4 + j]) - ev[j]);
+                for (int j = 0; j < 4; ++j) {
+                  const float pj = keep ? ex2f(fmaf(__uint_as_float(sv[j8 + j4 + j]), sc2, -lv[j])) : 0.f;
+                  p[j4 + j] = pj;
+                  d[j4 + j] = scale * pj * (__uint_as_float(dv[j8 + j4 + j]) - ev[j]);
+                }
               }
+              const int chunk = ((((cbase & 63) + c + j8) >> 3) ^ (row & 7)) << 4;
+              *reinterpret_cast<uint4*>(prow + chunk) =
+                  make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+              *reinterpret_cast<uint4*>(drow + chunk) =
+                  make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
             }
-            const int chunk = ((((c + j8) >> 3)) ^ (row & 7)) << 4;
-            *reinterpret_cast<uint4*>(prow + chunk) =
-                make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-            *reinterpret_cast<uint4*>(drow + chunk) =
-                make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
           }
         }
         fence_proxy_async();               // the generic-proxy stores above are read by the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_release(p_ready);
-        // (d) dQ of this tile for this half of the keys: query row `row`, 32 of the 64 head columns
-        mbar_wait_warp(dq_ready, (uint32_t)(it & 1), lane);
-        tc_fence_after();
+        if (lane == 0) {
+          mbar_arrive_release(p_ready);
+          mbar_arrive(sdp_free);
+        }
+        // (d) dQ of this tile for this half of the keys: query row `row`, kOC of the 64 head columns.  The second
+        // half adds onto the first half's result: that is requested before the wait for the tensor core.
         {
-          uint32_t qv[32];
-          tmem_ld32(lane_addr + kColDQ + hf * 32, qv);
           const int qrow = q0 + row;
-          if (qrow < g.T) {
-            __nv_bfloat16* dst = g.dq + ((size_t)b * g.T + qrow) * g.E + head * DH + hf * 32;
+          __nv_bfloat16* dst = g.dq + ((size_t)b * g.T + (qrow < g.T ? qrow : 0)) * g.E + head * DH + part * kOC;
+          uint4 oldv[kOC / 8];
+          if (h > 0 && qrow < g.T) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < kOC / 8; ++j) oldv[j] = *reinterpret_cast<const uint4*>(dst + 8 * j);
+          }
+          mbar_wait_warp(dq_ready, (uint32_t)(it & 1), lane);
+          tc_fence_after();
+          uint32_t qv[16], dummy[16];
+          static_assert(kOC == 16, "dQ / dK / dV: 16 columns per thread");
+          tmem_ld16_nowait(lane_addr + kColDQ + part * kOC, qv);
+          tmem_ld16_nowait(lane_addr + kColDQ + part * kOC, dummy);
+          tmem_wait_ld_tied16(qv, dummy);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+          if (qrow < g.T) {
+#pragma unroll
+            for (int j = 0; j < kOC / 8; ++j) {
               float v[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[j + q]);
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[8 * j + q]);
               if (h > 0) {
                 float old[8];
-                unpack_bf16x8(*reinterpret_cast<const uint4*>(dst + j), old);
+                unpack_bf16x8(oldv[j], old);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] += old[q];
               }
-              *reinterpret_cast<uint4*>(dst + j) =
+              *reinterpret_cast<uint4*>(dst + 8 * j) =
                   make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_free);
       }
       // dK_h, dV_h of this thread's key row
       mbar_wait_warp(kv_done, (uint32_t)(h & 1), lane);
       tc_fence_after();
       {
-        uint32_t kv[32], vv[32];
-        tmem_ld32_nowait(lane_addr + kColDK + hf * 32, kv);
-        tmem_ld32_nowait(lane_addr + kColDV + hf * 32, vv);
-        tmem_wait_ld_tied(kv);
-        reg_tie32(vv);
+        uint32_t kv[16], vv[16];
+        tmem_ld16_nowait(lane_addr + kColDK + part * kOC, kv);
+        tmem_ld16_nowait(lane_addr + kColDV + part * kOC, vv);
+        tmem_wait_ld_tied16(kv, vv);
         if (key < g.Tk) {
-          __nv_bfloat16* dk = g.dkv + ((size_t)b * g.Tk + key) * (2 * g.E) + head * DH + hf * 32;
+          __nv_bfloat16* dk = g.dkv + ((size_t)b * g.Tk + key) * (2 * g.E) + head * DH + part * kOC;
           __nv_bfloat16* dvp = dk + g.E;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < kOC; j += 8) {
             *reinterpret_cast<uint4*>(dk + j) = make_uint4(
                 pack_bf16(__uint_as_float(kv[j]), __uint_as_float(kv[j + 1])),
                 pack_bf16(__uint_as_float(kv[j + 2]), __uint_as_float(kv[j + 3])),
