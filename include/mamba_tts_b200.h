@@ -639,7 +639,8 @@ typedef struct {
   void* o;
   void* out;
   float* lse2; /* (batch, heads, t_q) fp32 or NULL: written by the forward; when given to the backward (and head_dim is
-                  64) the fused mtts_attn_core_bwd replaces the GEMM-by-GEMM core and `p` / `ds` are not touched */
+                  64) the fused mtts_attn_core_bwd replaces the GEMM-by-GEMM core and `p` / `ds` are not touched; a
+                  forward with lse2 and p == NULL (head_dim 64) runs the fused mtts_attn_core_fwd */
   const void* dout;
   void* d_o;
   void* ds;
@@ -675,6 +676,20 @@ typedef struct {
   void* dkv;
 } mtts_attn_core_bwd_params;
 int mtts_attn_core_bwd(const mtts_attn_core_bwd_params* p, mtts_stream_t stream);
+
+/* The forward of the same core in one launch: o = softmax(scale q k^T + mask) v (bf16, (batch, t_q, d_model)) and
+ * lse2 (batch, heads, t_q) fp32, the scores and probabilities kept in tensor / shared memory.  Same shape limits.
+ * Used by mtts_cross_attn_fwd when the caller gives lse2 and no probability buffer. */
+typedef struct {
+  int32_t batch, heads, t_q, t_kv, d_model;
+  float scale;
+  const void* q;
+  const void* kv;
+  const uint8_t* mask;
+  void* o;
+  float* lse2;
+} mtts_attn_core_fwd_params;
+int mtts_attn_core_fwd(const mtts_attn_core_fwd_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FFN / projection glue (mamba_decoder.py:39-43,86-88: Linear -> GELU -> Linear, and the bias gradients

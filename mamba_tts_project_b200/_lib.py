@@ -176,6 +176,9 @@ AddLayerNormFinishParams = _struct("AddLayerNormFinishParams", """
 AttnCoreBwdParams = _struct("AttnCoreBwdParams", """
     i:batch i:heads i:t_q i:t_kv i:d_model f:scale p:q p:kv p:o p:d_o p:lse2 p:mask p:dq p:dkv""")
 
+AttnCoreFwdParams = _struct("AttnCoreFwdParams", """
+    i:batch i:heads i:t_q i:t_kv i:d_model f:scale p:q p:kv p:mask p:o p:lse2""")
+
 # argument of mtts_sizeof_params (declaration order of the header, later additions appended)
 PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdParams,
                  ScanBwdParams, StateUpdateParams, DecodeStepParams, CrossAttnDecodeParams,
@@ -183,7 +186,7 @@ PARAM_STRUCTS = [Conv1dFwdParams, Conv1dBwdParams, Conv1dUpdateParams, ScanFwdPa
                  GemmBf16Params, BiasGeluParams, CrossAttnBlockParams, DecodeEmbedParams, DecodeGreedyParams,
                  LengthRegulateFwdParams, LengthRegulateBwdParams, GemmParams,
                  EmbedSumParams, CeLossParams, AdamParams, AdamTensor, FilmFfnParams, CrossAttnParams,
-                 AddLayerNormFinishParams, AttnCoreBwdParams]
+                 AddLayerNormFinishParams, AttnCoreBwdParams, AttnCoreFwdParams]
 
 # every symbol include/mamba_tts_b200.h declares -> parameter struct (None: not a kernel call)
 ENTRY_POINTS = {
@@ -216,6 +219,7 @@ ENTRY_POINTS = {
     "mtts_cross_attn_fwd": CrossAttnParams,
     "mtts_cross_attn_bwd": CrossAttnParams,
     "mtts_attn_core_bwd": AttnCoreBwdParams,
+    "mtts_attn_core_fwd": AttnCoreFwdParams,
     "mtts_embed_sum_fwd": EmbedSumParams,
     "mtts_embed_sum_bwd": EmbedSumParams,
     "mtts_ce_loss": CeLossParams,

@@ -64,6 +64,7 @@ extern "C" int mtts_sizeof_params(int which) {
     case 24: return (int)sizeof(mtts_cross_attn_params);
     case 25: return (int)sizeof(mtts_add_layernorm_finish_params);
     case 26: return (int)sizeof(mtts_attn_core_bwd_params);
+    case 27: return (int)sizeof(mtts_attn_core_fwd_params);
     default: return -1;
   }
 }

@@ -394,6 +394,253 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward of the same core: o = softmax(scale q k^T + mask) v and the per-row base-2 log-sum-exp, scores and
+// probabilities never leaving the SM.  One CTA per (batch, head): K (K-major B operand of S = Q K^T) and V (the same
+// kind of tile, read MN-major as the B operand of O = P V) are loaded once, the CTA walks the query tiles of 128:
+//   MMA   S = Q_i K^T (128 x 256)                                  -> TMEM columns [0, 256)
+//   warps thread = query row x 64 keys: row max (masked) and, in a second sweep over TMEM, e = exp2(.) -> bf16 into
+//         the K-major operand tile of shared memory (UNnormalised: the row sum divides O at the end); max and sum are
+//         exchanged between the four warps of a TMEM lane group through shared memory
+//   MMA   O = e V (128 x 64, K = 256)                              -> TMEM columns [256, 320)
+//   warps o = O / sum -> global, lse2 = base + log2(sum)
+// The next tile's score MMA is issued right behind this tile's O MMA.
+namespace attnf {
+constexpr int DH = 64, TQ = 128, TK = 256;
+constexpr int kEpiWarps = 16, kParts = 4, kSC = TK / kParts, kOC = DH / kParts;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr uint32_t kTileBytes = 128 * 128;
+// K, V (256 rows each) | 2 Q stages | P (4 k-blocks) | exchange [4 lane groups][4 parts][32][2] | barriers
+constexpr size_t kSmemBytes = 4 * kTileBytes + 2 * kTileBytes + 4 * kTileBytes + 4 * 4 * 32 * 2 * 4 + 16 * 8 + 16;
+constexpr uint32_t kColS = 0, kColO = 256;
+struct Args {
+  int B, H, T, Tk, E;
+  const unsigned char* mask;
+  __nv_bfloat16* o;
+  float* lse2;
+  float scale;
+};
+}  // namespace attnf
+
+__global__ void __launch_bounds__(attnf::kThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const attnf::Args g) {
+  using namespace attnf;
+  extern __shared__ __align__(1024) unsigned char asm_raw[];
+  unsigned char* sm = asm_raw;
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
+  unsigned char* sK = sm;
+  unsigned char* sV = sK + 2 * kTileBytes;
+  unsigned char* sQ = sV + 2 * kTileBytes;                      // [2]
+  unsigned char* sP = sQ + 2 * kTileBytes;                      // [4 k-blocks of 64 keys][128 q rows][128 B]
+  float* sX = reinterpret_cast<float*>(sP + 4 * kTileBytes);    // [lane group][part][lane][max | sum]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 4 * 4 * 32 * 2);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;      // [2]
+  uint64_t* q_empty = bars + 3;     // [2]
+  uint64_t* s_ready = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_ready = bars + 7;
+  uint64_t* o_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / g.H, head = blockIdx.x % g.H;
+  const int nq = (g.T + TQ - 1) / TQ;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(q_full + s, 1);
+        mbar_init(q_empty + s, 1);
+      }
+      mbar_init(s_ready, 1);
+      mbar_init(p_ready, kEpiWarps);
+      mbar_init(o_ready, 1);
+      mbar_init(o_free, kEpiWarps);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 4 * kTileBytes);
+      tma_load_4d(sK, &map_k, kv_full, 0, 0, head, b);
+      tma_load_4d(sV, &map_v, kv_full, 0, 0, head, b);
+      for (int it = 0; it < nq; ++it) {
+        const int s = it & 1;
+        mbar_wait(q_empty + s, (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(q_full + s, kTileBytes);
+        tma_load_4d(sQ + (size_t)s * kTileBytes, &map_q, q_full + s, 0, it * TQ, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = instr_desc<128, 256, 0, 0>();    // S: A = Q K-major, B = K K-major, N = 256
+      constexpr uint32_t id_o = instr_desc<128, 64, 0, 1>();     // O: A = e K-major, B = V MN-major, N = 64
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      auto issue_s = [&](int it) {
+        const int s = it & 1;
+        const uint32_t aQ = smem_u32(sQ + (size_t)s * kTileBytes);
+        mbar_wait(q_full + s, (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          tc_mma(tmem_base + kColS, umma_desc<0>(aQ + 32 * k), umma_desc<0>(aK + 32 * k), id_s, k ? 1u : 0u);
+        tc_commit(s_ready);
+        tc_commit(q_empty + s);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      for (int it = 0; it < nq; ++it) {
+        mbar_wait(p_ready, (uint32_t)(it & 1));                  // e(it) is in shared memory, S(it) was read
+        mbar_wait(o_free, (uint32_t)((it & 1) ^ 1));             // O of the previous tile was read
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          const uint32_t ao = (uint32_t)(k >> 2) * kTileBytes + (uint32_t)(k & 3) * 32;
+          tc_mma(tmem_base + kColO, umma_desc<0>(aP + ao), umma_desc<1>(aV + 2048 * k), id_o, k ? 1u : 0u);
+        }
+        tc_commit(o_ready);
+        if (it + 1 < nq) issue_s(it + 1);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int lg = warp & 3, part = ew >> 2;
+    const int row = lg * 32 + lane;
+    const float sc2 = g.scale * kLog2e;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    // keys of this warp: [64 part, 64 part + 64); bit j of keep[c / 32]: key 64 part + c + j takes part
+    uint32_t keep[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int key = part * kSC + c * 32 + lane;
+      const bool on = key < g.Tk && (g.mask == nullptr || g.mask[(size_t)b * g.Tk + key] != 0);
+      keep[c] = __ballot_sync(0xffffffffu, on);
+    }
+    float* xmine = sX + ((lg * 4 + part) * 32 + lane) * 2;
+    auto xother = [&](int q) { return sX + ((lg * 4 + q) * 32 + lane) * 2; };
+    auto lg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(lg + 1) : "memory"); };
+    unsigned char* prow = sP + (size_t)part * kTileBytes + row * 128;
+    for (int it = 0; it < nq; ++it) {
+      const int q0 = it * TQ;
+      mbar_wait_warp(s_ready, (uint32_t)(it & 1), lane);
+      tc_fence_after();
+      // sweep 1: row maximum over this warp's keys
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kSC; c += 32) {
+        uint32_t a[16], bq[16];
+        tmem_ld16_nowait(lane_addr + kColS + part * kSC + c, a);
+        tmem_ld16_nowait(lane_addr + kColS + part * kSC + c + 16, bq);
+        tmem_wait_ld_tied16(a, bq);
+        const uint32_t kb = keep[c >> 5];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((kb >> j) & 1u) m0 = fmaxf(m0, __uint_as_float(a[j]));
+          if ((kb >> (16 + j)) & 1u) m1 = fmaxf(m1, __uint_as_float(bq[j]));
+        }
+      }
+      float mx = fmaxf(m0, m1);
+      xmine[0] = mx;
+      lg_sync();
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) mx = fmaxf(mx, xother(q)[0]);
+      const float base = mx == -INFINITY ? 0.f : mx * sc2;       // fully masked row: zeros (the reference gives NaN)
+      // sweep 2: e = exp2(scale log2(e) s - base) -> bf16 operand tile, row sum
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSC; c += 32) {
+        uint32_t a[16], bq[16];
+        tmem_ld16_nowait(lane_addr + kColS + part * kSC + c, a);
+        tmem_ld16_nowait(lane_addr + kColS + part * kSC + c + 16, bq);
+        tmem_wait_ld_tied16(a, bq);
+        const uint32_t kb = keep[c >> 5];
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          e[j] = ((kb >> j) & 1u) ? ex2f(fmaf(__uint_as_float(a[j]), sc2, -base)) : 0.f;
+          e[16 + j] = ((kb >> (16 + j)) & 1u) ? ex2f(fmaf(__uint_as_float(bq[j]), sc2, -base)) : 0.f;
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+          // the sum is taken over the ROUNDED values: numerator (tensor core) and denominator agree
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(e[j8 + 2 * q], e[j8 + 2 * q + 1]);
+            w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+            s0 += __low2float(hh);
+            s1 += __high2float(hh);
+          }
+          const int chunk = (((c + j8) >> 3) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + chunk) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_release(p_ready);
+      float sum = s0 + s1;
+      xmine[1] = sum;
+      lg_sync();
+      sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) sum += xother(q)[1];
+      const float inv = sum > 0.f ? 1.f / sum : 0.f;
+      const int qrow = q0 + row;
+      if (part == 0 && qrow < g.T)
+        g.lse2[((size_t)b * g.H + head) * g.T + qrow] = sum > 0.f ? base + lg2f(sum) : INFINITY;
+      // O of this tile: 16 of the 64 head columns per thread
+      mbar_wait_warp(o_ready, (uint32_t)(it & 1), lane);
+      tc_fence_after();
+      {
+        uint32_t ov[16], dummy[16];
+        tmem_ld16_nowait(lane_addr + kColO + part * kOC, ov);
+        tmem_ld16_nowait(lane_addr + kColO + part * kOC, dummy);
+        tmem_wait_ld_tied16(ov, dummy);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        if (qrow < g.T) {
+          __nv_bfloat16* dst = g.o + ((size_t)b * g.T + qrow) * g.E + head * DH + part * kOC;
+#pragma unroll
+          for (int j = 0; j < kOC; j += 8)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(
+                pack_bf16(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv),
+                pack_bf16(__uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv),
+                pack_bf16(__uint_as_float(ov[j + 4]) * inv, __uint_as_float(ov[j + 5]) * inv),
+                pack_bf16(__uint_as_float(ov[j + 6]) * inv, __uint_as_float(ov[j + 7]) * inv));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace g100
 }  // namespace mtts
 
@@ -434,5 +681,39 @@ extern "C" int mtts_attn_core_bwd(const mtts_attn_core_bwd_params* p, mtts_strea
   }
   attn_bwd_kernel<<<(unsigned)(B * H), attn::kThreads, attn::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
       mq, mdo, mo, mk, mv, a);
+  return mtts::launch_status();
+}
+
+extern "C" int mtts_attn_core_fwd(const mtts_attn_core_fwd_params* p, mtts_stream_t stream) {
+  using namespace mtts::g100;
+  if (!p || !p->q || !p->kv || !p->o || !p->lse2) return MTTS_ERR_NULL;
+  if (p->batch < 0 || p->heads < 1 || p->t_q < 0 || p->t_kv < 1 || p->t_kv > 256 || p->d_model != p->heads * attnf::DH)
+    return MTTS_ERR_SHAPE;
+  if (!(p->scale > 0.f)) return MTTS_ERR_UNSUPPORTED;
+  if (p->batch == 0 || p->t_q == 0) return MTTS_OK;
+  if (!mtts::aligned16(p->q) || !mtts::aligned16(p->kv) || !mtts::aligned16(p->o)) return MTTS_ERR_ALIGN;
+  const int64_t B = p->batch, H = p->heads, T = p->t_q, Tk = p->t_kv, E = p->d_model;
+  CUtensorMap mq, mk, mv;
+  const bool ok =
+      make_map(&mq, p->q, attnf::DH, T, E, H, attnf::DH, B, T * E, 64, 128) &&
+      make_map(&mk, p->kv, attnf::DH, Tk, 2 * E, H, attnf::DH, B, Tk * 2 * E, 64, 256) &&
+      make_map(&mv, reinterpret_cast<const unsigned char*>(p->kv) + 2 * E, attnf::DH, Tk, 2 * E, H, attnf::DH, B,
+               Tk * 2 * E, 64, 256);
+  if (!ok) return MTTS_ERR_UNSUPPORTED;
+  attnf::Args a{};
+  a.B = (int)B; a.H = (int)H; a.T = (int)T; a.Tk = (int)Tk; a.E = (int)E;
+  a.mask = p->mask;
+  a.o = reinterpret_cast<__nv_bfloat16*>(p->o);
+  a.lse2 = p->lse2;
+  a.scale = p->scale;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)attnf::kSmemBytes);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    configured = true;
+  }
+  attn_fwd_kernel<<<(unsigned)(B * H), attnf::kThreads, attnf::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+      mq, mk, mv, a);
   return mtts::launch_status();
 }

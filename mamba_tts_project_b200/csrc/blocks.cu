@@ -112,7 +112,7 @@ static int check_attn(const mtts_cross_attn_params* p, bool need_p) {
 }
 
 extern "C" int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_t stream) {
-  MTTS_TRY(check_attn(p, true));
+  MTTS_TRY(check_attn(p, !(p && p->lse2 != nullptr && p->d_model == p->heads * 64)));
   if (!p->out) return MTTS_ERR_NULL;
   if (p->batch == 0 || p->t_q == 0) return MTTS_OK;
   const int B = p->batch, T = p->t_q, Tk = p->t_kv, E = p->d_model, H = p->heads, dh = E / H;
@@ -126,23 +126,33 @@ extern "C" int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_
   gkv.A(p->memory, 0, E).B(at(p->w_in, (long long)E * E), 0, E).C(p->kv, 2 * E);
   gkv.bias_n = p->b_in + E;
   MTTS_TRY(mtts_gemm(&gkv, stream));
-  // P[b, h] = softmax(scale q_h k_h^T + mask): (batch, head) views of the projections, nothing is transposed
-  G gs(T, Tk, dh);
-  gs.batches(B, H)
-      .A(p->q, 0, E, (long long)T * E, dh)
-      .B(p->kv, 0, 2 * E, (long long)Tk * 2 * E, dh)
-      .C(p->p, Tkp, (long long)H * T * Tkp, (long long)T * Tkp);
-  gs.epilogue = MTTS_EPI_SOFTMAX; gs.mask = p->mask; gs.mask_bo_stride = Tk;
-  gs.scale = 1.f / std::sqrt((float)dh);
-  gs.row_stat = p->lse2;
-  MTTS_TRY(mtts_gemm(&gs, stream));
-  // o[b, :, h] = P[b, h] v_h: v read as B[n = dh, k = key] with n contiguous
-  G go(T, dh, Tk);
-  go.batches(B, H)
-      .A(p->p, 0, Tkp, (long long)H * T * Tkp, (long long)T * Tkp)
-      .B(at(p->kv, E), 1, 2 * E, (long long)Tk * 2 * E, dh)
-      .C(p->o, E, (long long)T * E, dh);
-  MTTS_TRY(mtts_gemm(&go, stream));
+  if (p->lse2 != nullptr && p->p == nullptr && E == H * 64) {
+    // scores, softmax and P V in one launch (attn_sm100.cu): only o and the row log-sum-exp reach memory
+    mtts_attn_core_fwd_params c;
+    std::memset(&c, 0, sizeof(c));
+    c.batch = B; c.heads = H; c.t_q = T; c.t_kv = Tk; c.d_model = E;
+    c.scale = 1.f / std::sqrt((float)dh);
+    c.q = p->q; c.kv = p->kv; c.mask = p->mask; c.o = p->o; c.lse2 = p->lse2;
+    MTTS_TRY(mtts_attn_core_fwd(&c, stream));
+  } else {
+    // P[b, h] = softmax(scale q_h k_h^T + mask): (batch, head) views of the projections, nothing is transposed
+    G gs(T, Tk, dh);
+    gs.batches(B, H)
+        .A(p->q, 0, E, (long long)T * E, dh)
+        .B(p->kv, 0, 2 * E, (long long)Tk * 2 * E, dh)
+        .C(p->p, Tkp, (long long)H * T * Tkp, (long long)T * Tkp);
+    gs.epilogue = MTTS_EPI_SOFTMAX; gs.mask = p->mask; gs.mask_bo_stride = Tk;
+    gs.scale = 1.f / std::sqrt((float)dh);
+    gs.row_stat = p->lse2;
+    MTTS_TRY(mtts_gemm(&gs, stream));
+    // o[b, :, h] = P[b, h] v_h: v read as B[n = dh, k = key] with n contiguous
+    G go(T, dh, Tk);
+    go.batches(B, H)
+        .A(p->p, 0, Tkp, (long long)H * T * Tkp, (long long)T * Tkp)
+        .B(at(p->kv, E), 1, 2 * E, (long long)Tk * 2 * E, dh)
+        .C(p->o, E, (long long)T * E, dh);
+    MTTS_TRY(mtts_gemm(&go, stream));
+  }
   G gout(B * T, E, E);
   gout.A(p->o, 0, E).B(p->w_out, 0, E).C(p->out, E);
   return mtts_gemm(&gout, stream);

@@ -182,7 +182,7 @@ class _CrossAttentionTC(torch.autograd.Function):
         fused = FUSED_ATTENTION_BACKWARD and E == heads * 64
         q = torch.empty((B, T, E), dtype=bf, device=dev)
         kv = torch.empty((B, Tk, 2 * E), dtype=bf, device=dev)
-        P = torch.empty((B, heads, T, tkp), dtype=bf, device=dev)
+        P = None if fused else torch.empty((B, heads, T, tkp), dtype=bf, device=dev)
         o = torch.empty((B, T, E), dtype=bf, device=dev)
         out = torch.empty((B, T, E), dtype=bf, device=dev)
         lse2 = torch.empty((B, heads, T), dtype=torch.float32, device=dev) if fused else None
@@ -190,7 +190,7 @@ class _CrossAttentionTC(torch.autograd.Function):
         p = _lib.CrossAttnParams(batch=B, t_q=T, t_kv=Tk, d_model=E, heads=heads, query=ptr(q_in), memory=ptr(m_in),
                                  w_in=ptr(wb), b_in=ptr(b32), w_out=ptr(wob), mask=ptr(mask), q=ptr(q), kv=ptr(kv),
                                  p=ptr(P), o=ptr(o), out=ptr(out), lse2=ptr(lse2))
-        _lib.call("mtts_cross_attn_fwd", p, launches=5)
+        _lib.call("mtts_cross_attn_fwd", p, launches=4 if fused else 5)
         if fused:
             ctx.save_for_backward(q_in, m_in, wb, wob, q, kv, lse2, o, mask)     # P dies here
         else:
