@@ -4,7 +4,7 @@
 //   given   q (B, T, E), k | v (B, Tk, 2E), o and d_o (B, T, E) bf16 (head h = columns [64 h, 64 h + 64)),
 //           lse2 (B, H, T) = base-2 log-sum-exp of every score row (the forward's softmax GEMM writes it)
 //   P  = exp2(scale log2(e) q k^T - lse2)   (masked / padded keys: 0)        delta = rowsum(d_o o)
-//   dS = scale P o (d_o v^T - delta)        dV = P^T d_o        dK = dS^T q        dQ = dS k
+//   dS = P o (d_o v^T - delta)        dV = P^T d_o        dK = scale dS^T q        dQ = scale dS k
 //
 // One CTA per (batch, head).  Everything is computed TRANSPOSED (keys on the TMEM lanes, queries along the columns):
 // with the row statistics of the forward at hand the softmax backward is elementwise, and with keys on the lanes the
@@ -298,7 +298,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 for (int j = 0; j < 4; ++j) {
                   const float pj = keep ? ex2f(fmaf(__uint_as_float(sv[j8 + j4 + j]), sc2, -lv[j])) : 0.f;
                   p[j4 + j] = pj;
-                  d[j4 + j] = scale * pj * (__uint_as_float(dv[j8 + j4 + j]) - ev[j]);
+                  d[j4 + j] = pj * (__uint_as_float(dv[j8 + j4 + j]) - ev[j]);   // (x scale: applied to dQ / dK)
                 }
               }
               const int chunk = ((((cbase & 63) + c + j8) >> 3) ^ (row & 7)) << 4;
@@ -341,7 +341,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int j = 0; j < kOC / 8; ++j) {
               float v[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[8 * j + q]);
+              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[8 * j + q]) * scale;
               if (h > 0) {
                 float old[8];
                 unpack_bf16x8(oldv[j], old);
@@ -368,10 +368,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < kOC; j += 8) {
             *reinterpret_cast<uint4*>(dk + j) = make_uint4(
-                pack_bf16(__uint_as_float(kv[j]), __uint_as_float(kv[j + 1])),
-                pack_bf16(__uint_as_float(kv[j + 2]), __uint_as_float(kv[j + 3])),
-                pack_bf16(__uint_as_float(kv[j + 4]), __uint_as_float(kv[j + 5])),
-                pack_bf16(__uint_as_float(kv[j + 6]), __uint_as_float(kv[j + 7])));
+                pack_bf16(__uint_as_float(kv[j]) * scale, __uint_as_float(kv[j + 1]) * scale),
+                pack_bf16(__uint_as_float(kv[j + 2]) * scale, __uint_as_float(kv[j + 3]) * scale),
+                pack_bf16(__uint_as_float(kv[j + 4]) * scale, __uint_as_float(kv[j + 5]) * scale),
+                pack_bf16(__uint_as_float(kv[j + 6]) * scale, __uint_as_float(kv[j + 7]) * scale));
             *reinterpret_cast<uint4*>(dvp + j) = make_uint4(
                 pack_bf16(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])),
                 pack_bf16(__uint_as_float(vv[j + 2]), __uint_as_float(vv[j + 3])),
@@ -552,10 +552,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_ld16_nowait(lane_addr + kColS + part * kSC + c + 16, bq);
         tmem_wait_ld_tied16(a, bq);
         const uint32_t kb = keep[c >> 5];
+        if (kb == 0xffffffffu) {               // warp-uniform: no masked / padded key among these 32
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if ((kb >> j) & 1u) m0 = fmaxf(m0, __uint_as_float(a[j]));
-          if ((kb >> (16 + j)) & 1u) m1 = fmaxf(m1, __uint_as_float(bq[j]));
+          for (int j = 0; j < 16; ++j) {
+            m0 = fmaxf(m0, __uint_as_float(a[j]));
+            m1 = fmaxf(m1, __uint_as_float(bq[j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if ((kb >> j) & 1u) m0 = fmaxf(m0, __uint_as_float(a[j]));
+            if ((kb >> (16 + j)) & 1u) m1 = fmaxf(m1, __uint_as_float(bq[j]));
+          }
         }
       }
       float mx = fmaxf(m0, m1);
@@ -574,10 +582,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_wait_ld_tied16(a, bq);
         const uint32_t kb = keep[c >> 5];
         float e[32];
+        if (kb == 0xffffffffu) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          e[j] = ((kb >> j) & 1u) ? ex2f(fmaf(__uint_as_float(a[j]), sc2, -base)) : 0.f;
-          e[16 + j] = ((kb >> (16 + j)) & 1u) ? ex2f(fmaf(__uint_as_float(bq[j]), sc2, -base)) : 0.f;
+          for (int j = 0; j < 16; ++j) {
+            e[j] = ex2f(fmaf(__uint_as_float(a[j]), sc2, -base));
+            e[16 + j] = ex2f(fmaf(__uint_as_float(bq[j]), sc2, -base));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            e[j] = ((kb >> j) & 1u) ? ex2f(fmaf(__uint_as_float(a[j]), sc2, -base)) : 0.f;
+            e[16 + j] = ((kb >> (16 + j)) & 1u) ? ex2f(fmaf(__uint_as_float(bq[j]), sc2, -base)) : 0.f;
+          }
         }
 #pragma unroll
         for (int j8 = 0; j8 < 32; j8 += 8) {
