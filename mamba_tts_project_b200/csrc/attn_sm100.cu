@@ -37,8 +37,8 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kTileBytes = 128 * 128;                 // a 128-row x 64-element bf16 operand tile
 constexpr uint32_t kStageBytes = 3 * kTileBytes;           // Q_i, dO_i, O_i
 // shared memory: K_h, V_h | 2 stages | P^T, dS^T (2 k-blocks each) | statistics [2][2][128] | barriers
-constexpr size_t kSmemBytes = 2 * kTileBytes + 2 * kStageBytes + 4 * kTileBytes + 2 * 2 * TQ * 4 + 16 * 8 + 16;
-constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+constexpr size_t kSmemBytes = 2 * kTileBytes + 2 * kStageBytes + 4 * kTileBytes + 2 * 2 * TQ * 4 + 24 * 8 + 16;
+constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;   // dQ: two buffers of 64 columns
 
 struct Args {
   int B, H, T, Tk, E;
@@ -99,12 +99,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* q_empty = bars + 4;     // [2]
   uint64_t* s_ready = bars + 6;
   uint64_t* p_ready = bars + 7;
-  uint64_t* dq_ready = bars + 8;
+  uint64_t* dq_ready = bars + 12;   // [2]: dQ is double buffered -- the warps read tile it - 1 after the elementwise
+                                    // work of tile it, so they never wait for the gradient MMAs
   uint64_t* sdp_free = bars + 9;    // the warps have read S^T / dP^T of the tile (they may be overwritten)
-  uint64_t* dq_free = bars + 12;    // ... and its dQ
+  uint64_t* dq_free = bars + 14;    // [2]
   uint64_t* kv_done = bars + 10;
   uint64_t* acc_free = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / g.H, head = blockIdx.x % g.H;
@@ -129,8 +130,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(s_ready, 1);
       mbar_init(p_ready, kEpiWarps);
       mbar_init(dq_ready, 1);
+      mbar_init(dq_ready + 1, 1);
       mbar_init(sdp_free, kEpiWarps);
       mbar_init(dq_free, kEpiWarps);
+      mbar_init(dq_free + 1, kEpiWarps);
       mbar_init(kv_done, 1);
       mbar_init(acc_free, kEpiWarps);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -201,7 +204,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t aQ = smem_u32(sStage + (size_t)s * kStageBytes), aDO = aQ + kTileBytes;
         if (i == 0) mbar_wait(acc_free, (uint32_t)((h & 1) ^ 1));   // the warps have read the previous half's dK / dV
         mbar_wait(p_ready, (uint32_t)(it & 1));
-        mbar_wait(dq_free, (uint32_t)((it & 1) ^ 1));            // dQ of the previous iteration was read
+        mbar_wait(dq_free + (it & 1), (uint32_t)(((it >> 1) & 1) ^ 1));   // this dQ buffer (tile it - 2) was read
         tc_fence_after();
         // contraction over the 128 queries of the tile: A k-block kb (64 q) at +16 KB, +32 B per 16 q inside it;
         // B (dO_i / Q_i read MN-major): +16 rows of 128 B per 16 q
@@ -219,10 +222,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // 128 B per step), B = K_h read MN-major
 #pragma unroll
         for (int k = 0; k < TKH / 16; ++k) {
-          tc_mma(tmem_base + kColDQ, umma_desc_lbo<1>(aDST + 2048 * k, kTileBytes), umma_desc<1>(aK + 2048 * k), id_nn,
+          tc_mma(tmem_base + kColDQ + 64 * (it & 1), umma_desc_lbo<1>(aDST + 2048 * k, kTileBytes), umma_desc<1>(aK + 2048 * k), id_nn,
                  k ? 1u : 0u);
         }
-        tc_commit(dq_ready);
+        tc_commit(dq_ready + (it & 1));
         tc_commit(q_empty + s);
         if (i == nq - 1) {                                       // last tile of the half
           tc_commit(kv_done);
@@ -240,6 +243,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int row = lg * 32 + lane;        // key row (S^T, dK, dV) or query row (dQ) of the tile
     const float sc2 = g.scale * kLog2e, scale = g.scale;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    // dQ of iteration jt (half jt / nq, tile jt % nq): query row `row`, kOC of the 64 head columns; the second half adds
+    // onto the first half's result, requested before the wait for the tensor core
+    auto dq_out = [&](int jt) {
+      const int hh = jt / nq, qrow = (jt - hh * nq) * TQ + row;
+      __nv_bfloat16* dst = g.dq + ((size_t)b * g.T + (qrow < g.T ? qrow : 0)) * g.E + head * DH + part * kOC;
+      uint4 oldv[kOC / 8];
+      if (hh > 0 && qrow < g.T) {
+#pragma unroll
+        for (int j = 0; j < kOC / 8; ++j) oldv[j] = *reinterpret_cast<const uint4*>(dst + 8 * j);
+      }
+      mbar_wait_warp(dq_ready + (jt & 1), (uint32_t)((jt >> 1) & 1), lane);
+      tc_fence_after();
+      uint32_t qv[16], dummy[16];
+      static_assert(kOC == 16, "dQ / dK / dV: 16 columns per thread");
+      tmem_ld16_nowait(lane_addr + kColDQ + 64 * (jt & 1) + part * kOC, qv);
+      tmem_ld16_nowait(lane_addr + kColDQ + 64 * (jt & 1) + part * kOC, dummy);
+      tmem_wait_ld_tied16(qv, dummy);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free + (jt & 1));
+      if (qrow < g.T) {
+#pragma unroll
+        for (int j = 0; j < kOC / 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[8 * j + q]) * scale;
+          if (hh > 0) {
+            float old[8];
+            unpack_bf16x8(oldv[j], old);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] += old[q];
+          }
+          *reinterpret_cast<uint4*>(dst + 8 * j) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+      }
+    };
+    float lse_next = (etid < TQ && etid < g.T) ? g.lse2[((size_t)b * g.H + head) * g.T + etid] : 0.f;
     int it = 0;
     for (int h = 0; h < nh; ++h) {
       const int key = h * TKH + row;
@@ -249,8 +290,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int q0 = i * TQ;
         float* stat = sStat + s * 2 * TQ;
         const unsigned char* st = sStage + (size_t)s * kStageBytes;
-        // (a) lse2 of the tile's 128 queries -> shared memory (one value per thread of the first four warps)
-        if (etid < TQ) stat[etid] = (q0 + etid < g.T) ? g.lse2[((size_t)b * g.H + head) * g.T + q0 + etid] : 0.f;
+        // (a) lse2 of the tile's 128 queries -> shared memory (one value per thread of the first four warps); the
+        // value was requested an iteration ago (a global load here would sit on the critical path of every tile)
+        if (etid < TQ) {
+          stat[etid] = lse_next;
+          const int qn = ((i + 1 < nq) ? (i + 1) : 0) * TQ + etid;       // next tile (or tile 0 of the next half)
+          lse_next = (qn < g.T) ? g.lse2[((size_t)b * g.H + head) * g.T + qn] : 0.f;
+        }
         // (b) delta = rowsum(dO o O) from the staged tiles: kParts threads per query row, 16-byte chunks dealt round robin
         mbar_wait_warp(q_full + s, (uint32_t)((it >> 1) & 1), lane);
         {
@@ -316,47 +362,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           mbar_arrive_release(p_ready);
           mbar_arrive(sdp_free);
         }
-        // (d) dQ of this tile for this half of the keys: query row `row`, kOC of the 64 head columns.  The second
-        // half adds onto the first half's result: that is requested before the wait for the tensor core.
-        {
-          const int qrow = q0 + row;
-          __nv_bfloat16* dst = g.dq + ((size_t)b * g.T + (qrow < g.T ? qrow : 0)) * g.E + head * DH + part * kOC;
-          uint4 oldv[kOC / 8];
-          if (h > 0 && qrow < g.T) {
-#pragma unroll
-            for (int j = 0; j < kOC / 8; ++j) oldv[j] = *reinterpret_cast<const uint4*>(dst + 8 * j);
-          }
-          mbar_wait_warp(dq_ready, (uint32_t)(it & 1), lane);
-          tc_fence_after();
-          uint32_t qv[16], dummy[16];
-          static_assert(kOC == 16, "dQ / dK / dV: 16 columns per thread");
-          tmem_ld16_nowait(lane_addr + kColDQ + part * kOC, qv);
-          tmem_ld16_nowait(lane_addr + kColDQ + part * kOC, dummy);
-          tmem_wait_ld_tied16(qv, dummy);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_free);
-          if (qrow < g.T) {
-#pragma unroll
-            for (int j = 0; j < kOC / 8; ++j) {
-              float v[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(qv[8 * j + q]) * scale;
-              if (h > 0) {
-                float old[8];
-                unpack_bf16x8(oldv[j], old);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] += old[q];
-              }
-              *reinterpret_cast<uint4*>(dst + 8 * j) =
-                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
-          }
-        }
+        // (d) dQ of the PREVIOUS tile (its MMAs were issued when this tile's S^T was being computed: long done)
+        if (i > 0) dq_out(it - 1);
       }
-      // dK_h, dV_h of this thread's key row
+      // dK_h, dV_h of this thread's key row (and the dQ of the half's last tile)
       mbar_wait_warp(kv_done, (uint32_t)(h & 1), lane);
       tc_fence_after();
+      dq_out(it - 1);
       {
         uint32_t kv[16], vv[16];
         tmem_ld16_nowait(lane_addr + kColDK + part * kOC, kv);
