@@ -275,3 +275,25 @@ def test_film_ffn_forward_with_fused_layernorm_film():
     assert rel_err(h, hr.view(-1, D)) < BF16_OUT
     ref = torch.nn.functional.gelu(h.float() @ w1.float().t() + b1) @ w2.float().t()
     assert rel_err(f, ref) < 2e-2
+
+
+def test_fused_attention_fully_masked_rows_and_memory():
+    """64-wide heads (fused mtts_attn_core_fwd / _bwd): a batch element whose keys are all masked gives zero attention
+    output and finite (zero) gradients through it -- the reference's nn.MultiheadAttention gives NaN there (SURVEY D3);
+    and the forward keeps no (B, H, T, T_kv) tensor for the backward."""
+    from mamba_tts_project_b200 import dense
+    B, T, Tk, E, H = 2, 200, 96, 128, 2
+    g = torch.Generator().manual_seed(9)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(torch.bfloat16).cuda()
+    query, memory = rnd(B, T, E).requires_grad_(), rnd(B, Tk, E).requires_grad_()
+    w_in, w_out = rnd(3 * E, E, sc=E ** -0.5).float().requires_grad_(), rnd(E, E, sc=E ** -0.5).float().requires_grad_()
+    b_in = torch.zeros(3 * E, device="cuda", requires_grad=True)
+    mask = torch.ones(B, Tk, dtype=torch.bool, device="cuda")
+    mask[1] = False
+    out = dense.cross_attention(query, memory, w_in, b_in, w_out, mask, H)
+    assert torch.count_nonzero(out[1]) == 0 and torch.isfinite(out).all()
+    saved = [t for t in out.grad_fn.saved_tensors if t is not None]
+    assert max(t.numel() for t in saved) <= max(B * T * E, B * Tk * 2 * E, 3 * E * E)   # no probability tensor
+    gq, gm = torch.autograd.grad(out, [query, memory], torch.ones_like(out))
+    assert torch.isfinite(gq).all() and torch.isfinite(gm).all()
+    assert torch.count_nonzero(gq[1]) == 0
