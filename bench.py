@@ -313,6 +313,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")   # the collective runs alone after the backward: use the SMs
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     cfg = C2
@@ -323,7 +324,9 @@ def run_ours(args):
     reducer = None
     if world > 1:
         broadcast_parameters(model)
-        reducer = GradAllReducer(model, bucket_bytes=32 << 20)
+        # the all-reduce follows the backward inside the graph: one bucket (fewer, larger NCCL launches), measured
+        # 34.65 -> 34.06 ms per step at N = 2 together with NCCL_MIN_NCHANNELS = 32 (set in run_ours below)
+        reducer = GradAllReducer(model, bucket_bytes=int(os.environ.get("MTTS_DP_BUCKET_MB", "512")) << 20)
     inp = make_inputs(cfg, B, dev, seed=rank)
 
     def barrier():
