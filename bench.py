@@ -340,7 +340,8 @@ def run_ours(args):
 
     # ---- device-timed region: inputs resident in HBM ----
     hook = {"mtts_selective_scan_fwd": [], "mtts_selective_scan_bwd": [],
-            "mtts_causal_conv1d_fwd": [], "mtts_causal_conv1d_bwd": []}
+            "mtts_causal_conv1d_fwd": [], "mtts_causal_conv1d_bwd": [],
+            "mtts_film_ffn_fwd": [], "mtts_film_ffn_bwd": [], "mtts_cross_attn_fwd": [], "mtts_cross_attn_bwd": []}
     _lib.event_hook = hook
     sampler = ClockSampler(local)
     sampler.start()
@@ -371,6 +372,25 @@ def run_ours(args):
            "mtts_selective_scan_bwd": scan_alg_bytes(B, Di, T, N, e, True),
            "mtts_causal_conv1d_fwd": conv_alg_bytes(B, Di, T, e, False),
            "mtts_causal_conv1d_bwd": conv_alg_bytes(B, Di, T, e, True)}
+    # the tensor-core branches (several mtts_gemm launches per call): FLOP/s against the measured dense bf16 throughput
+    tensor = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf_peak = json.load(f).get("bf16_tflops_sustained") or 1396.9
+    except Exception:
+        tf_peak = 1396.9
+    Dm, Fd, Tk_, rows = cfg["d_model"], cfg["d_ff"], cfg["t_text"], B * T
+    flops = {"mtts_film_ffn_fwd": 4 * rows * Dm * Fd, "mtts_film_ffn_bwd": 8 * rows * Dm * Fd,
+             # projections (q, o: rows x D x D; k | v: B Tk x 2D x D) + the two score-sized contractions per head
+             "mtts_cross_attn_fwd": 4 * rows * Dm * Dm + 4 * B * Tk_ * Dm * Dm + 4 * rows * Tk_ * Dm,
+             "mtts_cross_attn_bwd": 8 * rows * Dm * Dm + 8 * B * Tk_ * Dm * Dm + 10 * rows * Tk_ * Dm}
+    for name, fl in flops.items():
+        if kern.get(name):
+            tf = fl / kern[name] / 1e9
+            tensor[name] = {"bound": "tensor", "ms_per_call": round(kern[name], 4), "TFLOPs": round(tf, 1),
+                            "frac": round(tf / tf_peak, 4), "peak": tf_peak, "unit": "TFLOP/s",
+                            "share_of_step": round(kern[name] * (len(hook[name]) / args.steps) / ms, 4)}
+            del kern[name]
     dom = max(kern, key=lambda k: kern[k])
     traffic = None
     try:
@@ -393,7 +413,8 @@ def run_ours(args):
                 "others": {k: {"ms_per_launch": round(v, 4), "GBs": round(alg[k] / v / 1e6, 1),
                                "frac": round(alg[k] / v / 1e6 / peak, 4),
                                "share_of_step": round(v * (len(hook[k]) / args.steps) / ms, 4)}
-                           for k, v in kern.items() if k != dom}}
+                           for k, v in kern.items() if k != dom},
+                "tensor_core_branches": tensor}
 
     # ---- the reported step: forward + loss + backward captured ONCE in a CUDA graph and replayed
     # (mamba_tts_project_b200.GraphedForwardBackward).  Same kernels as the eager pass above, one graph launch
