@@ -4,7 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
 
-Workload at every N: BASELINE.json configs[1] ("C2"): 12-layer d_model 512 MambaTTSDecoder, bf16
+    python bench.py --workload c3|c5 [--decode-weak] ...     # the other multi-GPU configs of BASELINE.json
+
+Default workload at every N: BASELINE.json configs[1] ("C2"): 12-layer d_model 512 MambaTTSDecoder, bf16
 (fp32 master weights, bf16 activations/GEMMs, fp32 scan state), teacher-forced forward + backward,
 B = 16 per GPU, T_audio 2048, T_text 256, cross-attn + FiLM.  N > 1 is batch-sharded data
 parallelism (weak scaling: 16 samples per GPU) with a bucketed NCCL gradient all-reduce.
@@ -13,12 +15,14 @@ A "step" = forward + loss + backward (+ all-reduce) over one batch.
 Two timed passes per run, both over the same K steps after W warm-up steps:
   1. eager (one launch per kernel, all-reduce overlapped with backward): every call into the C-ABI library is
      bracketed by CUDA events -> per-kernel durations for `roofline` (config.eager_ms_per_step);
-  2. the reported one: forward + loss + backward replayed from a CUDA graph
-     (mamba_tts_project_b200.GraphedForwardBackward), then the all-reduce -> `value`, `ms_per_step`, and,
+  2. the reported one: forward + loss + backward (+ the gradient all-reduce, captured in the same graph) replayed from a
+     CUDA graph (mamba_tts_project_b200.GraphedForwardBackward) -> `value`, `ms_per_step`, and,
      with pinned host inputs copied in and loss.item() read back every step, `e2e`.
 
 One JSON line on stdout (rank 0).  Besides the contract keys it carries
-  roofline      the dominant hand-written kernel (selective-scan backward) against the measured HBM peak
+  roofline      the dominant hand-written kernel (selective-scan backward) against the measured HBM peak; `others` = the
+                other memory-bound kernels; `tensor_core_branches` = FLOP/s of the FFN / attention C-ABI calls (tcgen05
+                GEMM family + fused attention) against the measured sustained dense-bf16 throughput
   cpu_baseline  the CPU oracle (port of the reference path) timed on this box's host cores
   e2e           same metric through the public API with host (pinned) inputs copied in every step
   extra         the other two headline quantities of BASELINE.json's metric: isolated scan GB/s
