@@ -205,3 +205,22 @@ def test_preprocessed_reader_and_collate(tmp_path, parallel):
     assert batch["phoneme_ids"].shape == (2, 9) and batch["text_mask"].sum(1).tolist() == [5, 9]
     assert torch.equal(mt.unflatten_codes(batch["audio_tokens"], 5), want_3d)
     assert batch["style"].shape == (2, 16) and (batch["spk_emb"] is None) == parallel
+
+
+def test_film_terms_equal_the_per_layer_style_mlps():
+    """MambaTTSDecoder.film_terms stacks every layer's style_mlp (mamba_decoder.py:45-48,81-83) into one contraction:
+    pure host logic, the same (gamma, beta) as calling the layers' own Sequential(Linear, Tanh) one by one."""
+    import torch
+    from mamba_tts_project_b200 import MambaTTSDecoder
+    torch.manual_seed(0)
+    dec = MambaTTSDecoder(vocab_size_audio=32, d_model=48, n_layers=3, n_heads=4, d_ff=64, d_style=24, max_len=16)
+    z = torch.randn(5, 24)
+    films = dec.film_terms(z)
+    assert len(films) == 3
+    for layer, (gamma, beta) in zip(dec.layers, films):
+        g_ref, b_ref = torch.chunk(layer.style_mlp(z), 2, dim=-1)
+        assert gamma.is_contiguous() and beta.is_contiguous()
+        assert torch.allclose(gamma, g_ref, atol=1e-6) and torch.allclose(beta, b_ref, atol=1e-6)
+    # gradients reach every layer's own parameters through the stacked weight
+    sum(g.sum() + b.sum() for g, b in films).backward()
+    assert all(l.style_mlp[0].weight.grad is not None and l.style_mlp[0].bias.grad is not None for l in dec.layers)
