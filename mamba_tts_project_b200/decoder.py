@@ -28,9 +28,6 @@ from . import dense, ops
 from .mamba import Mamba, compute_dtype
 
 
-_DECODE_FUSED_GELU = os.environ.get("MTTS_DECODE_FUSED_GELU", "1") != "0"    # A/B switch (measurements)
-
-
 def _join_memory(text_hidden, text_mask, ref_hidden, ref_mask):
     """[ref || text] memory and validity mask (``mamba_decoder.py:148-165,226-241``); True = attend."""
     if ref_hidden is None:
@@ -368,12 +365,7 @@ class MambaTTSDecoder(nn.Module):
                 o = F.linear(a, lw.wo, lw.bo)
                 x, h = ops.add_layernorm(x, o, lw.ln3[0], lw.ln3[1], lw.ln3[2], gamma=lw.gamma,
                                          beta=lw.beta, out_dtype=dt, inplace=True)
-            if dt == torch.bfloat16 and lw.b1 is not None and _DECODE_FUSED_GELU:
-                # bias + GELU in the GEMM's epilogue (one launch instead of two; the tanh form, as on the bf16
-                # training path -- the fp32 path keeps the exact erf GELU of nn.GELU())
-                f = torch._addmm_activation(lw.b1, h, lw.w1.t(), use_gelu=True)
-            else:
-                f = F.gelu(F.linear(h, lw.w1, lw.b1))
+            f = F.gelu(F.linear(h, lw.w1, lw.b1))
             delta = F.linear(f, lw.w2, lw.b2)
         _, h = ops.add_layernorm(x, delta, ctx.ln_out[0], ctx.ln_out[1], ctx.ln_out[2], out_dtype=dt,
                                  inplace=True)
