@@ -411,7 +411,8 @@ typedef struct {
 } mtts_add_layernorm_bwd_params;
 int mtts_add_layernorm_bwd(const mtts_add_layernorm_bwd_params* p, mtts_stream_t stream);
 
-/* The (batch, dim)-sized finishing step of a FiLM'd add_layernorm_bwd in one launch: from colsum (batch, 3, dim)
+/* The (batch, dim)-sized finishing step of a FiLM'd add_layernorm_bwd (norm_ff + gamma / beta, mamba_decoder.py:81-86)
+ * in one launch: from colsum (batch, 3, dim)
  *   dweight = sum_b gamma_b S1_b,  dbias = sum_b gamma_b S2_b,  dgamma_b = w S1_b + bias S2_b,  dbeta_b = S2_b,
  *   ddelta_bias = sum_b S3_b (optional).  All fp32, all overwritten. */
 typedef struct {
@@ -656,7 +657,8 @@ int mtts_cross_attn_fwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
 int mtts_cross_attn_bwd(const mtts_cross_attn_params* p, mtts_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * attn_core_bwd -- the backward of softmax(scale q k^T + mask) v for all heads in ONE launch, with the score-sized
+ * attn_core_bwd -- the backward of softmax(scale q k^T + mask) v (the inside of nn.MultiheadAttention,
+ * mamba_decoder.py:32-36,72-77, under loss.backward(), train.py:231) for all heads in ONE launch, with the score-sized
  * tensors (P, dP, dS) kept on the SM (tensor memory / shared memory): given the forward's per-row base-2
  * log-sum-exp (mtts_gemm's row_stat), o and d_o, it produces dq and dk | dv.  head_dim = 64 (d_model = 64 heads),
  * t_kv <= 256; q, o, d_o, dq (batch, t_q, d_model), kv, dkv (batch, t_kv, 2 d_model) bf16 contiguous; lse2
@@ -677,7 +679,7 @@ typedef struct {
 } mtts_attn_core_bwd_params;
 int mtts_attn_core_bwd(const mtts_attn_core_bwd_params* p, mtts_stream_t stream);
 
-/* The forward of the same core in one launch: o = softmax(scale q k^T + mask) v (bf16, (batch, t_q, d_model)) and
+/* The forward of the same core (mamba_decoder.py:72-77) in one launch: o = softmax(scale q k^T + mask) v (bf16, (batch, t_q, d_model)) and
  * lse2 (batch, heads, t_q) fp32, the scores and probabilities kept in tensor / shared memory.  Same shape limits.
  * Used by mtts_cross_attn_fwd when the caller gives lse2 and no probability buffer. */
 typedef struct {
