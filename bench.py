@@ -435,6 +435,15 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         graphed_step(inp)
+    if os.environ.get("MTTS_BENCH_PROFILE"):
+        # ncu --profile-from-start off --metrics gpu__time_duration.sum ... python bench.py: the launch list of ONE
+        # replayed step of this very command (profiles/r2_bench_step_launches.*); numbers printed by such a run are
+        # not bench values
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        graphed_step(inp)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
